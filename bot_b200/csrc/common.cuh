@@ -1,0 +1,175 @@
+// Shared host/device helpers for libbotgat (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "botgat.h"
+
+namespace botgat {
+
+void set_error(const char* fmt, ...);
+
+#define BG_CHECK(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      ::botgat::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return -2;                                                                        \
+    }                                                                                   \
+  } while (0)
+
+#define BG_REQUIRE(cond, ...)            \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::botgat::set_error(__VA_ARGS__);  \
+      return -1;                         \
+    }                                    \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (dev != prev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur;
+    cudaGetDevice(&cur);
+    if (cur != prev && prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace botgat
+
+// The opaque graph handle.  Immutable after create.
+struct botgat_graph {
+  int device = 0;
+  int sm_count = 148;
+  int64_t n_src = 0, n_dst = 0, n_edges = 0;
+  int64_t max_in_deg = 0, max_out_deg = 0;
+  int has_zero_in_degree = 0;
+  int32_t *in_indptr = nullptr, *in_indices = nullptr, *in_eid = nullptr;
+  int32_t *out_indptr = nullptr, *out_indices = nullptr, *out_eid = nullptr;
+  int32_t *in_deg = nullptr, *out_deg = nullptr;
+};
+
+namespace botgat {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float leaky_relu(float z, float slope) { return z > 0.f ? z : z * slope; }
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// Philox4x32-10 keyed on (seed), counter (eid, head>>2); component head&3.
+// Used for the in-kernel ("fast") attention dropout; reproducible from
+// (seed, edge id, head) so forward and both backward passes agree.
+__device__ __forceinline__ uint32_t philox_u32(uint64_t seed, uint32_t eid, uint32_t head) {
+  uint32_t c0 = eid, c1 = head >> 2, c2 = 0x9E3779B9u, c3 = 0xBB67AE85u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  uint32_t sel = head & 3u;
+  return sel == 0 ? c0 : sel == 1 ? c1 : sel == 2 ? c2 : c3;
+}
+// multiplier 0 or 1/(1-p); keep iff u >= p with u = (x >> 8) * 2^-24
+__device__ __forceinline__ float philox_dropout_mul(uint64_t seed, uint32_t eid, uint32_t head, float p, float inv_keep) {
+  float u = (float)(philox_u32(seed, eid, head) >> 8) * (1.0f / 16777216.0f);
+  return u >= p ? inv_keep : 0.f;
+}
+
+// ---------------------------------------------------------------------------
+// VW-wide vectors (VW = 4, 2, 1 floats) with read-only global loads
+// ---------------------------------------------------------------------------
+template <int VW> struct Vec;
+template <> struct Vec<4> {
+  float4 v;
+  __device__ __forceinline__ void load(const float* p) { v = __ldg(reinterpret_cast<const float4*>(p)); }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
+  __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void fma(float w, const Vec& o) {
+    v.x = fmaf(w, o.v.x, v.x); v.y = fmaf(w, o.v.y, v.y); v.z = fmaf(w, o.v.z, v.z); v.w = fmaf(w, o.v.w, v.w);
+  }
+  __device__ __forceinline__ float dot(const Vec& o, float acc) const {
+    acc = fmaf(v.x, o.v.x, acc); acc = fmaf(v.y, o.v.y, acc); acc = fmaf(v.z, o.v.z, acc); acc = fmaf(v.w, o.v.w, acc);
+    return acc;
+  }
+  __device__ __forceinline__ void scale(float s) { v.x *= s; v.y *= s; v.z *= s; v.w *= s; }
+  __device__ __forceinline__ void add_shfl_xor(int o) {
+    v.x += __shfl_xor_sync(kFull, v.x, o); v.y += __shfl_xor_sync(kFull, v.y, o);
+    v.z += __shfl_xor_sync(kFull, v.z, o); v.w += __shfl_xor_sync(kFull, v.w, o);
+  }
+};
+template <> struct Vec<2> {
+  float2 v;
+  __device__ __forceinline__ void load(const float* p) { v = __ldg(reinterpret_cast<const float2*>(p)); }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float2*>(p) = v; }
+  __device__ __forceinline__ void zero() { v = make_float2(0.f, 0.f); }
+  __device__ __forceinline__ void fma(float w, const Vec& o) { v.x = fmaf(w, o.v.x, v.x); v.y = fmaf(w, o.v.y, v.y); }
+  __device__ __forceinline__ float dot(const Vec& o, float acc) const {
+    acc = fmaf(v.x, o.v.x, acc); acc = fmaf(v.y, o.v.y, acc);
+    return acc;
+  }
+  __device__ __forceinline__ void scale(float s) { v.x *= s; v.y *= s; }
+  __device__ __forceinline__ void add_shfl_xor(int o) {
+    v.x += __shfl_xor_sync(kFull, v.x, o); v.y += __shfl_xor_sync(kFull, v.y, o);
+  }
+};
+template <> struct Vec<1> {
+  float v;
+  __device__ __forceinline__ void load(const float* p) { v = __ldg(p); }
+  __device__ __forceinline__ void store(float* p) const { *p = v; }
+  __device__ __forceinline__ void zero() { v = 0.f; }
+  __device__ __forceinline__ void fma(float w, const Vec& o) { v = fmaf(w, o.v, v); }
+  __device__ __forceinline__ float dot(const Vec& o, float acc) const { return fmaf(v, o.v, acc); }
+  __device__ __forceinline__ void scale(float s) { v *= s; }
+  __device__ __forceinline__ void add_shfl_xor(int o) { v += __shfl_xor_sync(kFull, v, o); }
+};
+
+// ---------------------------------------------------------------------------
+// Work decomposition shared by forward and both backward passes.
+//
+// A work item is (head h, column part cp, CSR row r) and is owned by one warp.
+// Items are ordered head-major, then column part, then row, so that all warps
+// resident at one time gather from the same (N x part_cols) slab of the feature
+// table — a slab is sized to stay L2-resident (DESIGN.md "Slabs").
+//
+// Inside the warp, a group of G = 1<<gshift lanes serves one neighbour; lane j of
+// the group owns vectors j, j+G, j+2G, ... (VPL of them, VW floats each) of the
+// slab row, so one warp instruction covers 32/G neighbours and each group reads
+// G*VW*4 contiguous bytes.
+// ---------------------------------------------------------------------------
+struct Tiling {
+  int vw;         // floats per vector (4, 2 or 1)
+  int vpl;        // vectors per lane
+  int gshift;     // log2(lanes per neighbour)
+  int col_parts;  // parts per head
+  int part_cols;  // floats per part (last part may be shorter)
+};
+
+// host: choose the tiling for a (D, ld, alignment) combination
+Tiling choose_tiling(int D, int64_t ld_a, int64_t ld_b, const void* pa, const void* pb, int col_parts_req,
+                     int64_t n_rows_table, int vpl_cap);
+
+}  // namespace botgat

@@ -1,0 +1,196 @@
+// Fused GAT forward for sm_100a:
+//   per-edge logits (el[src] + er[dst] + eb[edge]) -> leaky_relu -> online
+//   per-destination softmax -> attention dropout -> weighted neighbour sum ->
+//   degree scaling, in ONE pass over the in-CSR.  No E-sized intermediate is
+//   written.  Replaces src/no-sampling/models.py:500-505,523-555 and
+//   src/ogbn-proteins/models.py:125-156 of the reference (DGL apply_edges,
+//   edge_softmax, update_all and the torch elementwise ops between them).
+//
+// HBM/L2-bound gather: no tensor cores (the only dense contraction, fc, stays a
+// torch matmul).  See common.cuh "Work decomposition" for the item/lane layout.
+#include "common.cuh"
+
+namespace botgat {
+
+struct FwdParams {
+  const int32_t* indptr;
+  const int32_t* indices;
+  const int32_t* eid;
+  int n_rows;
+  int64_t n_edges;
+  int H, D;
+  int64_t ld_ft, ld_out;
+  const float *ft, *el, *er, *eb, *am, *cs, *ds;
+  int Hb;
+  float slope, attn_p, inv_keep;
+  uint64_t seed;
+  float *out, *row_max, *row_sum;
+  int col_parts, part_cols, gshift;
+  int blocks_per_slab;
+};
+
+template <int VW, int VPL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) gat_fwd_kernel(const FwdParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slab = blockIdx.x / p.blocks_per_slab;
+  const int row = (blockIdx.x - slab * p.blocks_per_slab) * kWarpsPerBlock + warp;
+  if (row >= p.n_rows) return;
+  const int h = slab / p.col_parts;
+  const int cp = slab - h * p.col_parts;
+  const int c0 = cp * p.part_cols;
+  const int ncols = min(p.D - c0, p.part_cols);
+
+  const int G = 1 << p.gshift;
+  const int j = lane & (G - 1);
+  const int grp = lane >> p.gshift;
+  const int EPS = 32 >> p.gshift;  // neighbours per warp step
+  const int gstride = G * VW;      // floats between a lane's consecutive vectors
+
+  bool act[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) act[i] = (i * G + j) * VW < ncols;
+
+  const int beg = p.indptr[row], end = p.indptr[row + 1];
+  const float er_v = p.er ? p.er[(int64_t)row * p.H + h] : 0.f;
+  const float* __restrict__ ft_h = p.ft + h * p.D + c0 + j * VW;
+  const float* __restrict__ eb_h = p.eb ? p.eb + (int64_t)(p.Hb == 1 ? 0 : h) * p.n_edges : nullptr;
+  const float* __restrict__ am_h = p.am ? p.am + (int64_t)h * p.n_edges : nullptr;
+  const bool philox = (p.am == nullptr) && p.attn_p > 0.f;
+
+  Vec<VW> acc[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) acc[i].zero();
+  float m = -INFINITY;  // running row max (warp-uniform)
+  float l_lane = 0.f;   // this lane's share of sum exp(s - m)
+
+  for (int base = beg; base < end; base += 32) {
+    const int cnt = min(32, end - base);
+    // ---- lane = neighbour: logit, leaky_relu, multiplier ----
+    int u = 0;
+    float s = -INFINITY, mul = 1.f;
+    if (lane < cnt) {
+      const int pos = base + lane;
+      u = __ldg(p.indices + pos);
+      float z = __ldg(p.el + (int64_t)u * p.H + h) + er_v;
+      if (eb_h) z += __ldg(eb_h + pos);
+      s = leaky_relu(z, p.slope);
+      if (p.cs) mul = __ldg(p.cs + u);
+      if (am_h) mul *= __ldg(am_h + pos);
+      else if (philox) mul *= philox_dropout_mul(p.seed, (uint32_t)__ldg(p.eid + pos), (uint32_t)h, p.attn_p, p.inv_keep);
+    }
+    // ---- online softmax: rescale what has been accumulated if the max moved ----
+    const float m_new = fmaxf(m, warp_max(s));
+    if (m_new > m) {
+      const float f = expf(m - m_new);  // m == -inf -> 0, and everything accumulated so far is 0
+      l_lane *= f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) acc[i].scale(f);
+      m = m_new;
+    }
+    const float pexp = (s == -INFINITY) ? 0.f : expf(s - m);
+    l_lane += pexp;
+    const float w_lane = pexp * mul;
+
+    // ---- group = neighbour: gather slab rows, acc += w * row ----
+    for (int e = 0; e < cnt; e += 2 * EPS) {
+      const int my0 = e + grp, my1 = e + EPS + grp;
+      const int u0 = __shfl_sync(kFull, u, my0 & 31);
+      const float w0 = __shfl_sync(kFull, w_lane, my0 & 31);
+      const int u1 = __shfl_sync(kFull, u, my1 & 31);
+      const float w1 = __shfl_sync(kFull, w_lane, my1 & 31);
+      const bool ok0 = my0 < cnt, ok1 = my1 < cnt;
+      const float* r0 = ft_h + (int64_t)u0 * p.ld_ft;
+      const float* r1 = ft_h + (int64_t)u1 * p.ld_ft;
+      Vec<VW> x0[VPL], x1[VPL];
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        if (ok0 && act[i]) x0[i].load(r0 + i * gstride); else x0[i].zero();
+      }
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        if (ok1 && act[i]) x1[i].load(r1 + i * gstride); else x1[i].zero();
+      }
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) acc[i].fma(ok0 ? w0 : 0.f, x0[i]);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) acc[i].fma(ok1 ? w1 : 0.f, x1[i]);
+    }
+  }
+
+  // ---- epilogue: combine the groups, normalise, degree-scale, store ----
+  const float l = warp_sum(l_lane);
+  for (int o = G; o < 32; o <<= 1) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) acc[i].add_shfl_xor(o);
+  }
+  float scale = l > 0.f ? 1.f / l : 0.f;
+  if (p.ds) scale *= p.ds[row];
+  if (grp == 0) {
+    float* o = p.out + (int64_t)row * p.ld_out + h * p.D + c0 + j * VW;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      if (act[i]) {
+        acc[i].scale(scale);
+        acc[i].store(o + i * gstride);
+      }
+    }
+  }
+  if (cp == 0 && lane == 0) {
+    p.row_max[(int64_t)row * p.H + h] = m;
+    p.row_sum[(int64_t)row * p.H + h] = l;
+  }
+}
+
+template <int VW>
+static int launch_fwd_vw(const FwdParams& p, int vpl, dim3 grid, cudaStream_t st) {
+  dim3 block(kWarpsPerBlock * 32);
+  switch (vpl) {
+    case 1: gat_fwd_kernel<VW, 1><<<grid, block, 0, st>>>(p); break;
+    case 2: gat_fwd_kernel<VW, 2><<<grid, block, 0, st>>>(p); break;
+    case 3: gat_fwd_kernel<VW, 3><<<grid, block, 0, st>>>(p); break;
+    case 4: gat_fwd_kernel<VW, 4><<<grid, block, 0, st>>>(p); break;
+    case 5: gat_fwd_kernel<VW, 5><<<grid, block, 0, st>>>(p); break;
+    case 6: gat_fwd_kernel<VW, 6><<<grid, block, 0, st>>>(p); break;
+    case 8: gat_fwd_kernel<VW, 8><<<grid, block, 0, st>>>(p); break;
+    default: set_error("forward: unsupported vectors-per-lane %d", vpl); return -1;
+  }
+  return 0;
+}
+
+}  // namespace botgat
+
+using namespace botgat;
+
+extern "C" int botgat_gat_forward(const botgat_graph* g, const botgat_fwd_args* a, void* stream) {
+  BG_REQUIRE(g && a, "forward: null graph/args");
+  BG_REQUIRE(a->H > 0 && a->D > 0, "forward: bad H=%d D=%d", a->H, a->D);
+  BG_REQUIRE(a->ft && a->el && a->out && a->row_max && a->row_sum, "forward: null ft/el/out/row_max/row_sum");
+  BG_REQUIRE(a->ld_ft >= (int64_t)a->H * a->D && a->ld_out >= (int64_t)a->H * a->D, "forward: leading dimension < H*D");
+  BG_REQUIRE(a->eb ? (a->Hb == 1 || a->Hb == a->H) : true, "forward: Hb must be 1 or H when eb is given (got %d)", a->Hb);
+  BG_REQUIRE(a->attn_p >= 0.f && a->attn_p < 1.f, "forward: attn_p must be in [0,1)");
+  if (g->n_dst == 0) return 0;
+  DeviceGuard guard(g->device);
+  cudaStream_t st = (cudaStream_t)stream;
+
+  Tiling t = choose_tiling(a->D, a->ld_ft, a->ld_out, a->ft, a->out, a->col_parts, g->n_src, 8);
+  FwdParams p;
+  p.indptr = g->in_indptr; p.indices = g->in_indices; p.eid = g->in_eid;
+  p.n_rows = (int)g->n_dst; p.n_edges = g->n_edges;
+  p.H = a->H; p.D = a->D; p.ld_ft = a->ld_ft; p.ld_out = a->ld_out;
+  p.ft = a->ft; p.el = a->el; p.er = a->er; p.eb = a->eb; p.am = a->am;
+  p.cs = a->src_scale; p.ds = a->dst_scale; p.Hb = a->Hb;
+  p.slope = a->slope; p.attn_p = a->attn_p; p.inv_keep = 1.f / (1.f - a->attn_p); p.seed = a->seed;
+  p.out = a->out; p.row_max = a->row_max; p.row_sum = a->row_sum;
+  p.col_parts = t.col_parts; p.part_cols = t.part_cols; p.gshift = t.gshift;
+  p.blocks_per_slab = (p.n_rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const int64_t nblocks = (int64_t)p.blocks_per_slab * a->H * t.col_parts;
+  BG_REQUIRE(nblocks < (1ll << 31), "forward: grid too large");
+  dim3 grid((unsigned)nblocks);
+  int rc;
+  if (t.vw == 4) rc = launch_fwd_vw<4>(p, t.vpl, grid, st);
+  else if (t.vw == 2) rc = launch_fwd_vw<2>(p, t.vpl, grid, st);
+  else rc = launch_fwd_vw<1>(p, t.vpl, grid, st);
+  if (rc) return rc;
+  BG_CHECK(cudaGetLastError());
+  return 0;
+}

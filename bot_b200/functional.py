@@ -1,0 +1,160 @@
+"""``GATFusedFn`` — the autograd seam between BoT's GATConv modules and libbotgat.
+
+One call replaces, for a whole layer, the DGL/torch op sequence of
+src/no-sampling/models.py:500-505,523-555 and src/ogbn-proteins/models.py:125-156
+(SDDMM -> leaky_relu -> [edge-drop] edge_softmax -> attention dropout -> SpMM ->
+degree scaling) and, in backward, the autograd replay of their adjoints.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .graph import Graph, _stream
+
+
+def _f32c(t, name):
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name}: expected float32, got {t.dtype}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: bot_b200 has no CPU path — tensor must be on a CUDA device")
+    return t.contiguous()
+
+
+def edge_stage(graph: Graph, order, H, ee=None, keep=None, attn_mul=None):
+    """Permute per-edge operands from edge-id order to CSR order, head-major
+    (``botgat_edge_stage``).  Returns (eb, Hb, am)."""
+    E = graph.number_of_edges()
+    dev = graph.device
+    eb = am = None
+    Hb = 0
+    if ee is not None or keep is not None:
+        Hb = H if ee is not None else 1
+        eb = torch.empty((Hb, E), dtype=torch.float32, device=dev)
+    if attn_mul is not None:
+        am = torch.empty((H, E), dtype=torch.float32, device=dev)
+    if eb is None and am is None:
+        return None, 0, None
+    rc = _lib.load().botgat_edge_stage(graph._ensure(), order, H, _lib.ptr(ee), _lib.ptr(keep), _lib.ptr(attn_mul),
+                                       _lib.ptr(eb), _lib.ptr(am), _stream())
+    _lib.check(rc, "botgat_edge_stage")
+    return eb, Hb, am
+
+
+class GATFusedFn(torch.autograd.Function):
+    """out = dst_scale * sum_k softmax_v(leaky_relu(el[u]+er[v]+ee[k]))*attn_mul[k] * src_scale[u] * ft[u].
+
+    Arguments (tensors float32 on the graph's CUDA device):
+      graph      bot_b200.Graph
+      ft         (N_s,H,D)  projected source features, unscaled
+      el         (N_s,H)    er (N_d,H)|None    ee (E,H)|None (edge-id order)
+      keep       (E,) bool/uint8 | None   edge-drop keep set (edge-id order)
+      attn_mul   (E,H) | None   explicit attention-dropout multiplier (edge-id order)
+      src_scale  (N_s,)|None   dst_scale (N_d,)|None
+      slope      leaky_relu slope
+      attn_p, seed   in-kernel Philox attention dropout (used when attn_mul is None and attn_p > 0)
+    """
+
+    @staticmethod
+    def forward(ctx, graph, ft, el, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed):
+        lib = _lib.load()
+        h = graph._ensure()
+        if ft.dim() != 3:
+            raise ValueError("ft must be (N_src, H, D)")
+        ft = _f32c(ft, "ft")
+        N_s, H, D = ft.shape
+        N_d, E = graph.number_of_dst_nodes(), graph.number_of_edges()
+        if N_s != graph.number_of_src_nodes():
+            raise ValueError(f"ft has {N_s} rows, graph has {graph.number_of_src_nodes()} source nodes")
+        el = _f32c(el, "el").view(N_s, H)
+        er = None if er is None else _f32c(er, "er").view(N_d, H)
+        ee = None if ee is None else _f32c(ee, "ee").view(E, H)
+        attn_mul = None if attn_mul is None else _f32c(attn_mul, "attn_mul").view(E, H)
+        if keep is not None:
+            keep = keep.to(torch.uint8).contiguous()
+            if keep.numel() != E:
+                raise ValueError("keep must have one entry per edge")
+        src_scale, dst_scale = _f32c(src_scale, "src_scale"), _f32c(dst_scale, "dst_scale")
+
+        with torch.cuda.device(ft.device):
+            eb_in, Hb, am_in = edge_stage(graph, _lib.ORDER_IN, H, ee, keep, attn_mul)
+            out = torch.empty((N_d, H, D), dtype=torch.float32, device=ft.device)
+            row_max = torch.empty((N_d, H), dtype=torch.float32, device=ft.device)
+            row_sum = torch.empty((N_d, H), dtype=torch.float32, device=ft.device)
+            a = _lib.FwdArgs()
+            a.H, a.D, a.ld_ft, a.ld_out = H, D, H * D, H * D
+            a.ft, a.el, a.er = ft.data_ptr(), el.data_ptr(), (er.data_ptr() if er is not None else None)
+            a.eb, a.Hb, a.col_parts = (eb_in.data_ptr() if eb_in is not None else None), Hb, 0
+            a.am = am_in.data_ptr() if am_in is not None else None
+            a.src_scale = src_scale.data_ptr() if src_scale is not None else None
+            a.dst_scale = dst_scale.data_ptr() if dst_scale is not None else None
+            a.slope, a.attn_p, a.seed = float(slope), float(attn_p if attn_mul is None else 0.0), int(seed)
+            a.out, a.row_max, a.row_sum = out.data_ptr(), row_max.data_ptr(), row_sum.data_ptr()
+            _lib.check(lib.botgat_gat_forward(h, C.byref(a), _stream()), "botgat_gat_forward")
+
+        ctx.graph = graph
+        ctx.cfg = (H, D, Hb, float(slope), float(a.attn_p), int(seed))
+        ctx.has = (er is not None, ee is not None, keep is not None, attn_mul is not None)
+        ctx.save_for_backward(ft, el, er, ee, keep, attn_mul, src_scale, dst_scale, out, row_max, row_sum, eb_in, am_in)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _lib.load()
+        graph = ctx.graph
+        h = graph._ensure()
+        ft, el, er, ee, keep, attn_mul, src_scale, dst_scale, out, row_max, row_sum, eb_in, am_in = ctx.saved_tensors
+        H, D, Hb, slope, attn_p, seed = ctx.cfg
+        N_s, N_d, E = ft.shape[0], out.shape[0], graph.number_of_edges()
+        dev = ft.device
+        need_er = er is not None and ctx.needs_input_grad[3]
+        need_ee = ee is not None and ctx.needs_input_grad[4]
+        gout = _f32c(gout, "grad_out")
+
+        with torch.cuda.device(dev):
+            eb_out, _, am_out = edge_stage(graph, _lib.ORDER_OUT, H, ee, keep, attn_mul)
+            drec = torch.empty((H, N_d, 4), dtype=torch.float32, device=dev)
+            gprime = torch.empty_like(gout) if dst_scale is not None else None
+            grad_ft = torch.empty_like(ft)
+            grad_el = torch.empty((N_s, H), dtype=torch.float32, device=dev)
+            grad_er = torch.empty((N_d, H), dtype=torch.float32, device=dev) if need_er else None
+            gz = torch.empty((H, E), dtype=torch.float32, device=dev) if need_ee else None
+            a = _lib.BwdArgs()
+            a.H, a.D, a.ld_ft, a.ld_out, a.ld_gft = H, D, H * D, H * D, H * D
+            a.ft, a.el = ft.data_ptr(), el.data_ptr()
+            a.er = er.data_ptr() if er is not None else None
+            a.eb_in = eb_in.data_ptr() if eb_in is not None else None
+            a.eb_out = eb_out.data_ptr() if eb_out is not None else None
+            a.Hb, a.col_parts = Hb, 1
+            a.am_in = am_in.data_ptr() if am_in is not None else None
+            a.am_out = am_out.data_ptr() if am_out is not None else None
+            a.src_scale = src_scale.data_ptr() if src_scale is not None else None
+            a.dst_scale = dst_scale.data_ptr() if dst_scale is not None else None
+            a.slope, a.attn_p, a.seed = slope, attn_p, seed
+            a.out, a.row_max, a.row_sum, a.gout = out.data_ptr(), row_max.data_ptr(), row_sum.data_ptr(), gout.data_ptr()
+            a.drec = drec.data_ptr()
+            a.gprime = gprime.data_ptr() if gprime is not None else None
+            a.grad_ft, a.grad_el = grad_ft.data_ptr(), grad_el.data_ptr()
+            a.grad_er = grad_er.data_ptr() if grad_er is not None else None
+            a.gz = gz.data_ptr() if gz is not None else None
+            _lib.check(lib.botgat_gat_backward(h, C.byref(a), _stream()), "botgat_gat_backward")
+            grad_ee = None
+            if need_ee:
+                grad_ee = torch.empty((E, H), dtype=torch.float32, device=dev)
+                _lib.check(lib.botgat_edge_unstage(h, H, gz.data_ptr(), grad_ee.data_ptr(), _stream()), "botgat_edge_unstage")
+        return None, grad_ft, grad_el, grad_er, grad_ee, None, None, None, None, None, None, None
+
+
+def gat_fused(graph, ft, el, er=None, ee=None, keep=None, attn_mul=None, src_scale=None, dst_scale=None,
+              slope=0.2, attn_p=0.0, seed=0):
+    """Functional form of :class:`GATFusedFn` (accepts the reference's trailing-1 shapes, e.g. el (N,H,1))."""
+    H = ft.shape[1]
+    el = el.reshape(-1, H)
+    er = None if er is None else er.reshape(-1, H)
+    ee = None if ee is None else ee.reshape(-1, H)
+    attn_mul = None if attn_mul is None else attn_mul.reshape(-1, H)
+    return GATFusedFn.apply(graph, ft, el, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed)

@@ -1,0 +1,253 @@
+"""Graph object for the GAT engine: the DGLGraph subset BoT's GATConv touches.
+
+Mirrors the protocol listed in SURVEY.md section 8b: ``local_scope()``,
+``in_degrees()``, ``out_degrees()``, ``is_block``, ``number_of_*()``, ``device``,
+dict-like ``srcdata/dstdata/ndata/edata``, ``to()``, ``remove_self_loop()``,
+``add_self_loop()``, ``create_formats_()`` (reference call sites:
+src/no-sampling/run.py:133-148, src/no-sampling/models.py:476-555,
+src/ogbn-proteins/gat.py:54-68, src/ogbn-proteins/models.py:88-156).
+
+Structure (in-CSR / out-CSR / edge-id maps / degree tables) is built on the GPU by
+``libbotgat.so`` (``botgat_graph_create``); this module never computes it on the
+host.
+"""
+from __future__ import annotations
+
+import contextlib
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: bot_b200 has no CPU path — move the graph to a CUDA device first (graph.to('cuda'))")
+
+
+class _DevArray:
+    """int32 device array exposed through ``__cuda_array_interface__``."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, True), "version": 2}
+
+
+class Graph:
+    """Homogeneous graph or bipartite block (``is_block=True``: dst nodes are the
+    first ``num_dst_nodes`` src nodes, as in DGL message-flow blocks)."""
+
+    def __init__(self, src, dst, num_src_nodes=None, num_dst_nodes=None, is_block=False):
+        src = torch.as_tensor(src, dtype=torch.int64)
+        dst = torch.as_tensor(dst, dtype=torch.int64)
+        if src.shape != dst.shape or src.dim() != 1:
+            raise ValueError("src and dst must be 1-D tensors of equal length")
+        if src.device != dst.device:
+            raise ValueError("src and dst must live on one device")
+        self._src, self._dst = src.contiguous(), dst.contiguous()
+        if num_src_nodes is None:
+            num_src_nodes = int(max(src.max().item(), dst.max().item())) + 1 if src.numel() else 0
+        self._n_src = int(num_src_nodes)
+        self._n_dst = int(self._n_src if num_dst_nodes is None else num_dst_nodes)
+        self.is_block = bool(is_block)
+        self.edata = {}
+        if self.is_block or self._n_src != self._n_dst:
+            self.srcdata, self.dstdata = {}, {}
+            self.ndata = self.srcdata
+        else:
+            self.ndata = {}
+            self.srcdata = self.dstdata = self.ndata
+        self._handle = None
+        self._info = None
+        self._cache = {}
+
+    # ---- lifetime of the device structure ---------------------------------
+    def _ensure(self):
+        if self._handle is not None:
+            return self._handle
+        _require_cuda(self._src, "graph structure")
+        lib = _lib.load()
+        h = C.c_void_p()
+        with torch.cuda.device(self._src.device):
+            rc = lib.botgat_graph_create(self._n_src, self._n_dst, self._src.numel(), _lib.ptr(self._src),
+                                         _lib.ptr(self._dst), self._src.device.index, _stream(), C.byref(h))
+        _lib.check(rc, "botgat_graph_create")
+        self._handle = h
+        info = _lib.GraphInfo()
+        _lib.check(lib.botgat_graph_get_info(h, C.byref(info)), "botgat_graph_get_info")
+        self._info = info
+        return h
+
+    def __del__(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h is not None and _lib._lib is not None:
+            try:
+                _lib._lib.botgat_graph_destroy(h)
+            except Exception:
+                pass
+
+    def create_formats_(self):
+        """``graph.create_formats_()`` (run.py:146): materialise CSR + CSC now."""
+        if self._src.is_cuda:
+            self._ensure()
+
+    # ---- DGLGraph protocol -------------------------------------------------
+    @property
+    def device(self):
+        return self._src.device
+
+    def edges(self, order="eid"):
+        return self._src, self._dst
+
+    def number_of_edges(self):
+        return self._src.numel()
+
+    num_edges = number_of_edges
+
+    def number_of_nodes(self):
+        return self._n_src
+
+    num_nodes = number_of_nodes
+
+    def number_of_src_nodes(self):
+        return self._n_src
+
+    def number_of_dst_nodes(self):
+        return self._n_dst
+
+    def structure(self, name):
+        """Copy of one device structure array as an int64 tensor (names: _lib.ARRAYS)."""
+        h = self._ensure()
+        p, n = C.c_void_p(), C.c_int64()
+        _lib.check(_lib.load().botgat_graph_get(h, _lib.ARRAYS.index(name), C.byref(p), C.byref(n)), "botgat_graph_get")
+        if n.value == 0:
+            return torch.empty(0, dtype=torch.int64, device=self.device)
+        view = torch.as_tensor(_DevArray(p.value, n.value), device=self.device)  # zero-copy view of library memory
+        return view.long()  # the copy is what escapes
+
+    def in_degrees(self):
+        if "in_deg" not in self._cache:
+            self._cache["in_deg"] = self.structure("in_deg")
+        return self._cache["in_deg"]
+
+    def out_degrees(self):
+        if "out_deg" not in self._cache:
+            self._cache["out_deg"] = self.structure("out_deg")
+        return self._cache["out_deg"]
+
+    @property
+    def has_zero_in_degree(self):
+        """Cached replacement of ``(graph.in_degrees() == 0).any()`` (models.py:478): no host sync per forward."""
+        self._ensure()
+        return bool(self._info.has_zero_in_degree)
+
+    def deg_scale(self, which, power):
+        """``clamp(deg,1)^power`` exactly as the reference spells it (models.py:501-502, 551-552), cached."""
+        key = (which, power)
+        if key not in self._cache:
+            deg = self.out_degrees() if which == "out" else self.in_degrees()
+            self._cache[key] = torch.pow(deg.float().clamp(min=1), power).contiguous()
+        return self._cache[key]
+
+    @contextlib.contextmanager
+    def local_scope(self):
+        saved = [dict(d) for d in (self.srcdata, self.dstdata, self.edata)]
+        try:
+            yield
+        finally:
+            for d, s in zip((self.srcdata, self.dstdata, self.edata), saved):
+                d.clear()
+                d.update(s)
+
+    def to(self, device):
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        if device == self.device:
+            return self
+        g = Graph(self._src.to(device), self._dst.to(device), self._n_src, self._n_dst, self.is_block)
+        for name in ("srcdata", "dstdata", "edata"):
+            getattr(g, name).update({k: v.to(device) for k, v in getattr(self, name).items()})
+        return g
+
+    def cpu(self):
+        return self.to("cpu")
+
+    # ---- preprocessing (run.py:133-148) ------------------------------------
+    def _new_like(self, src, dst):
+        if self.is_block or self._n_src != self._n_dst:
+            raise RuntimeError("preprocessing ops are defined for homogeneous graphs only")
+        g = Graph(src, dst, self._n_src)
+        g.ndata.update(self.ndata)
+        return g
+
+    def remove_self_loop(self):
+        _require_cuda(self._src, "remove_self_loop")
+        lib, e = _lib.load(), self._src.numel()
+        o_s, o_d, n = torch.empty_like(self._src), torch.empty_like(self._dst), C.c_int64()
+        with torch.cuda.device(self.device):
+            rc = lib.botgat_coo_remove_self_loop(e, _lib.ptr(self._src), _lib.ptr(self._dst), _lib.ptr(o_s), _lib.ptr(o_d),
+                                                 C.byref(n), self.device.index, _stream())
+        _lib.check(rc, "botgat_coo_remove_self_loop")
+        return self._new_like(o_s[: n.value].clone(), o_d[: n.value].clone())
+
+    def add_self_loop(self):
+        _require_cuda(self._src, "add_self_loop")
+        lib, e = _lib.load(), self._src.numel()
+        o_s = torch.empty(e + self._n_src, dtype=torch.int64, device=self.device)
+        o_d = torch.empty_like(o_s)
+        with torch.cuda.device(self.device):
+            rc = lib.botgat_coo_add_self_loop(self._n_src, e, _lib.ptr(self._src), _lib.ptr(self._dst), _lib.ptr(o_s),
+                                              _lib.ptr(o_d), self.device.index, _stream())
+        _lib.check(rc, "botgat_coo_add_self_loop")
+        return self._new_like(o_s, o_d)
+
+    def to_bidirected(self):
+        """``dgl.to_bidirected(graph)`` (run.py:137): drops node/edge data like DGL does."""
+        _require_cuda(self._src, "to_bidirected")
+        if self.is_block or self._n_src != self._n_dst:
+            raise RuntimeError("to_bidirected is defined for homogeneous graphs only")
+        lib, e = _lib.load(), self._src.numel()
+        o_s = torch.empty(2 * e, dtype=torch.int64, device=self.device)
+        o_d, n = torch.empty_like(o_s), C.c_int64()
+        with torch.cuda.device(self.device):
+            rc = lib.botgat_coo_to_bidirected(self._n_src, e, _lib.ptr(self._src), _lib.ptr(self._dst), _lib.ptr(o_s),
+                                              _lib.ptr(o_d), C.byref(n), self.device.index, _stream())
+        _lib.check(rc, "botgat_coo_to_bidirected")
+        return Graph(o_s[: n.value].clone(), o_d[: n.value].clone(), self._n_src)
+
+
+def graph(data, num_nodes=None, device=None):
+    """``dgl.graph((src, dst), num_nodes=...)`` look-alike."""
+    src, dst = data
+    src = torch.as_tensor(src, dtype=torch.int64)
+    dst = torch.as_tensor(dst, dtype=torch.int64)
+    if device is not None:
+        src, dst = src.to(device), dst.to(device)
+    return Graph(src, dst, num_nodes)
+
+
+def to_bidirected(g):
+    return g.to_bidirected()
+
+
+def remove_self_loop(g):
+    return g.remove_self_loop()
+
+
+def add_self_loop(g):
+    return g.add_self_loop()
+
+
+def create_block(data, num_src_nodes, num_dst_nodes, device=None):
+    """``dgl.create_block`` look-alike: bipartite block whose dst nodes are a prefix of src."""
+    src, dst = data
+    src = torch.as_tensor(src, dtype=torch.int64)
+    dst = torch.as_tensor(dst, dtype=torch.int64)
+    if device is not None:
+        src, dst = src.to(device), dst.to(device)
+    return Graph(src, dst, num_src_nodes, num_dst_nodes, is_block=True)

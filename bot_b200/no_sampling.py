@@ -1,0 +1,238 @@
+"""Drop-in for ``src/no-sampling/models.py`` of AiRyunn/BoT: ``GATConv`` (full-graph
+variant), ``ElementWiseLinear`` and the ``GAT`` wrapper, with the same constructor
+arguments, parameter names (``fc``, ``attn_l``, ``attn_r``, ``res_fc``) and
+``forward(graph, feat)`` signature, so ``run.py`` can do ``from bot_b200.no_sampling
+import GAT`` unchanged.  The DGL calls in the layer body are replaced by one call of
+``bot_b200.functional.gat_fused`` (hand-written sm_100a kernels); the dense
+projections stay torch matmuls.
+
+Reference: GATConv  src/no-sampling/models.py:416-566
+           GAT      src/no-sampling/models.py:644-736
+           ElementWiseLinear  src/no-sampling/models.py:18-50
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .functional import gat_fused
+
+
+def draw_edge_keep(n_edges, edge_drop, device):
+    """Edge-drop keep set exactly as the reference draws it (models.py:529-532):
+    ``perm = randperm(E); eids = perm[int(E*p):]`` kept, the rest dropped."""
+    perm = torch.randperm(n_edges, device=device)
+    bound = int(n_edges * edge_drop)
+    keep = torch.ones(n_edges, dtype=torch.uint8, device=device)
+    keep[perm[:bound]] = 0
+    return keep, perm[bound:]
+
+
+def draw_attn_mul(attn_drop_module, n_edges, n_heads, device, eids=None):
+    """Attention-dropout multiplier m/(1-p) drawn by the module's own ``nn.Dropout``
+    on a tensor shaped like the reference's ``edge_softmax`` output ((E',H,1),
+    models.py:537/544), scattered to edge-id order."""
+    rows = n_edges if eids is None else eids.numel()
+    mul = attn_drop_module(torch.ones((rows, n_heads, 1), dtype=torch.float32, device=device))
+    if eids is None:
+        return mul.view(n_edges, n_heads)
+    full = torch.zeros((n_edges, n_heads), dtype=torch.float32, device=device)
+    full[eids] = mul.view(rows, n_heads)
+    return full
+
+
+class ElementWiseLinear(nn.Module):
+    """Per-feature scale and/or shift (models.py:18-50)."""
+
+    def __init__(self, size, weight=True, bias=True, inplace=False):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(size)) if weight else None
+        self.bias = nn.Parameter(torch.zeros(size)) if bias else None
+        self.inplace = inplace
+
+    def reset_parameters(self):
+        if self.weight is not None:
+            nn.init.ones_(self.weight)
+        if self.bias is not None:
+            nn.init.zeros_(self.bias)
+
+    def forward(self, x):
+        if self.inplace:
+            if self.weight is not None:
+                x.mul_(self.weight)
+            if self.bias is not None:
+                x.add_(self.bias)
+            return x
+        if self.weight is not None:
+            x = x * self.weight
+        if self.bias is not None:
+            x = x + self.bias
+        return x
+
+
+class GATConv(nn.Module):
+    """GAT layer, full-graph variant (models.py:416-566).
+
+    ``attn_dropout_mode``: "exact" draws the attention-dropout mask with torch's own
+    generator (the reference's semantics, mask materialised once as (E,H)); "fused"
+    draws it inside the kernels from a Philox stream keyed on (seed, edge id, head).
+    """
+
+    attn_dropout_mode = "exact"
+
+    def __init__(self, in_feats, out_feats, num_heads=1, feat_drop=0.0, attn_drop=0.0, edge_drop=0.0,
+                 negative_slope=0.2, linear=True, activation=None, allow_zero_in_degree=False,
+                 use_symmetric_norm=False, non_interactive_attn=False):
+        super().__init__()
+        self._num_heads = num_heads
+        if isinstance(in_feats, tuple):
+            self._in_src_feats, self._in_dst_feats = in_feats
+        else:
+            self._in_src_feats = self._in_dst_feats = in_feats
+        self._out_feats = out_feats
+        self._allow_zero_in_degree = allow_zero_in_degree
+        self._use_symmetric_norm = use_symmetric_norm
+        self._negative_slope = negative_slope
+        hd = out_feats * num_heads
+        if isinstance(in_feats, tuple):
+            self.fc_src = nn.Linear(self._in_src_feats, hd, bias=False)
+            self.fc_dst = nn.Linear(self._in_dst_feats, hd, bias=False)
+        else:
+            self.fc = nn.Linear(self._in_src_feats, hd, bias=False)
+        self.attn_l = nn.Parameter(torch.empty(1, num_heads, out_feats))
+        # the flag name is inverted in the reference (models.py:444-447): True ADDS attn_r
+        if non_interactive_attn:
+            self.attn_r = nn.Parameter(torch.empty(1, num_heads, out_feats))
+        else:
+            self.register_buffer("attn_r", None)
+        self.feat_drop = nn.Dropout(feat_drop)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.edge_drop = edge_drop
+        self.leaky_relu = nn.LeakyReLU(negative_slope)
+        if linear:
+            self.res_fc = nn.Linear(self._in_dst_feats, hd, bias=False)
+        else:
+            self.register_buffer("res_fc", None)
+        self.reset_parameters()
+        self._activation = activation
+
+    def reset_parameters(self):
+        gain = nn.init.calculate_gain("relu")
+        for lin in ("fc", "fc_src", "fc_dst"):
+            if hasattr(self, lin):
+                nn.init.xavier_normal_(getattr(self, lin).weight, gain=gain)
+        nn.init.xavier_normal_(self.attn_l, gain=gain)
+        if isinstance(self.attn_r, nn.Parameter):
+            nn.init.xavier_normal_(self.attn_r, gain=gain)
+        if isinstance(self.res_fc, nn.Linear):
+            nn.init.xavier_normal_(self.res_fc.weight, gain=gain)
+
+    def set_allow_zero_in_degree(self, set_value):
+        self._allow_zero_in_degree = set_value
+
+    def forward(self, graph, feat):
+        H, D = self._num_heads, self._out_feats
+        with graph.local_scope():
+            if not self._allow_zero_in_degree and graph.has_zero_in_degree:  # models.py:477-479
+                assert False
+            n_dst = graph.number_of_dst_nodes()
+            if isinstance(feat, tuple):                                      # models.py:481-488
+                h_src, h_dst = self.feat_drop(feat[0]), self.feat_drop(feat[1])
+                if not hasattr(self, "fc_src"):
+                    self.fc_src, self.fc_dst = self.fc, self.fc
+                ft = self.fc_src(h_src).view(-1, H, D)
+                ft_dst = self.fc_dst(h_dst).view(-1, H, D)
+            else:                                                            # models.py:490-498
+                h_src = self.feat_drop(feat)
+                ft = self.fc(h_src).view(-1, H, D)
+                if graph.is_block:
+                    h_dst, ft_dst = h_src[:n_dst], ft[:n_dst]
+                else:
+                    h_dst, ft_dst = h_src, ft
+
+            # symmetric normalisation: the source scale applies to messages and el only;
+            # er and the residual see the unscaled projection (models.py:497-505, 521)
+            src_scale = dst_scale = None
+            if self._use_symmetric_norm:
+                src_scale = graph.deg_scale("out", -0.5)
+                dst_scale = graph.deg_scale("in", 0.5)                        # +0.5, models.py:552
+            el = torch.einsum("nhd,hd->nh", ft, self.attn_l[0])               # models.py:517
+            if src_scale is not None:
+                el = el * src_scale.unsqueeze(-1)
+            er = None
+            if self.attn_r is not None:
+                er = torch.einsum("nhd,hd->nh", ft_dst, self.attn_r[0])       # models.py:521
+
+            E = graph.number_of_edges()
+            keep = attn_mul = eids = None
+            attn_p, seed = 0.0, 0
+            if self.training and self.edge_drop > 0:                          # models.py:528-537
+                keep, eids = draw_edge_keep(E, self.edge_drop, ft.device)
+            if self.training and self.attn_drop.p > 0:
+                if self.attn_dropout_mode == "exact":
+                    attn_mul = draw_attn_mul(self.attn_drop, E, H, ft.device, eids)
+                else:
+                    attn_p = self.attn_drop.p
+                    seed = int(torch.randint(0, 2**62, (1,)).item())
+
+            rst = gat_fused(graph, ft, el, er, None, keep, attn_mul, src_scale, dst_scale,
+                            self._negative_slope, attn_p, seed)                # models.py:523-555
+
+            if self.res_fc is not None:                                       # models.py:557-560
+                rst = rst + self.res_fc(h_dst).view(h_dst.shape[0], -1, D)
+            if self._activation is not None:
+                rst = self._activation(rst)
+            return rst
+
+
+class GAT(nn.Module):
+    """Stack of GATConv layers with the reference's per-layer epilogue (models.py:644-736)."""
+
+    def __init__(self, dim_node, dim_edge, dim_output, n_hidden, n_layers, n_heads, activation, norm="none",
+                 dropout=0.0, input_drop=0.0, attn_drop=0.0, edge_drop=0.0, non_interactive_attn=False,
+                 use_symmetric_norm=False, linear=False, residual=False):
+        super().__init__()
+        self.n_node_feats = dim_node
+        self.n_hidden = n_hidden
+        self.n_classes = dim_output
+        self.n_layers = n_layers
+        self.num_heads = n_heads
+
+        self.convs = nn.ModuleList()
+        # the reference compares against "none:" (sic, models.py:672) so norms is always a
+        # ModuleList; an empty one is falsy and selects the bias path in forward
+        self.norms = nn.ModuleList()
+        self.biases = nn.ModuleList()
+        for i in range(n_layers):
+            last = i == n_layers - 1
+            in_hidden = n_heads * n_hidden if i > 0 else dim_node
+            out_hidden = dim_output if last else n_hidden
+            heads = 1 if last else n_heads
+            self.convs.append(GATConv(in_hidden, out_hidden, num_heads=heads, attn_drop=attn_drop,
+                                      edge_drop=edge_drop, non_interactive_attn=non_interactive_attn,
+                                      use_symmetric_norm=use_symmetric_norm, linear=linear))
+            if last:
+                self.biases.append(ElementWiseLinear(out_hidden, weight=False, bias=True))
+            elif norm == "batch":
+                self.norms.append(nn.BatchNorm1d(heads * out_hidden))
+            elif norm == "none":
+                self.biases.append(ElementWiseLinear(heads * out_hidden, weight=False, bias=True))
+        self.input_drop = nn.Dropout(input_drop)
+        self.dropout = nn.Dropout(dropout)
+        self.activation = activation
+        self.residual = residual
+
+    def forward(self, graph, feat):
+        h = self.input_drop(feat)
+        h_last = None
+        for i in range(self.n_layers):
+            h = self.convs[i](graph, h)
+            if i < self.n_layers - 1:
+                if self.residual and h_last is not None:
+                    h = h + h_last
+                h_last = h
+                h = h.flatten(1)
+                h = self.norms[i](h) if self.norms else self.biases[i](h)
+                h = self.dropout(self.activation(h))
+        h = h.mean(1)
+        return self.biases[-1](h)

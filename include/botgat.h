@@ -1,0 +1,221 @@
+/*
+ * botgat.h — C ABI of the B200-native GAT message-passing engine.
+ *
+ * Drop-in boundary for the sparse section of BoT's GATConv layers
+ * (reference: src/no-sampling/models.py:475-566, src/ogbn-proteins/models.py:87-168,
+ * src/ogbn-products/models.py:88-167).  The reference reaches this arithmetic
+ * through DGL 0.5 Python calls; each entry point below names the call(s) it
+ * replaces.  Plain pointers and sizes only — no torch / C++ types.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer on `device` unless marked HOST;
+ *  - every entry point enqueues on `stream` (a cudaStream_t passed as void*) and
+ *    returns without synchronising unless stated otherwise;
+ *  - return value 0 = success, negative = error; the message is available from
+ *    botgat_last_error() (thread-local);
+ *  - the caller owns every buffer passed in (inputs, outputs, workspaces); the
+ *    library owns only the internals of a botgat_graph.
+ *  - node ids / edge ids are int64 at the boundary (DGL's idtype) and int32
+ *    inside (all structure arrays returned by botgat_graph_get are int32);
+ *    n_edges must be < 2^31.
+ */
+#ifndef BOTGAT_H_
+#define BOTGAT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define BOTGAT_ABI_VERSION 1
+
+typedef struct botgat_graph botgat_graph;
+
+int botgat_abi_version(void);
+const char* botgat_last_error(void);
+
+/* ------------------------------------------------------------------------
+ * Graph ingestion.
+ * Replaces DGLGraph construction + `graph.create_formats_()`
+ * (src/no-sampling/run.py:146, src/ogbn-proteins/gat.py:66,
+ * src/ogbn-products/gat.py:75) and `graph.in_degrees()/out_degrees()`
+ * (src/no-sampling/models.py:478,501,551).
+ *
+ * src/dst: (n_edges) int64 COO in edge-id order.  Builds, on the device,
+ *   in-CSR  (rows = dst, CSC in DGL terms): indptr, indices (= src), eid
+ *   out-CSR (rows = src):                   indptr, indices (= dst), eid
+ * with a stable sort (inside a row, increasing edge id), plus degree tables.
+ * Synchronises `stream` once before returning (it reads back two scalars).
+ * ---------------------------------------------------------------------- */
+int botgat_graph_create(int64_t n_src, int64_t n_dst, int64_t n_edges,
+                        const int64_t* src, const int64_t* dst,
+                        int device, void* stream, botgat_graph** out);
+void botgat_graph_destroy(botgat_graph* g);
+
+enum {
+  BOTGAT_IN_INDPTR = 0,   /* int32 (n_dst+1) */
+  BOTGAT_IN_INDICES = 1,  /* int32 (n_edges)  source id of each in-CSR entry */
+  BOTGAT_IN_EID = 2,      /* int32 (n_edges)  edge id of each in-CSR entry */
+  BOTGAT_OUT_INDPTR = 3,  /* int32 (n_src+1) */
+  BOTGAT_OUT_INDICES = 4, /* int32 (n_edges)  destination id of each out-CSR entry */
+  BOTGAT_OUT_EID = 5,     /* int32 (n_edges) */
+  BOTGAT_IN_DEG = 6,      /* int32 (n_dst) */
+  BOTGAT_OUT_DEG = 7      /* int32 (n_src) */
+};
+/* Expose a structure array (device pointer + element count). */
+int botgat_graph_get(const botgat_graph* g, int which, void** dev_ptr, int64_t* len);
+
+typedef struct {
+  int64_t n_src, n_dst, n_edges;
+  int64_t max_in_deg, max_out_deg;
+  int32_t has_zero_in_degree; /* replaces `(graph.in_degrees()==0).any()`, models.py:478 */
+  int32_t device;
+} botgat_graph_info;
+int botgat_graph_get_info(const botgat_graph* g, botgat_graph_info* info /* HOST */);
+
+/* ------------------------------------------------------------------------
+ * COO preprocessing on the device.
+ * Replaces dgl.to_bidirected / remove_self_loop / add_self_loop
+ * (src/no-sampling/run.py:137,143).  Outputs are caller-allocated with the
+ * stated capacity; *n_out (HOST) receives the edge count; these calls
+ * synchronise `stream`.
+ * ---------------------------------------------------------------------- */
+/* add reverse edges, dedup, sort by (src,dst).  capacity of out_*: 2*n_edges */
+int botgat_coo_to_bidirected(int64_t n_nodes, int64_t n_edges,
+                             const int64_t* src, const int64_t* dst,
+                             int64_t* out_src, int64_t* out_dst, int64_t* n_out,
+                             int device, void* stream);
+/* drop (i,i) edges, keep order.  capacity: n_edges */
+int botgat_coo_remove_self_loop(int64_t n_edges, const int64_t* src, const int64_t* dst,
+                                int64_t* out_src, int64_t* out_dst, int64_t* n_out,
+                                int device, void* stream);
+/* append (i,i), i = 0..n_nodes-1.  capacity: n_edges + n_nodes.  Does not synchronise. */
+int botgat_coo_add_self_loop(int64_t n_nodes, int64_t n_edges,
+                             const int64_t* src, const int64_t* dst,
+                             int64_t* out_src, int64_t* out_dst,
+                             int device, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Per-edge operand staging.  Edge tensors arrive in edge-id order
+ * (DGL `edata`); the fused kernels stream them in CSR order, head-major.
+ * ---------------------------------------------------------------------- */
+enum { BOTGAT_ORDER_IN = 0, BOTGAT_ORDER_OUT = 1 };
+/*
+ * eb[hb][p] = (ee ? ee[eid(p)*H + hb] : 0), or -inf when keep && !keep[eid(p)]
+ * am[h][p]  = attn_mul[eid(p)*H + h]
+ *   ee        (n_edges,H) float or NULL — `attn_edge_fc(feat_edge)`, proteins models.py:131
+ *   keep      (n_edges) uint8 or NULL   — edge-drop keep set, models.py:529-532
+ *   attn_mul  (n_edges,H) float or NULL — attention-dropout multiplier, models.py:537/544
+ *   eb        (Hb,n_edges) out, Hb = H if ee else 1; NULL iff ee==NULL && keep==NULL
+ *   am        (H,n_edges) out; NULL iff attn_mul==NULL
+ */
+int botgat_edge_stage(const botgat_graph* g, int order, int32_t H,
+                      const float* ee, const uint8_t* keep, const float* attn_mul,
+                      float* eb, float* am, void* stream);
+/* grad_ee[eid(p)*H + h] = gz[h][p]  (gz in in-CSR order, head-major) */
+int botgat_edge_unstage(const botgat_graph* g, int32_t H, const float* gz,
+                        float* grad_ee, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Fused forward: logits -> leaky_relu -> online edge-softmax -> attention
+ * dropout -> u_mul_e/sum SpMM -> degree scaling, one pass over the in-CSR.
+ * Replaces src/no-sampling/models.py:500-505,523-555 and
+ * src/ogbn-proteins/models.py:125-156 (DGL apply_edges / edge_softmax /
+ * update_all and the torch elementwise ops between them).
+ *
+ *   out[v,h,:] = dst_scale[v] * sum_k a~[k,h] * src_scale[u_k] * ft[u_k,h,:]
+ *   a~ = softmax_v( leaky_relu(el[u]+er[v]+eb[k]) ) * am[k]
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  int32_t H;              /* heads */
+  int32_t D;              /* per-head width */
+  int64_t ld_ft;          /* row stride of ft, floats (>= H*D) */
+  int64_t ld_out;         /* row stride of out, floats */
+  const float* ft;        /* (n_src, ld_ft)  projected source features, unscaled */
+  const float* el;        /* (n_src, H) */
+  const float* er;        /* (n_dst, H) or NULL */
+  const float* eb;        /* (Hb, n_edges) in-CSR order, or NULL */
+  int32_t Hb;             /* 0, 1 or H */
+  int32_t col_parts;      /* split each head's D columns in this many parts; 0 = auto */
+  const float* am;        /* (H, n_edges) in-CSR order, or NULL */
+  const float* src_scale; /* (n_src) or NULL */
+  const float* dst_scale; /* (n_dst) or NULL */
+  float slope;            /* leaky_relu negative slope */
+  float attn_p;           /* in-kernel Philox attention dropout prob (used iff am==NULL && attn_p>0) */
+  uint64_t seed;          /* Philox key for the above */
+  float* out;             /* (n_dst, ld_out) */
+  float* row_max;         /* (n_dst, H)  saved for backward */
+  float* row_sum;         /* (n_dst, H)  saved for backward */
+} botgat_fwd_args;
+int botgat_gat_forward(const botgat_graph* g, const botgat_fwd_args* a /* HOST */, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Backward.  Replaces the autograd replay of DGL's
+ * GSpMM / GSDDMM / EdgeSoftmax backward kernels.  Deterministic (no atomics).
+ *   node pass : t[v,h] = <out[v,h,:], gout[v,h,:]>, packs per-dst records
+ *   pass B    : out-CSR (src-major): grad_ft, grad_el
+ *   pass A    : in-CSR  (dst-major): grad_er, gz (only when either is requested)
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  int32_t H, D;
+  int64_t ld_ft, ld_out, ld_gft;
+  const float* ft;        /* (n_src, ld_ft) */
+  const float* el;        /* (n_src, H) */
+  const float* er;        /* (n_dst, H) or NULL */
+  const float* eb_in;     /* (Hb, n_edges) in-CSR order or NULL */
+  const float* eb_out;    /* (Hb, n_edges) out-CSR order or NULL */
+  int32_t Hb;
+  int32_t col_parts;
+  const float* am_in;     /* (H, n_edges) or NULL */
+  const float* am_out;    /* (H, n_edges) or NULL */
+  const float* src_scale;
+  const float* dst_scale;
+  float slope;
+  float attn_p;
+  uint64_t seed;
+  const float* out;       /* (n_dst, ld_out) forward output (post dst_scale) */
+  const float* row_max;   /* (n_dst, H) */
+  const float* row_sum;   /* (n_dst, H) */
+  const float* gout;      /* (n_dst, ld_out) gradient w.r.t. out */
+  /* workspaces */
+  float* drec;            /* (H, n_dst, 4) */
+  float* gprime;          /* (n_dst, ld_out); required iff dst_scale != NULL */
+  /* outputs */
+  float* grad_ft;         /* (n_src, ld_gft) w.r.t. the unscaled ft */
+  float* grad_el;         /* (n_src, H) */
+  float* grad_er;         /* (n_dst, H) or NULL */
+  float* gz;              /* (H, n_edges) in-CSR order, or NULL (feed to botgat_edge_unstage) */
+} botgat_bwd_args;
+int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args* a /* HOST */, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Multi-GPU: 1-D destination-row partition (no reference implementation —
+ * the reference is single-GPU; contract in DESIGN.md).
+ * ---------------------------------------------------------------------- */
+/* bounds[p] = first row r with in_indptr[r] >= floor(p*E/P); bounds (HOST, n_parts+1). Synchronises. */
+int botgat_partition_1d(const botgat_graph* g, int32_t n_parts, int64_t* bounds /* HOST */, void* stream);
+/*
+ * Local edge set of rows [lo,hi): counts the edges (phase 0: out_* NULL, *n_local set)
+ * or writes them (phase 1): global edge id, global src, local dst (= dst-lo), edge-id order.
+ * Synchronises.
+ */
+int botgat_partition_extract(const botgat_graph* g, int64_t lo, int64_t hi,
+                             int64_t* out_eid, int64_t* out_src, int64_t* out_ldst,
+                             int64_t* n_local /* HOST */, void* stream);
+/* Row gather/scatter used by the halo exchange (send-list packing and the transposed add). */
+int botgat_rows_gather(const float* table, int64_t ld, int64_t width, const int64_t* rows, int64_t n_rows,
+                       float* out /* (n_rows,width) */, void* stream);
+int botgat_rows_scatter_add(float* table, int64_t ld, int64_t width, const int64_t* rows, int64_t n_rows,
+                            const float* in /* (n_rows,width), rows unique */, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* BOTGAT_H_ */

@@ -1,0 +1,141 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle — `-m gpu`."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import graph_ref
+from util import check_case, engine_run, make_case, oracle_run, rel_err, FWD_TOL
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,e,seed", [(1, 0, 0), (7, 3, 1), (100, 1000, 2), (2708, 13264, 3), (5000, 200000, 4)])
+def test_structure_bit_exact(cuda, n, e, seed):
+    import bot_b200
+
+    src, dst = graph_ref.synthetic_coo(n, e, seed, power_law=0.8 if seed == 4 else 0.0)
+    ref = graph_ref.build_formats(src, dst, n, n)
+    g = bot_b200.Graph(torch.from_numpy(src).to(cuda), torch.from_numpy(dst).to(cuda), n)
+    for name, arr in ref.items():
+        got = g.structure(name).cpu().numpy()
+        assert got.dtype == np.int64 and got.shape == arr.shape, name
+        assert np.array_equal(got, arr), name
+    assert g.has_zero_in_degree == bool((ref["in_deg"] == 0).any())
+
+
+def test_block_structure(cuda):
+    import bot_b200
+
+    rng = np.random.default_rng(0)
+    n_src, n_dst, e = 300, 40, 2000
+    src = rng.integers(0, n_src, e)
+    dst = rng.integers(0, n_dst, e)
+    ref = graph_ref.build_formats(src, dst, n_src, n_dst)
+    g = bot_b200.create_block((src, dst), n_src, n_dst, device=cuda)
+    for name, arr in ref.items():
+        assert np.array_equal(g.structure(name).cpu().numpy(), arr), name
+
+
+def test_preprocess_bit_exact(cuda):
+    """to_bidirected -> remove_self_loop -> add_self_loop (run.py:133-148)."""
+    import bot_b200
+
+    n, e = 500, 4000
+    src, dst = graph_ref.synthetic_coo(n, e, 7)
+    g = bot_b200.graph((src, dst), num_nodes=n, device=cuda)
+    g2 = bot_b200.to_bidirected(g)
+    rs, rd = graph_ref.to_bidirected(src, dst, n)
+    assert np.array_equal(g2.edges()[0].cpu().numpy(), rs) and np.array_equal(g2.edges()[1].cpu().numpy(), rd)
+    g3 = g2.remove_self_loop().add_self_loop()
+    rs, rd = graph_ref.add_self_loop(*graph_ref.remove_self_loop(rs, rd), n)
+    assert np.array_equal(g3.edges()[0].cpu().numpy(), rs) and np.array_equal(g3.edges()[1].cpu().numpy(), rd)
+    assert g3.number_of_edges() == rs.shape[0]
+    assert not g3.has_zero_in_degree
+
+
+CASES = {
+    # name: (n_src, n_dst, E, H, D, kwargs)
+    "src_only_H3_D8": (200, 200, 3000, 3, 8, dict(er=False)),
+    "er_H2_D16": (300, 300, 4000, 2, 16, dict()),
+    "proteins_like_H6_D80_er_ee": (400, 400, 30000, 6, 80, dict(ee=True)),
+    "proteins_like_edge_drop": (400, 400, 30000, 6, 80, dict(ee=True, keep_p=0.1)),
+    "products_like_H4_D120": (500, 500, 20000, 4, 120, dict(keep_p=0.1)),
+    "arxiv_like_H3_D250_symm": (600, 600, 9000, 3, 250, dict(er=False, symm=True, self_loops=True, attn_p=0.1)),
+    "reddit_like_H4_D64_symm": (300, 300, 60000, 4, 64, dict(er=False, symm=True, attn_p=0.1)),
+    "last_layer_H1_D40": (500, 500, 8000, 1, 40, dict(er=False, symm=True)),
+    "last_layer_H1_D41_scalar": (500, 500, 8000, 1, 41, dict(er=False, symm=True)),
+    "cora_like_H8_D8": (2708, 2708, 10556, 8, 8, dict(er=True, keep_p=0.5, self_loops=True)),
+    "cora_last_H1_D7": (2708, 2708, 10556, 1, 7, dict(er=False, keep_p=0.5, self_loops=True, symm=True)),
+    "block_Nd_lt_Ns": (900, 120, 5000, 4, 32, dict(ee=True)),
+    "power_law_skew": (2000, 2000, 100000, 2, 64, dict(power_law=1.0, ee=True)),
+    "zero_in_degree_rows": (300, 300, 200, 2, 24, dict(ee=True, keep_p=0.3)),
+    "wide_D512": (100, 100, 2000, 1, 512, dict()),
+    "odd_D250_H1": (150, 150, 3000, 1, 250, dict(ee=True, attn_p=0.2, keep_p=0.2)),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_fwd_bwd_parity(cuda, name):
+    n_src, n_dst, e, H, D, kw = CASES[name]
+    c = make_case(n_src, n_dst, e, H, D, seed=hash(name) % 1000, **kw)
+    errs = check_case(c, cuda)
+    print(name, {k: f"{v:.2e}" for k, v in errs.items()})
+
+
+def test_empty_graph(cuda):
+    c = make_case(10, 10, 0, 2, 8, ee=True)
+    out, g, _ = engine_run(c, cuda)
+    assert out.shape == (10, 2, 8) and float(out.abs().max()) == 0.0
+    assert float(g["ft"].abs().max()) == 0.0 and float(g["el"].abs().max()) == 0.0
+    assert g["ee"].shape == (0, 2)
+
+
+def test_all_edges_dropped_rows(cuda):
+    """Rows whose every in-edge is dropped must produce 0 (reference: softmax over the kept edge subgraph)."""
+    c = make_case(50, 50, 400, 2, 16, ee=True)
+    keep = torch.ones(400, dtype=torch.bool)
+    keep[c["dst"] < 10] = False
+    c["keep"] = keep
+    errs = check_case(c, cuda)
+    out, _, _ = engine_run(c, cuda)
+    assert float(out[:10].abs().max()) == 0.0
+    assert torch.isfinite(out).all()
+
+
+def test_column_parts_forward(cuda, monkeypatch):
+    """Forcing a tiny L2 slab budget splits heads into column parts; results must not change."""
+    c = make_case(3000, 3000, 20000, 2, 128, ee=True, seed=5)
+    ref, _ = oracle_run(c)
+    monkeypatch.setenv("BOTGAT_SLAB_MB", "1")
+    out, _, _ = engine_run(c, cuda)
+    assert rel_err(out, ref) <= FWD_TOL
+
+
+def test_forced_group_sizes(cuda, monkeypatch):
+    c = make_case(300, 300, 20000, 2, 64, ee=True, seed=6)
+    ref, refg = oracle_run(c)
+    for G in (1, 2, 4, 8, 16, 32):
+        monkeypatch.setenv("BOTGAT_G", str(G))
+        out, g, _ = engine_run(c, cuda)
+        assert rel_err(out, ref) <= FWD_TOL, G
+        assert rel_err(g["ft"], refg["ft"]) <= 1e-4 and rel_err(g["el"], refg["el"]) <= 1e-4, G
+        assert rel_err(g["er"], refg["er"]) <= 1e-4 and rel_err(g["ee"], refg["ee"]) <= 1e-4, G
+
+
+def test_deterministic(cuda):
+    c = make_case(2000, 2000, 100000, 4, 64, ee=True, power_law=0.8, seed=9)
+    o1, g1, _ = engine_run(c, cuda)
+    o2, g2, _ = engine_run(c, cuda)
+    assert torch.equal(o1, o2)
+    for k in g1:
+        assert torch.equal(g1[k], g2[k]), k
+
+
+def test_softmax_rows_sum_to_one(cuda):
+    """With ft = 1 the output is the row sum of attention = 1 on every row with an in-edge."""
+    c = make_case(500, 500, 5000, 3, 16, ee=True, seed=11)
+    c["ft"] = torch.ones_like(c["ft"])
+    out, _, g = engine_run(c, cuda)
+    has = (g.in_degrees() > 0).cpu()
+    assert torch.allclose(out.cpu()[has], torch.ones_like(out.cpu()[has]), atol=2e-6)
+    assert float(out.cpu()[~has].abs().max() if (~has).any() else 0.0) == 0.0

@@ -1,0 +1,113 @@
+"""Shared helpers for the parity tests (oracle = checker only)."""
+import numpy as np
+import torch
+
+from oracle import gat_ref, graph_ref
+
+FWD_TOL = 1e-5   # north_star: fp32 layer outputs within 1e-5 relative
+GRAD_TOL = 1e-4  # north_star: gradients within 1e-4 relative
+
+
+def rel_err(x, ref):
+    """max|x-ref| / max|ref| (norm-relative; elementwise relative error is ill-defined near 0)."""
+    x = x.detach().double().cpu()
+    ref = ref.detach().double().cpu()
+    assert x.shape == ref.shape, (x.shape, ref.shape)
+    if ref.numel() == 0:
+        return 0.0
+    denom = ref.abs().max().item()
+    return (x - ref).abs().max().item() / (denom if denom > 0 else 1.0)
+
+
+def make_case(n_src, n_dst, n_edges, H, D, *, er=True, ee=False, keep_p=0.0, attn_p=0.0, symm=False,
+              seed=0, power_law=0.0, self_loops=False):
+    """Random inputs of the sparse section, on CPU, fp32.  Returns a dict."""
+    g = torch.Generator().manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    src = rng.integers(0, n_src, size=n_edges, dtype=np.int64)
+    if power_law > 0:
+        w = np.arange(1, n_dst + 1, dtype=np.float64) ** (-power_law)
+        cdf = np.cumsum(w / w.sum())
+        dst = np.minimum(np.searchsorted(cdf, rng.random(n_edges)), n_dst - 1).astype(np.int64)
+    else:
+        dst = rng.integers(0, n_dst, size=n_edges, dtype=np.int64)
+    if self_loops:
+        assert n_src == n_dst
+        src, dst = graph_ref.add_self_loop(*graph_ref.remove_self_loop(src, dst), n_src)
+    E = src.shape[0]
+    c = {
+        "src": torch.from_numpy(src), "dst": torch.from_numpy(dst), "n_src": n_src, "n_dst": n_dst, "H": H, "D": D,
+        "ft": torch.randn(n_src, H, D, generator=g),
+        "el": torch.randn(n_src, H, generator=g),
+        "er": torch.randn(n_dst, H, generator=g) if er else None,
+        "ee": torch.randn(E, H, generator=g) if ee else None,
+        "keep": None, "attn_mul": None, "src_scale": None, "dst_scale": None,
+        "gout": torch.randn(n_dst, H, D, generator=g),
+    }
+    if keep_p > 0:
+        perm = torch.randperm(E, generator=g)
+        keep = torch.ones(E, dtype=torch.bool)
+        keep[perm[: int(E * keep_p)]] = False
+        c["keep"] = keep
+    if attn_p > 0:
+        m = (torch.rand(E, H, generator=g) >= attn_p).float() / (1.0 - attn_p)
+        c["attn_mul"] = m
+    if symm:
+        f = graph_ref.build_formats(src, dst, n_src, n_dst)
+        c["src_scale"] = torch.from_numpy(graph_ref.deg_scale(f["out_deg"], -0.5))
+        c["dst_scale"] = torch.from_numpy(graph_ref.deg_scale(f["in_deg"], 0.5))
+    return c
+
+
+def oracle_run(c, dtype=torch.float64, slope=0.2):
+    """Forward + gradients from the oracle (autograd).  Returns (out, grads dict)."""
+    def cvt(t, grad):
+        if t is None:
+            return None
+        t = t.to(dtype).clone()
+        return t.requires_grad_(grad)
+
+    ft, el = cvt(c["ft"], True), cvt(c["el"], True)
+    er, ee = cvt(c["er"], True), cvt(c["ee"], True)
+    out = gat_ref.gat_sparse(c["src"], c["dst"], c["n_dst"], ft, el, er, ee, c["keep"],
+                             cvt(c["attn_mul"], False), slope, cvt(c["src_scale"], False), cvt(c["dst_scale"], False))
+    out.backward(c["gout"].to(dtype))
+    grads = {"ft": ft.grad, "el": el.grad, "er": None if er is None else er.grad, "ee": None if ee is None else ee.grad}
+    return out.detach(), grads
+
+
+def engine_run(c, device, slope=0.2, attn_p=0.0, seed=0):
+    """Same through bot_b200 (CUDA).  Returns (out, grads dict)."""
+    import bot_b200
+    from bot_b200.functional import gat_fused
+
+    def dev(t, grad):
+        if t is None:
+            return None
+        t = t.to(device).clone()
+        return t.requires_grad_(grad)
+
+    g = bot_b200.Graph(c["src"].to(device), c["dst"].to(device), c["n_src"], c["n_dst"],
+                       is_block=c["n_src"] != c["n_dst"])
+    ft, el = dev(c["ft"], True), dev(c["el"], True)
+    er, ee = dev(c["er"], True), dev(c["ee"], True)
+    out = gat_fused(g, ft, el, er, ee, dev(c["keep"], False), dev(c["attn_mul"], False), dev(c["src_scale"], False),
+                    dev(c["dst_scale"], False), slope, attn_p, seed)
+    out.backward(c["gout"].to(device))
+    torch.cuda.synchronize()
+    grads = {"ft": ft.grad, "el": el.grad, "er": None if er is None else er.grad, "ee": None if ee is None else ee.grad}
+    return out.detach(), grads, g
+
+
+def check_case(c, device, **kw):
+    ref_out, ref_g = oracle_run(c)
+    out, g, _ = engine_run(c, device, **kw)
+    errs = {"out": rel_err(out, ref_out)}
+    assert errs["out"] <= FWD_TOL, f"forward rel err {errs['out']:.3e} > {FWD_TOL}"
+    for k in ("ft", "el", "er", "ee"):
+        if ref_g[k] is None:
+            assert g[k] is None
+            continue
+        errs[k] = rel_err(g[k], ref_g[k])
+        assert errs[k] <= GRAD_TOL, f"grad_{k} rel err {errs[k]:.3e} > {GRAD_TOL}"
+    return errs
