@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Contract benchmark: GAT layer fwd+bwd edges/sec at the ogbn-proteins shape.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One "step" = one forward + backward of the GATConv sparse section (logits -> leaky_relu
+-> edge-softmax -> dropout -> SpMM -> scaling) over the whole
+synthetic graph; dense fc projections are excluded from `value` (they stay cuBLAS) and
+included in `e2e`, which goes through the reference-facing `GATConv.forward(graph,
+feat_src, feat_edge)` with HOST input buffers.
+
+N > 1: the same graph is 1-D partitioned on destination rows (strong scaling); every
+rank all-gathers the source table halo, runs its rows, and the gradient halo is
+reduce-scattered back (bot_b200/partition.py).
+
+--impl reference: the oracle port of the reference math (pure torch, CPU) on a bounded
+sample of the same workload, on the host cores of this box (DGL itself is not
+installable offline: DESIGN.md).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# ogbn-proteins layer shape
+N_NODES, N_EDGES, HEADS, HID, EDGE_EMB = 132534, 39561252, 6, 80, 16
+EDGE_DROP, SLOPE = 0.1, 0.2
+METRIC = "GAT layer fwd+bwd edges/sec (ogbn-proteins shape)"
+CPU_SAMPLE_EDGES = N_EDGES // 16
+
+
+def workload_name(n_nodes=N_NODES, n_edges=N_EDGES):
+    return (f"ogbn-proteins-shape GATConv layer: N={n_nodes} E={n_edges} H={HEADS} D={HID} fp32, attn_dst + "
+            f"edge-feature logits ({EDGE_EMB}-dim edge emb), edge_drop={EDGE_DROP} (training), uniform random edges")
+
+
+def algorithmic_bytes(E, N_s, N_d, H, D, er=True, ee=True):
+    """SURVEY.md section 8(d) gather/streaming model.  Returns (fwd, bwd) bytes per layer pass."""
+    R, h = 4 * H * D, 4 * H
+    x = (h + 4) if ee else 0
+    e_r = 1 if er else 0
+    fwd = E * (4 + h + R + x) + N_d * (8 + h * e_r + R + 2 * h)
+    bwd = E * ((4 + h + R + x + h) + (8 + 2 * h + R)) + N_d * (8 + 2 * R + 2 * h + 2 * h * e_r) + N_s * (8 + R + h)
+    return fwd, bwd
+
+
+# ----------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ----------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------
+# synthetic inputs
+# ----------------------------------------------------------------------------
+def synth_edges(n_nodes, n_edges, device, seed=0):
+    g = torch.Generator(device=device).manual_seed(seed)
+    src = torch.randint(0, n_nodes, (n_edges,), device=device, generator=g)
+    dst = torch.randint(0, n_nodes, (n_edges,), device=device, generator=g)
+    return src, dst
+
+
+# ----------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference math on a bounded sample
+# ----------------------------------------------------------------------------
+def cpu_port_run(steps, warmup, n_edges=CPU_SAMPLE_EDGES):
+    """fwd+bwd of the same layer math on the host (oracle port, non-materialising form).
+    Returns dict(value, unit, cores, kind, sample, ms_per_step)."""
+    from oracle import gat_ref
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    src, dst = synth_edges(N_NODES, n_edges, "cpu", seed=0)
+    bg = gat_ref.BigGraph(src, dst, N_NODES, N_NODES)
+    g = torch.Generator().manual_seed(1)
+    ft = torch.randn(N_NODES, HEADS, HID, generator=g)
+    el = torch.randn(N_NODES, HEADS, generator=g)
+    er = torch.randn(N_NODES, HEADS, generator=g)
+    ee = torch.randn(n_edges, HEADS, generator=g)
+    gout = torch.randn(N_NODES, HEADS, HID, generator=g)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            out, a, z = gat_ref.gat_sparse_big_forward(bg, ft, el, er, ee, SLOPE)
+            gat_ref.gat_sparse_big_backward(bg, ft, a, z, out, gout, SLOPE)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    return {"value": n_edges / t, "unit": "edges/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"same layer math on a {n_edges}-edge uniform subsample (1/16 of the edges) over all {N_NODES} "
+                      f"nodes, fwd+bwd, {len(times)} timed steps, oracle/gat_ref.py gat_sparse_big_* "
+                      f"(segment_reduce + per-head sparse CSR matmul), torch {torch.__version__} CPU",
+            "ms_per_step": t * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_port_run(args.steps, max(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "edges/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(), "sampled_edges_per_step": CPU_SAMPLE_EDGES},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+
+    import bot_b200
+    from bot_b200 import _lib, functional
+    from bot_b200.functional import gat_fused
+    from bot_b200.ogbn_proteins import GATConv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl ours) needs a CUDA device: bot_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_nodes, n_edges = args.nodes, args.edges
+    src, dst = synth_edges(n_nodes, n_edges, dev, seed=0)
+    gen = torch.Generator(device=dev).manual_seed(1)
+
+    if world == 1:
+        graph = bot_b200.Graph(src, dst, n_nodes)
+        graph.create_formats_()
+        layer = None
+    else:
+        from bot_b200 import partition
+
+        full = bot_b200.Graph(src, dst, n_nodes)
+        layer = partition.PartitionedGraph(full, world, rank)
+        graph = layer.local
+        del full
+    del src, dst
+    E_local = graph.number_of_edges()
+    n_src_l, n_dst_l = graph.number_of_src_nodes(), graph.number_of_dst_nodes()
+
+    # ---------------- device-resident leg (value) ----------------
+    n_own = n_dst_l if world > 1 else n_nodes
+    ft_own = torch.randn(n_own, HEADS, HID, device=dev, generator=gen).requires_grad_(True)
+    el_own = torch.randn(n_own, HEADS, device=dev, generator=gen).requires_grad_(True)
+    er = torch.randn(n_dst_l, HEADS, device=dev, generator=gen).requires_grad_(True)
+    ee = torch.randn(E_local, HEADS, device=dev, generator=gen).requires_grad_(True)
+    gout = torch.randn(n_dst_l, HEADS, HID, device=dev, generator=gen)
+
+    def step_resident():
+        keep = (torch.rand(E_local, device=dev) >= EDGE_DROP).to(torch.uint8)
+        if world == 1:
+            out = gat_fused(graph, ft_own, el_own, er, ee, keep, None, None, None, SLOPE, 0.0, 0)
+        else:
+            ft_all, el_all = layer.halo_gather(ft_own, el_own)
+            out = gat_fused(graph, ft_all, el_all, er, ee, keep, None, None, None, SLOPE, 0.0, 0)
+        out.backward(gout)
+        for t in (ft_own, el_own, er, ee):
+            t.grad = None
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    launches0 = lib.botgat_launch_count()
+    kt = functional.KernelTimer()
+    functional.timer = kt
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    functional.timer = None
+    clocks = sampler.stop() if rank == 0 else None
+    launches = lib.botgat_launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = n_edges / (ms_step * 1e-3)
+    ktot = kt.totals()
+
+    # roofline of the dominant kernel (largest share of the timed region)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md); MEASURED_PEAKS.json absent"
+    bf, bb = algorithmic_bytes(E_local, n_src_l, n_dst_l, HEADS, HID)
+    # backward bytes split by pass (first bracket = dst pass over the in-CSR, second = src pass)
+    R, h = 4 * HEADS * HID, 4 * HEADS
+    b_dst = E_local * (4 + h + R + (h + 4) + h) + n_dst_l * (8 + R + 2 * h + 2 * h)
+    b_src = bb - b_dst
+    alg = {"gat_fwd": bf, "gat_bwd_src": b_src, "gat_bwd_dst": b_dst}
+    kernels = {}
+    for name, (n, tot) in ktot.items():
+        avg = tot / n
+        k = {"launches": n, "avg_ms": round(avg, 4), "share_of_step": round(tot / ms_total, 4)}
+        if name in alg:
+            k["algorithmic_bytes"] = alg[name]
+            k["achieved_GBs"] = round(alg[name] / (avg * 1e-3) / 1e9, 1)
+            k["frac_of_peak"] = round(k["achieved_GBs"] / peak, 4)
+        kernels[name] = k
+    dom = max((n for n in kernels if n in alg), key=lambda n: kernels[n]["avg_ms"] * kernels[n]["launches"])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(dom)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_GBs"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["frac_of_peak"], "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg[dom],
+                "whole_step": {"algorithmic_bytes": bf + bb,
+                               "achieved_GBs": round((bf + bb) / (ms_step * 1e-3) / 1e9, 1),
+                               "frac": round((bf + bb) / (ms_step * 1e-3) / 1e9 / peak, 4)}}
+
+    del ft_own, el_own, er, ee, gout
+    torch.cuda.empty_cache()
+
+    # ---------------- end-to-end leg through GATConv.forward with host buffers ----------------
+    e2e = None
+    if world == 1:
+        torch.manual_seed(0)
+        conv = GATConv(HEADS * HID, EDGE_EMB, HID, n_heads=HEADS, edge_drop=EDGE_DROP).to(dev)
+        conv.train()
+        h_host = torch.randn(n_nodes, HEADS * HID).pin_memory()
+        fe_host = torch.randn(n_edges, EDGE_EMB).pin_memory()
+        h2d = h_host.numel() * 4 + fe_host.numel() * 4
+
+        def step_e2e():
+            h = h_host.to(dev, non_blocking=True).requires_grad_(True)
+            fe = fe_host.to(dev, non_blocking=True).requires_grad_(True)
+            y = conv(graph, h, fe)
+            loss = y.square().mean()
+            loss.backward()
+            conv.zero_grad(set_to_none=True)
+            return float(loss.item())  # device -> host read of the step's result
+
+        for _ in range(max(1, min(args.warmup, 3))):
+            step_e2e()
+        torch.cuda.synchronize()
+        k_e2e = max(1, min(args.steps, 5))
+        e0.record()
+        for _ in range(k_e2e):
+            step_e2e()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_e2e = e0.elapsed_time(e1) / k_e2e
+        e2e = {"value": n_edges / (ms_e2e * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+               "ms_per_step": round(ms_e2e, 3), "steps": k_e2e,
+               "call": "bot_b200.ogbn_proteins.GATConv.forward(graph, feat_src, feat_edge) + backward; feat_src (N,480) and "
+                       "feat_edge (E,16) copied from pinned host memory every step, loss read back; graph structure resident "
+                       "(the reference moves the graph once, run.py:539); includes the five nn.Linear projections"}
+        del conv, h_host, fe_host
+        torch.cuda.empty_cache()
+    else:
+        e2e = {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "note": "end-to-end host-buffer leg is measured at N=1 only; at N>1 this repeats the device-resident value"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_port_run(steps=2, warmup=1)
+        cpu_baseline = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(n_nodes, n_edges), "l2": "inputs_exceed_l2 (no flush between iterations: "
+                       "the per-step working set, >= 2.5 GB, is 20x the 126 MB L2)",
+                       "parallelism": "single GPU" if world == 1 else f"1-D dst-row partition x{world}, halo all-gather + "
+                       "gradient reduce-scatter (NCCL)",
+                       "timed": "edge-drop mask draw + edge staging + fused fwd + bwd (node/src/dst passes) + edge unstage"},
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nodes", type=int, default=N_NODES)
+    ap.add_argument("--edges", type=int, default=N_EDGES)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -45,7 +45,7 @@ class BwdArgs(C.Structure):
         ("H", C.c_int32), ("D", C.c_int32),
         ("ld_ft", C.c_int64), ("ld_out", C.c_int64), ("ld_gft", C.c_int64),
         ("ft", c_vp), ("el", c_vp), ("er", c_vp), ("eb_in", c_vp), ("eb_out", c_vp),
-        ("Hb", C.c_int32), ("col_parts", C.c_int32),
+        ("Hb", C.c_int32), ("phases", C.c_int32),
         ("am_in", c_vp), ("am_out", c_vp), ("src_scale", c_vp), ("dst_scale", c_vp),
         ("slope", C.c_float), ("attn_p", C.c_float), ("seed", C.c_uint64),
         ("out", c_vp), ("row_max", c_vp), ("row_sum", c_vp), ("gout", c_vp),
@@ -58,6 +58,7 @@ class BwdArgs(C.Structure):
 SIGNATURES = {
     "botgat_abi_version": (C.c_int, []),
     "botgat_last_error": (C.c_char_p, []),
+    "botgat_launch_count": (C.c_int64, []),
     "botgat_graph_create": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, c_vp, c_vp, C.c_int, c_vp, C.POINTER(c_vp)]),
     "botgat_graph_destroy": (None, [c_vp]),
     "botgat_graph_get": (C.c_int, [c_vp, C.c_int, C.POINTER(c_vp), c_i64p]),

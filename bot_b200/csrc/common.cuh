@@ -1,6 +1,7 @@
 // Shared host/device helpers for libbotgat (sm_100a only).
 #pragma once
 
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -10,6 +11,8 @@
 namespace botgat {
 
 void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;  // kernels launched by this library (botgat_launch_count)
+#define BG_LAUNCHED(n) (::botgat::g_launches.fetch_add(n, std::memory_order_relaxed))
 
 #define BG_CHECK(expr)                                                                  \
   do {                                                                                  \

@@ -252,13 +252,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) gat_bwd_dst_kernel(const 
 
 #define BG_VPL_SWITCH(KERNEL, VW)                                                        \
   switch (vpl) {                                                                         \
-    case 1: KERNEL<VW, 1><<<grid, block, 0, st>>>(p); break;                             \
-    case 2: KERNEL<VW, 2><<<grid, block, 0, st>>>(p); break;                             \
-    case 3: KERNEL<VW, 3><<<grid, block, 0, st>>>(p); break;                             \
-    case 4: KERNEL<VW, 4><<<grid, block, 0, st>>>(p); break;                             \
-    case 5: KERNEL<VW, 5><<<grid, block, 0, st>>>(p); break;                             \
-    case 6: KERNEL<VW, 6><<<grid, block, 0, st>>>(p); break;                             \
-    case 8: KERNEL<VW, 8><<<grid, block, 0, st>>>(p); break;                             \
+    case 1: KERNEL<VW, 1><<<grid, block, 0, st>>>(p); BG_LAUNCHED(1); break;                             \
+    case 2: KERNEL<VW, 2><<<grid, block, 0, st>>>(p); BG_LAUNCHED(1); break;                             \
+    case 3: KERNEL<VW, 3><<<grid, block, 0, st>>>(p); BG_LAUNCHED(1); break;                             \
+    case 4: KERNEL<VW, 4><<<grid, block, 0, st>>>(p); BG_LAUNCHED(1); break;                             \
+    case 5: KERNEL<VW, 5><<<grid, block, 0, st>>>(p); BG_LAUNCHED(1); break;                             \
+    case 6: KERNEL<VW, 6><<<grid, block, 0, st>>>(p); BG_LAUNCHED(1); break;                             \
+    case 8: KERNEL<VW, 8><<<grid, block, 0, st>>>(p); BG_LAUNCHED(1); break;                             \
     default: set_error("backward: unsupported vectors-per-lane %d", vpl); return -1;     \
   }
 
@@ -297,12 +297,13 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
   cudaStream_t st = (cudaStream_t)stream;
   dim3 block(kWarpsPerBlock * 32);
 
+  const int phases = a->phases ? a->phases : 7;
   // node pass
-  {
+  if (phases & 1) {
     dim3 grid((unsigned)((g->n_dst + kWarpsPerBlock - 1) / kWarpsPerBlock));
     gat_bwd_node_kernel<<<grid, block, 0, st>>>((int)g->n_dst, a->H, a->D, a->ld_out, a->out, a->gout, a->er,
                                                 a->row_max, a->row_sum, a->dst_scale, (float4*)a->drec,
-                                                a->dst_scale ? a->gprime : nullptr);
+                                                a->dst_scale ? a->gprime : nullptr); BG_LAUNCHED(1);
     BG_CHECK(cudaGetLastError());
   }
   const float* gp = a->dst_scale ? a->gprime : a->gout;
@@ -315,7 +316,7 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
   p.grad_ft = a->grad_ft; p.grad_el = a->grad_el; p.grad_er = a->grad_er; p.gz = a->gz;
 
   // src pass (out-CSR): the gathered table is g' (ld_out), the row-local one is ft
-  {
+  if (phases & 2) {
     Tiling t = choose_tiling(a->D, a->ld_out, a->ld_ft, gp, a->ft, 1, g->n_dst, 8);
     // grad_ft stores use the same vector width
     if ((a->ld_gft % t.vw) != 0 || ((uintptr_t)a->grad_ft % (t.vw * 4)) != 0)
@@ -331,7 +332,7 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
     BG_CHECK(cudaGetLastError());
   }
   // dst pass (in-CSR), only when something needs it
-  if (a->grad_er || a->gz) {
+  if ((phases & 4) && (a->grad_er || a->gz)) {
     Tiling t = choose_tiling(a->D, a->ld_ft, a->ld_out, a->ft, gp, 1, g->n_src, 8);
     BG_REQUIRE(t.col_parts == 1, "backward: D=%d too wide for one pass (max %d)", a->D, 32 * 8 * t.vw);
     p.indptr = g->in_indptr; p.indices = g->in_indices; p.eid = g->in_eid;

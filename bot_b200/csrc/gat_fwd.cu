@@ -145,13 +145,13 @@ template <int VW>
 static int launch_fwd_vw(const FwdParams& p, int vpl, dim3 grid, cudaStream_t st) {
   dim3 block(kWarpsPerBlock * 32);
   switch (vpl) {
-    case 1: gat_fwd_kernel<VW, 1><<<grid, block, 0, st>>>(p); break;
-    case 2: gat_fwd_kernel<VW, 2><<<grid, block, 0, st>>>(p); break;
-    case 3: gat_fwd_kernel<VW, 3><<<grid, block, 0, st>>>(p); break;
-    case 4: gat_fwd_kernel<VW, 4><<<grid, block, 0, st>>>(p); break;
-    case 5: gat_fwd_kernel<VW, 5><<<grid, block, 0, st>>>(p); break;
-    case 6: gat_fwd_kernel<VW, 6><<<grid, block, 0, st>>>(p); break;
-    case 8: gat_fwd_kernel<VW, 8><<<grid, block, 0, st>>>(p); break;
+    case 1: gat_fwd_kernel<VW, 1><<<grid, block, 0, st>>>(p); BG_LAUNCHED(1); break;
+    case 2: gat_fwd_kernel<VW, 2><<<grid, block, 0, st>>>(p); BG_LAUNCHED(1); break;
+    case 3: gat_fwd_kernel<VW, 3><<<grid, block, 0, st>>>(p); BG_LAUNCHED(1); break;
+    case 4: gat_fwd_kernel<VW, 4><<<grid, block, 0, st>>>(p); BG_LAUNCHED(1); break;
+    case 5: gat_fwd_kernel<VW, 5><<<grid, block, 0, st>>>(p); BG_LAUNCHED(1); break;
+    case 6: gat_fwd_kernel<VW, 6><<<grid, block, 0, st>>>(p); BG_LAUNCHED(1); break;
+    case 8: gat_fwd_kernel<VW, 8><<<grid, block, 0, st>>>(p); BG_LAUNCHED(1); break;
     default: set_error("forward: unsupported vectors-per-lane %d", vpl); return -1;
   }
   return 0;

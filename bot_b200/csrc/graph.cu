@@ -6,6 +6,7 @@
 // stable LSD radix sort (CUB) keyed on the row id with the edge id as payload.
 #include <cub/cub.cuh>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -15,6 +16,7 @@
 namespace botgat {
 
 static thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -155,14 +157,14 @@ static int build_csr(int64_t n_rows, int64_t n_edges, const int32_t* key, const 
     void* tmp = nullptr;
     BG_CHECK(cudaMallocAsync(&tmp, tmp_bytes, st));
     BG_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key, key_sorted_tmp, iota, eid, (int)n_edges, 0,
-                                             bits_for(n_rows), st));
+                                             bits_for(n_rows), st)); BG_LAUNCHED(1);
     BG_CHECK(cudaFreeAsync(tmp, st));
-    k_gather_i32<<<grid_for(n_edges), 256, 0, st>>>(n_edges, other, eid, indices);
+    k_gather_i32<<<grid_for(n_edges), 256, 0, st>>>(n_edges, other, eid, indices); BG_LAUNCHED(1);
     BG_CHECK(cudaGetLastError());
   }
   BG_CHECK(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (n_rows + 1), st));  // deg has n_rows+1 slots (scan input)
   if (n_edges > 0) {
-    k_histogram<<<grid_for(n_edges), 256, 0, st>>>(n_edges, key, deg);
+    k_histogram<<<grid_for(n_edges), 256, 0, st>>>(n_edges, key, deg); BG_LAUNCHED(1);
     BG_CHECK(cudaGetLastError());
   }
   {
@@ -170,7 +172,7 @@ static int build_csr(int64_t n_rows, int64_t n_edges, const int32_t* key, const 
     BG_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, deg, indptr, (int)(n_rows + 1), st));
     void* tmp = nullptr;
     BG_CHECK(cudaMallocAsync(&tmp, tmp_bytes, st));
-    BG_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, deg, indptr, (int)(n_rows + 1), st));
+    BG_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, deg, indptr, (int)(n_rows + 1), st)); BG_LAUNCHED(1);
     BG_CHECK(cudaFreeAsync(tmp, st));
   }
   return 0;
@@ -182,6 +184,7 @@ using namespace botgat;
 
 extern "C" int botgat_abi_version(void) { return BOTGAT_ABI_VERSION; }
 extern "C" const char* botgat_last_error(void) { return g_err; }
+extern "C" int64_t botgat_launch_count(void) { return (int64_t)g_launches.load(); }
 
 extern "C" void botgat_graph_destroy(botgat_graph* g) {
   if (!g) return;
@@ -227,16 +230,16 @@ extern "C" int botgat_graph_create(int64_t n_src, int64_t n_dst, int64_t n_edges
   BG_CHECK(cudaMallocAsync(&flags, sizeof(int) * 5, st));
   BG_CHECK(cudaMemsetAsync(flags, 0, sizeof(int) * 5, st));
   if (n_edges > 0) {
-    k_narrow_and_check<<<grid_for(n_edges), 256, 0, st>>>(n_edges, src, n_src, src32, iota, flags);
-    k_narrow_and_check<<<grid_for(n_edges), 256, 0, st>>>(n_edges, dst, n_dst, dst32, nullptr, flags);
+    k_narrow_and_check<<<grid_for(n_edges), 256, 0, st>>>(n_edges, src, n_src, src32, iota, flags); BG_LAUNCHED(1);
+    k_narrow_and_check<<<grid_for(n_edges), 256, 0, st>>>(n_edges, dst, n_dst, dst32, nullptr, flags); BG_LAUNCHED(1);
     BG_CHECK(cudaGetLastError());
   }
   int rc = build_csr(n_dst, n_edges, dst32, src32, iota, ktmp, g->in_indptr, g->in_indices, g->in_eid, g->in_deg, st);
   if (rc) return rc;
   rc = build_csr(n_src, n_edges, src32, dst32, iota, ktmp, g->out_indptr, g->out_indices, g->out_eid, g->out_deg, st);
   if (rc) return rc;
-  if (n_dst > 0) k_deg_stats<<<grid_for(n_dst), 256, 0, st>>>(n_dst, g->in_deg, flags + 1);
-  if (n_src > 0) k_deg_stats<<<grid_for(n_src), 256, 0, st>>>(n_src, g->out_deg, flags + 3);
+  if (n_dst > 0) k_deg_stats<<<grid_for(n_dst), 256, 0, st>>>(n_dst, g->in_deg, flags + 1); BG_LAUNCHED(1);
+  if (n_src > 0) k_deg_stats<<<grid_for(n_src), 256, 0, st>>>(n_src, g->out_deg, flags + 3); BG_LAUNCHED(1);
   BG_CHECK(cudaGetLastError());
   int h[5];
   BG_CHECK(cudaMemcpyAsync(h, flags, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -329,7 +332,7 @@ extern "C" int botgat_coo_to_bidirected(int64_t n_nodes, int64_t n_edges, const 
   BG_CHECK(cudaMallocAsync(&d_count, sizeof(int64_t), st));
   BG_CHECK(cudaMallocAsync(&bad, sizeof(int), st));
   BG_CHECK(cudaMemsetAsync(bad, 0, sizeof(int), st));
-  k_pack_bidirected<<<grid_for(n_edges), 256, 0, st>>>(n_edges, src, dst, n_nodes, keys, bad);
+  k_pack_bidirected<<<grid_for(n_edges), 256, 0, st>>>(n_edges, src, dst, n_nodes, keys, bad); BG_LAUNCHED(1);
   BG_CHECK(cudaGetLastError());
   const int bits = std::min(64, 2 * bits_for(n_nodes) + 1);
   size_t tb = 0, tb2 = 0;
@@ -337,15 +340,15 @@ extern "C" int botgat_coo_to_bidirected(int64_t n_nodes, int64_t n_edges, const 
   BG_CHECK(cub::DeviceSelect::Unique(nullptr, tb2, sorted, uniq, d_count, (int)n2, st));
   void* tmp = nullptr;
   BG_CHECK(cudaMallocAsync(&tmp, std::max(tb, tb2), st));
-  BG_CHECK(cub::DeviceRadixSort::SortKeys(tmp, tb, keys, sorted, (int)n2, 0, bits, st));
-  BG_CHECK(cub::DeviceSelect::Unique(tmp, tb2, sorted, uniq, d_count, (int)n2, st));
+  BG_CHECK(cub::DeviceRadixSort::SortKeys(tmp, tb, keys, sorted, (int)n2, 0, bits, st)); BG_LAUNCHED(1);
+  BG_CHECK(cub::DeviceSelect::Unique(tmp, tb2, sorted, uniq, d_count, (int)n2, st)); BG_LAUNCHED(1);
   int64_t cnt = 0;
   int hbad = 0;
   BG_CHECK(cudaMemcpyAsync(&cnt, d_count, sizeof(cnt), cudaMemcpyDeviceToHost, st));
   BG_CHECK(cudaMemcpyAsync(&hbad, bad, sizeof(hbad), cudaMemcpyDeviceToHost, st));
   BG_CHECK(cudaStreamSynchronize(st));
   if (!hbad && cnt > 0) {
-    k_unpack<<<grid_for(cnt), 256, 0, st>>>(cnt, uniq, n_nodes, out_src, out_dst);
+    k_unpack<<<grid_for(cnt), 256, 0, st>>>(cnt, uniq, n_nodes, out_src, out_dst); BG_LAUNCHED(1);
     BG_CHECK(cudaGetLastError());
   }
   BG_CHECK(cudaFreeAsync(tmp, st)); BG_CHECK(cudaFreeAsync(keys, st)); BG_CHECK(cudaFreeAsync(sorted, st));
@@ -369,14 +372,14 @@ extern "C" int botgat_coo_remove_self_loop(int64_t n_edges, const int64_t* src, 
   int64_t* d_count = nullptr;
   BG_CHECK(cudaMallocAsync(&flag, n_edges, st));
   BG_CHECK(cudaMallocAsync(&d_count, sizeof(int64_t), st));
-  k_flag_not_loop<<<grid_for(n_edges), 256, 0, st>>>(n_edges, src, dst, flag);
+  k_flag_not_loop<<<grid_for(n_edges), 256, 0, st>>>(n_edges, src, dst, flag); BG_LAUNCHED(1);
   BG_CHECK(cudaGetLastError());
   size_t tb = 0;
   BG_CHECK(cub::DeviceSelect::Flagged(nullptr, tb, src, flag, out_src, d_count, (int)n_edges, st));
   void* tmp = nullptr;
   BG_CHECK(cudaMallocAsync(&tmp, tb, st));
-  BG_CHECK(cub::DeviceSelect::Flagged(tmp, tb, src, flag, out_src, d_count, (int)n_edges, st));
-  BG_CHECK(cub::DeviceSelect::Flagged(tmp, tb, dst, flag, out_dst, d_count, (int)n_edges, st));
+  BG_CHECK(cub::DeviceSelect::Flagged(tmp, tb, src, flag, out_src, d_count, (int)n_edges, st)); BG_LAUNCHED(1);
+  BG_CHECK(cub::DeviceSelect::Flagged(tmp, tb, dst, flag, out_dst, d_count, (int)n_edges, st)); BG_LAUNCHED(1);
   int64_t cnt = 0;
   BG_CHECK(cudaMemcpyAsync(&cnt, d_count, sizeof(cnt), cudaMemcpyDeviceToHost, st));
   BG_CHECK(cudaFreeAsync(tmp, st)); BG_CHECK(cudaFreeAsync(flag, st)); BG_CHECK(cudaFreeAsync(d_count, st));
@@ -395,7 +398,7 @@ extern "C" int botgat_coo_add_self_loop(int64_t n_nodes, int64_t n_edges, const 
     BG_CHECK(cudaMemcpyAsync(out_dst, dst, sizeof(int64_t) * n_edges, cudaMemcpyDeviceToDevice, st));
   }
   if (n_nodes > 0) {
-    k_iota64<<<grid_for(n_nodes), 256, 0, st>>>(n_nodes, out_src + n_edges, out_dst + n_edges);
+    k_iota64<<<grid_for(n_nodes), 256, 0, st>>>(n_nodes, out_src + n_edges, out_dst + n_edges); BG_LAUNCHED(1);
     BG_CHECK(cudaGetLastError());
   }
   return 0;
@@ -444,17 +447,18 @@ extern "C" int botgat_edge_stage(const botgat_graph* g, int order, int32_t H, co
   DeviceGuard guard(g->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int32_t* eid = order == BOTGAT_ORDER_IN ? g->in_eid : g->out_eid;
-  k_edge_stage<<<grid_for(g->n_edges), 256, 0, st>>>(g->n_edges, H, ee ? H : 1, eid, ee, keep, attn_mul, eb, am);
+  k_edge_stage<<<grid_for(g->n_edges), 256, 0, st>>>(g->n_edges, H, ee ? H : 1, eid, ee, keep, attn_mul, eb, am); BG_LAUNCHED(1);
   BG_CHECK(cudaGetLastError());
   return 0;
 }
 
 extern "C" int botgat_edge_unstage(const botgat_graph* g, int32_t H, const float* gz, float* grad_ee, void* stream) {
-  BG_REQUIRE(g && H > 0 && gz && grad_ee, "edge_unstage: bad arguments");
+  BG_REQUIRE(g && H > 0, "edge_unstage: bad arguments");
   if (g->n_edges == 0) return 0;
+  BG_REQUIRE(gz && grad_ee, "edge_unstage: null gz/grad_ee");
   DeviceGuard guard(g->device);
   cudaStream_t st = (cudaStream_t)stream;
-  k_edge_unstage<<<grid_for(g->n_edges), 256, 0, st>>>(g->n_edges, H, g->in_eid, gz, grad_ee);
+  k_edge_unstage<<<grid_for(g->n_edges), 256, 0, st>>>(g->n_edges, H, g->in_eid, gz, grad_ee); BG_LAUNCHED(1);
   BG_CHECK(cudaGetLastError());
   return 0;
 }
@@ -539,7 +543,7 @@ extern "C" int botgat_partition_1d(const botgat_graph* g, int32_t n_parts, int64
   cudaStream_t st = (cudaStream_t)stream;
   int64_t* d = nullptr;
   BG_CHECK(cudaMallocAsync(&d, sizeof(int64_t) * (n_parts + 1), st));
-  k_partition_bounds<<<(n_parts + 1 + 127) / 128, 128, 0, st>>>((int)g->n_dst, g->in_indptr, n_parts, g->n_edges, d);
+  k_partition_bounds<<<(n_parts + 1 + 127) / 128, 128, 0, st>>>((int)g->n_dst, g->in_indptr, n_parts, g->n_edges, d); BG_LAUNCHED(1);
   BG_CHECK(cudaGetLastError());
   BG_CHECK(cudaMemcpyAsync(bounds, d, sizeof(int64_t) * (n_parts + 1), cudaMemcpyDeviceToHost, st));
   BG_CHECK(cudaFreeAsync(d, st));
@@ -573,10 +577,10 @@ extern "C" int botgat_partition_extract(const botgat_graph* g, int64_t lo, int64
   BG_CHECK(cub::DeviceRadixSort::SortKeys(nullptr, tb, g->in_eid + span[0], sel, (int)cnt, 0, bits_for(g->n_edges), st));
   void* tmp = nullptr;
   BG_CHECK(cudaMallocAsync(&tmp, tb, st));
-  BG_CHECK(cub::DeviceRadixSort::SortKeys(tmp, tb, g->in_eid + span[0], sel, (int)cnt, 0, bits_for(g->n_edges), st));
+  BG_CHECK(cub::DeviceRadixSort::SortKeys(tmp, tb, g->in_eid + span[0], sel, (int)cnt, 0, bits_for(g->n_edges), st)); BG_LAUNCHED(1);
   k_expand_rows<<<grid_for(g->n_dst * 32), 256, 0, st>>>((int)g->n_dst, g->in_indptr, g->in_eid, g->in_indices,
-                                                        dst_by_eid, src_by_eid);
-  k_extract_write<<<grid_for(cnt), 256, 0, st>>>(cnt, sel, src_by_eid, dst_by_eid, lo, out_eid, out_src, out_ldst);
+                                                        dst_by_eid, src_by_eid); BG_LAUNCHED(1);
+  k_extract_write<<<grid_for(cnt), 256, 0, st>>>(cnt, sel, src_by_eid, dst_by_eid, lo, out_eid, out_src, out_ldst); BG_LAUNCHED(1);
   BG_CHECK(cudaGetLastError());
   BG_CHECK(cudaFreeAsync(tmp, st)); BG_CHECK(cudaFreeAsync(sel, st));
   BG_CHECK(cudaFreeAsync(dst_by_eid, st)); BG_CHECK(cudaFreeAsync(src_by_eid, st));
@@ -588,7 +592,7 @@ extern "C" int botgat_rows_gather(const float* table, int64_t ld, int64_t width,
                                   float* out, void* stream) {
   if (n_rows == 0 || width == 0) return 0;
   BG_REQUIRE(table && rows && out, "rows_gather: null pointer");
-  k_rows_gather<<<grid_for(n_rows * width), 256, 0, (cudaStream_t)stream>>>(table, ld, width, rows, n_rows, out);
+  k_rows_gather<<<grid_for(n_rows * width), 256, 0, (cudaStream_t)stream>>>(table, ld, width, rows, n_rows, out); BG_LAUNCHED(1);
   BG_CHECK(cudaGetLastError());
   return 0;
 }
@@ -597,7 +601,7 @@ extern "C" int botgat_rows_scatter_add(float* table, int64_t ld, int64_t width, 
                                        const float* in, void* stream) {
   if (n_rows == 0 || width == 0) return 0;
   BG_REQUIRE(table && rows && in, "rows_scatter_add: null pointer");
-  k_rows_scatter_add<<<grid_for(n_rows * width), 256, 0, (cudaStream_t)stream>>>(table, ld, width, rows, n_rows, in);
+  k_rows_scatter_add<<<grid_for(n_rows * width), 256, 0, (cudaStream_t)stream>>>(table, ld, width, rows, n_rows, in); BG_LAUNCHED(1);
   BG_CHECK(cudaGetLastError());
   return 0;
 }

@@ -15,6 +15,49 @@ from . import _lib
 from .graph import Graph, _stream
 
 
+class KernelTimer:
+    """Optional per-ABI-call device timing (CUDA events on the launching stream).
+    ``bench.py`` installs one to get the per-kernel durations its roofline needs;
+    when installed, the backward passes are issued as three separate ABI calls."""
+
+    def __init__(self):
+        self.events = []  # (name, start, end)
+
+    def span(self, name):
+        return _Span(self, name)
+
+    def totals(self):
+        """{name: (n_calls, total_ms)}; call after torch.cuda.synchronize()."""
+        out = {}
+        for name, s, e in self.events:
+            n, t = out.get(name, (0, 0.0))
+            out[name] = (n + 1, t + s.elapsed_time(e))
+        return out
+
+
+class _Span:
+    def __init__(self, timer, name):
+        self.timer, self.name = timer, name
+
+    def __enter__(self):
+        if self.timer is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+
+    def __exit__(self, *exc):
+        if self.timer is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.timer.events.append((self.name, self.s, e))
+
+
+timer = None  # set to a KernelTimer to record
+
+
+def _span(name):
+    return _Span(timer, name)
+
+
 def _f32c(t, name):
     if t is None:
         return None
@@ -39,8 +82,9 @@ def edge_stage(graph: Graph, order, H, ee=None, keep=None, attn_mul=None):
         am = torch.empty((H, E), dtype=torch.float32, device=dev)
     if eb is None and am is None:
         return None, 0, None
-    rc = _lib.load().botgat_edge_stage(graph._ensure(), order, H, _lib.ptr(ee), _lib.ptr(keep), _lib.ptr(attn_mul),
-                                       _lib.ptr(eb), _lib.ptr(am), _stream())
+    with _span("edge_stage"):
+        rc = _lib.load().botgat_edge_stage(graph._ensure(), order, H, _lib.ptr(ee), _lib.ptr(keep), _lib.ptr(attn_mul),
+                                           _lib.ptr(eb), _lib.ptr(am), _stream())
     _lib.check(rc, "botgat_edge_stage")
     return eb, Hb, am
 
@@ -94,7 +138,9 @@ class GATFusedFn(torch.autograd.Function):
             a.dst_scale = dst_scale.data_ptr() if dst_scale is not None else None
             a.slope, a.attn_p, a.seed = float(slope), float(attn_p if attn_mul is None else 0.0), int(seed)
             a.out, a.row_max, a.row_sum = out.data_ptr(), row_max.data_ptr(), row_sum.data_ptr()
-            _lib.check(lib.botgat_gat_forward(h, C.byref(a), _stream()), "botgat_gat_forward")
+            with _span("gat_fwd"):
+                rc = lib.botgat_gat_forward(h, C.byref(a), _stream())
+            _lib.check(rc, "botgat_gat_forward")
 
         ctx.graph = graph
         ctx.cfg = (H, D, Hb, float(slope), float(a.attn_p), int(seed))
@@ -129,7 +175,7 @@ class GATFusedFn(torch.autograd.Function):
             a.er = er.data_ptr() if er is not None else None
             a.eb_in = eb_in.data_ptr() if eb_in is not None else None
             a.eb_out = eb_out.data_ptr() if eb_out is not None else None
-            a.Hb, a.col_parts = Hb, 1
+            a.Hb, a.phases = Hb, 0
             a.am_in = am_in.data_ptr() if am_in is not None else None
             a.am_out = am_out.data_ptr() if am_out is not None else None
             a.src_scale = src_scale.data_ptr() if src_scale is not None else None
@@ -141,11 +187,20 @@ class GATFusedFn(torch.autograd.Function):
             a.grad_ft, a.grad_el = grad_ft.data_ptr(), grad_el.data_ptr()
             a.grad_er = grad_er.data_ptr() if grad_er is not None else None
             a.gz = gz.data_ptr() if gz is not None else None
-            _lib.check(lib.botgat_gat_backward(h, C.byref(a), _stream()), "botgat_gat_backward")
+            if timer is None:
+                _lib.check(lib.botgat_gat_backward(h, C.byref(a), _stream()), "botgat_gat_backward")
+            else:
+                for bit, name in ((1, "gat_bwd_node"), (2, "gat_bwd_src"), (4, "gat_bwd_dst")):
+                    a.phases = bit
+                    with _span(name):
+                        rc = lib.botgat_gat_backward(h, C.byref(a), _stream())
+                    _lib.check(rc, "botgat_gat_backward")
             grad_ee = None
             if need_ee:
                 grad_ee = torch.empty((E, H), dtype=torch.float32, device=dev)
-                _lib.check(lib.botgat_edge_unstage(h, H, gz.data_ptr(), grad_ee.data_ptr(), _stream()), "botgat_edge_unstage")
+                with _span("edge_unstage"):
+                    rc = lib.botgat_edge_unstage(h, H, gz.data_ptr(), grad_ee.data_ptr(), _stream())
+                _lib.check(rc, "botgat_edge_unstage")
         return None, grad_ft, grad_el, grad_er, grad_ee, None, None, None, None, None, None, None
 
 

@@ -34,7 +34,7 @@ class _DevArray:
     """int32 device array exposed through ``__cuda_array_interface__``."""
 
     def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, True), "version": 2}
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
 
 
 class Graph:

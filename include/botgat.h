@@ -37,6 +37,8 @@ typedef struct botgat_graph botgat_graph;
 
 int botgat_abi_version(void);
 const char* botgat_last_error(void);
+/* number of CUDA kernels this library has launched so far in this process (CUB passes count as one each) */
+int64_t botgat_launch_count(void);
 
 /* ------------------------------------------------------------------------
  * Graph ingestion.
@@ -169,8 +171,8 @@ typedef struct {
   const float* eb_in;     /* (Hb, n_edges) in-CSR order or NULL */
   const float* eb_out;    /* (Hb, n_edges) out-CSR order or NULL */
   int32_t Hb;
-  int32_t col_parts;
-  const float* am_in;     /* (H, n_edges) or NULL */
+  int32_t phases;         /* bitmask of passes to run: 1 node, 2 src, 4 dst; 0 = all (profiling splits them) */
+  const float* am_in;    /* (H, n_edges) or NULL */
   const float* am_out;    /* (H, n_edges) or NULL */
   const float* src_scale;
   const float* dst_scale;
