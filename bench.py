@@ -269,7 +269,10 @@ def run_ours(args):
     R, h = 4 * HEADS * HID, 4 * HEADS
     b_dst = E_local * (4 + h + R + (h + 4) + h) + n_dst_l * (8 + R + 2 * h + 2 * h)
     b_src = bb - b_dst
-    alg = {"gat_fwd": bf, "gat_bwd_src": b_src, "gat_bwd_dst": b_dst}
+    # the dst-major re-gather of the reference's backward (b_dst) is eliminated algorithmically: the src pass
+    # produces the per-edge dot products from the rows it gathers anyway.  Per-kernel rooflines count only
+    # the bytes of the kernel's own gather; `whole_step` keeps SURVEY's full fwd+bwd figure.
+    alg = {"gat_fwd": bf, "gat_bwd_src": b_src}
     kernels = {}
     for name, (n, tot) in ktot.items():
         avg = tot / n

@@ -44,13 +44,13 @@ class BwdArgs(C.Structure):
     _fields_ = [
         ("H", C.c_int32), ("D", C.c_int32),
         ("ld_ft", C.c_int64), ("ld_out", C.c_int64), ("ld_gft", C.c_int64),
-        ("ft", c_vp), ("el", c_vp), ("er", c_vp), ("eb_in", c_vp), ("eb_out", c_vp),
+        ("ft", c_vp), ("el", c_vp), ("er", c_vp), ("eb_out", c_vp),
         ("Hb", C.c_int32), ("phases", C.c_int32),
-        ("am_in", c_vp), ("am_out", c_vp), ("src_scale", c_vp), ("dst_scale", c_vp),
+        ("am_out", c_vp), ("src_scale", c_vp), ("dst_scale", c_vp),
         ("slope", C.c_float), ("attn_p", C.c_float), ("seed", C.c_uint64),
         ("out", c_vp), ("row_max", c_vp), ("row_sum", c_vp), ("gout", c_vp),
-        ("drec", c_vp), ("gprime", c_vp),
-        ("grad_ft", c_vp), ("grad_el", c_vp), ("grad_er", c_vp), ("gz", c_vp),
+        ("drec", c_vp), ("gprime", c_vp), ("gz", c_vp),
+        ("grad_ft", c_vp), ("grad_el", c_vp), ("grad_ee", c_vp), ("grad_er", c_vp),
     ]
 
 
@@ -67,7 +67,7 @@ SIGNATURES = {
     "botgat_coo_remove_self_loop": (C.c_int, [C.c_int64, c_vp, c_vp, c_vp, c_vp, c_i64p, C.c_int, c_vp]),
     "botgat_coo_add_self_loop": (C.c_int, [C.c_int64, C.c_int64, c_vp, c_vp, c_vp, c_vp, C.c_int, c_vp]),
     "botgat_edge_stage": (C.c_int, [c_vp, C.c_int, C.c_int32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "botgat_edge_unstage": (C.c_int, [c_vp, C.c_int32, c_vp, c_vp, c_vp]),
+    "botgat_edge_unstage": (C.c_int, [c_vp, C.c_int, C.c_int32, c_vp, c_vp, c_vp]),
     "botgat_gat_forward": (C.c_int, [c_vp, C.POINTER(FwdArgs), c_vp]),
     "botgat_gat_backward": (C.c_int, [c_vp, C.POINTER(BwdArgs), c_vp]),
     "botgat_partition_1d": (C.c_int, [c_vp, C.c_int32, c_i64p, c_vp]),

@@ -105,10 +105,14 @@ __device__ __forceinline__ float philox_dropout_mul(uint64_t seed, uint32_t eid,
 // ---------------------------------------------------------------------------
 // VW-wide vectors (VW = 4, 2, 1 floats) with read-only global loads
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg_stream4(const float* p);
+__device__ __forceinline__ float2 ldg_stream2(const float* p);
+__device__ __forceinline__ float ldg_stream1(const float* p);
 template <int VW> struct Vec;
 template <> struct Vec<4> {
   float4 v;
   __device__ __forceinline__ void load(const float* p) { v = __ldg(reinterpret_cast<const float4*>(p)); }
+  __device__ __forceinline__ void load_stream(const float* p) { v = ldg_stream4(p); }
   __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
   __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
   __device__ __forceinline__ void fma(float w, const Vec& o) {
@@ -127,6 +131,7 @@ template <> struct Vec<4> {
 template <> struct Vec<2> {
   float2 v;
   __device__ __forceinline__ void load(const float* p) { v = __ldg(reinterpret_cast<const float2*>(p)); }
+  __device__ __forceinline__ void load_stream(const float* p) { v = ldg_stream2(p); }
   __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float2*>(p) = v; }
   __device__ __forceinline__ void zero() { v = make_float2(0.f, 0.f); }
   __device__ __forceinline__ void fma(float w, const Vec& o) { v.x = fmaf(w, o.v.x, v.x); v.y = fmaf(w, o.v.y, v.y); }
@@ -142,6 +147,7 @@ template <> struct Vec<2> {
 template <> struct Vec<1> {
   float v;
   __device__ __forceinline__ void load(const float* p) { v = __ldg(p); }
+  __device__ __forceinline__ void load_stream(const float* p) { v = ldg_stream1(p); }
   __device__ __forceinline__ void store(float* p) const { *p = v; }
   __device__ __forceinline__ void zero() { v = 0.f; }
   __device__ __forceinline__ void fma(float w, const Vec& o) { v = fmaf(w, o.v, v); }
@@ -151,7 +157,7 @@ template <> struct Vec<1> {
 };
 
 // ---------------------------------------------------------------------------
-// Work decomposition shared by forward and both backward passes.
+// Work decomposition shared by the forward and the backward gather pass.
 //
 // A work item is (head h, column part cp, CSR row r) and is owned by one warp.
 // Items are ordered head-major, then column part, then row, so that all warps
@@ -159,20 +165,45 @@ template <> struct Vec<1> {
 // table — a slab is sized to stay L2-resident (DESIGN.md "Slabs").
 //
 // Inside the warp, a group of G = 1<<gshift lanes serves one neighbour; lane j of
-// the group owns vectors j, j+G, j+2G, ... (VPL of them, VW floats each) of the
-// slab row, so one warp instruction covers 32/G neighbours and each group reads
-// G*VW*4 contiguous bytes.
+// the group owns vectors (i*G + j - o), i = 0..VPL-1, of the slab row (VW floats
+// each), so one warp instruction covers 32/G neighbours.  G is chosen so that one
+// group reads one 128-byte line per instruction, and `o` (lanes) shifts the
+// mapping so that each instruction's piece is line-ALIGNED even when the slab
+// starts mid-line (odd heads at D=80): an L1 wavefront then carries a full line.
 // ---------------------------------------------------------------------------
 struct Tiling {
   int vw;         // floats per vector (4, 2 or 1)
-  int vpl;        // vectors per lane
+  int vpl;        // vector slots per lane
   int gshift;     // log2(lanes per neighbour)
   int col_parts;  // parts per head
   int part_cols;  // floats per part (last part may be shorter)
+  int omask;      // lane-offset mask: o = (first vector index of the slab) & omask; 0 = no alignment shift
 };
 
-// host: choose the tiling for a (D, ld, alignment) combination
-Tiling choose_tiling(int D, int64_t ld_a, int64_t ld_b, const void* pa, const void* pb, int col_parts_req,
-                     int64_t n_rows_table, int vpl_cap);
+// host: choose the tiling.  `ld_g`/`pg` describe the GATHERED table (alignment shift is derived from it),
+// `ld_o`/`po` the row-local one (only constrains the vector width).
+Tiling choose_tiling(int H, int D, int64_t ld_g, const void* pg, int64_t ld_o, const void* po, int col_parts_req,
+                     int64_t n_rows_table);
+
+// read-only, no-L1-allocate gather loads (rows are touched once per SM: keep L1 for the index/logit streams)
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float2 ldg_stream2(const float* p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ldg_stream1(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+
+// steps (of 32/G neighbours each) whose row loads are kept in flight together
+__host__ __device__ constexpr int steps_in_flight(int vpl) { return vpl <= 1 ? 8 : vpl <= 3 ? 4 : vpl <= 6 ? 2 : 1; }
 
 }  // namespace botgat

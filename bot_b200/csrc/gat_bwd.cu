@@ -3,11 +3,16 @@
 // kernels behind src/no-sampling/models.py:523-555 and
 // src/ogbn-proteins/models.py:125-156.
 //
-//   node pass  : t[v,h] = <out[v,h,:], gout[v,h,:]>; packs drec[h][v] =
+//   node phase : t[v,h] = <out[v,h,:], gout[v,h,:]>; packs drec[h][v] =
 //                {er, row_max, 1/row_sum, t}; g' = gout * dst_scale
-//   src pass   : out-CSR (src-major)  -> grad_ft, grad_el            (always)
-//   dst pass   : in-CSR  (dst-major)  -> grad_er, gz (= grad of the edge logit
-//                term, in-CSR order)                                 (on request)
+//   src phase  : ONE gather pass over the out-CSR (src-major): grad_ft, grad_el
+//                and gz (gradient of the per-edge logit, out-CSR order)
+//   edge phase : gz -> grad_ee (edge-id order); grad_er[v] = sum over in-edges
+//
+// The reference's backward gathers E x H x D twice (SpMM on the reversed graph
+// for grad_ft, SDDMM-dot for grad_a).  Here the dot <ft[u], g'[v]> rides on the
+// rows the src pass gathers anyway (ft[u] is row-local there), so the second
+// gather disappears; what remains E-sized is the 4*H-byte-per-edge gz stream.
 //
 // Attention weights are recomputed from (el, er, eb, row_max, row_sum); nothing
 // E-sized is saved by the forward.  No atomics: every output element is produced
@@ -20,24 +25,24 @@ struct BwdParams {
   const int32_t* indptr;
   const int32_t* indices;
   const int32_t* eid;
-  int n_rows;     // rows of the CSR being walked
+  int n_rows;  // rows of the out-CSR (= n_src)
   int n_dst;
   int64_t n_edges;
   int H, D;
   int64_t ld_ft, ld_g, ld_gft;
   const float *ft, *el, *eb, *am, *cs;
-  const float* g;       // g' (n_dst, ld_g)
-  const float4* drec;   // (H, n_dst)
+  const float* g;      // g' (n_dst, ld_g)
+  const float4* drec;  // (H, n_dst)
   int Hb;
   float slope, attn_p, inv_keep;
   uint64_t seed;
-  float *grad_ft, *grad_el, *grad_er, *gz;
-  int gshift;
+  float *grad_ft, *grad_el, *gz;
+  int gshift, omask;
   int blocks_per_slab;
 };
 
 // ---------------------------------------------------------------------------
-// node pass: one warp per destination row
+// node phase: one warp per destination row
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 gat_bwd_node_kernel(int n_dst, int H, int D, int64_t ld, const float* __restrict__ out,
@@ -66,92 +71,124 @@ gat_bwd_node_kernel(int n_dst, int H, int D, int64_t ld, const float* __restrict
   }
 }
 
-// deliver a per-group value (held by every lane of group q) to lane e+q
-__device__ __forceinline__ void deliver(float part, int e, int EPS, int gshift, int lane, float& d_lane) {
-  const float got = __shfl_sync(kFull, part, ((lane - e) << gshift) & 31);
-  if (lane >= e && lane < e + EPS) d_lane = got;
-}
+// ---------------------------------------------------------------------------
+// src phase: one warp per (head, source row u) over the out-CSR
+// ---------------------------------------------------------------------------
+struct SrcOps {
+  float4 rec;  // {er[v], row_max[v], 1/row_sum[v], t[v]}
+  float eb, amul;
+};
 
-// ---------------------------------------------------------------------------
-// src pass: one warp per (head, source row u) over the out-CSR
-// ---------------------------------------------------------------------------
 template <int VW, int VPL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) gat_bwd_src_kernel(const BwdParams p) {
+  constexpr int NS = steps_in_flight(VPL);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x / p.blocks_per_slab;
   const int row = (blockIdx.x - h * p.blocks_per_slab) * kWarpsPerBlock + warp;
   if (row >= p.n_rows) return;
   const int G = 1 << p.gshift;
-  const int j = lane & (G - 1);
   const int grp = lane >> p.gshift;
   const int EPS = 32 >> p.gshift;
   const int gstride = G * VW;
+  const int v0 = (lane & (G - 1)) - (((h * p.D) / VW) & p.omask);
 
   bool act[VPL];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) act[i] = (i * G + j) * VW < p.D;
+  for (int i = 0; i < VPL; ++i) {
+    const int v = v0 + i * G;
+    act[i] = v >= 0 && v * VW < p.D;
+  }
 
   const int beg = p.indptr[row], end = p.indptr[row + 1];
   const float csu = p.cs ? p.cs[row] : 1.f;
   const float el_u = p.el[(int64_t)row * p.H + h];
   Vec<VW> fu[VPL], acc[VPL];
   {
-    const float* f = p.ft + (int64_t)row * p.ld_ft + h * p.D + j * VW;
+    const float* f = p.ft + (int64_t)row * p.ld_ft + h * p.D + v0 * VW;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       if (act[i]) { fu[i].load(f + i * gstride); fu[i].scale(csu); } else fu[i].zero();
       acc[i].zero();
     }
   }
-  const float* __restrict__ g_h = p.g + h * p.D + j * VW;
+  const float* __restrict__ g_h = p.g + h * p.D + v0 * VW;
   const float4* __restrict__ drec_h = p.drec + (int64_t)h * p.n_dst;
   const float* __restrict__ eb_h = p.eb ? p.eb + (int64_t)(p.Hb == 1 ? 0 : h) * p.n_edges : nullptr;
   const float* __restrict__ am_h = p.am ? p.am + (int64_t)h * p.n_edges : nullptr;
+  float* __restrict__ gz_h = p.gz ? p.gz + (int64_t)h * p.n_edges : nullptr;
   const bool philox = (p.am == nullptr) && p.attn_p > 0.f;
   float gel_lane = 0.f;
 
+  // 3-stage software pipeline, as in the forward: index (c+2) | records (c+1) | row gathers (c)
+  auto load_index = [&](int base) -> int {
+    const int pos = base + lane;
+    return pos < end ? __ldg(p.indices + pos) : 0;
+  };
+  auto load_operands = [&](int base, int v, SrcOps& o) {
+    const int pos = base + lane;
+    o.rec = make_float4(0.f, 0.f, 0.f, 0.f);
+    o.eb = -INFINITY;  // lanes past the row end behave like dropped edges: alpha = 0
+    o.amul = 1.f;
+    if (pos < end) {
+      o.rec = __ldg(drec_h + v);
+      o.eb = eb_h ? __ldg(eb_h + pos) : 0.f;
+      if (am_h) o.amul = __ldg(am_h + pos);
+      else if (philox) o.amul = philox_dropout_mul(p.seed, (uint32_t)__ldg(p.eid + pos), (uint32_t)h, p.attn_p, p.inv_keep);
+    }
+  };
+  int vtx0 = load_index(beg), vtx1 = load_index(beg + 32), vtx2 = 0;
+  SrcOps o0, o1;
+  load_operands(beg, vtx0, o0);
+
   for (int base = beg; base < end; base += 32) {
     const int cnt = min(32, end - base);
-    int v = 0;
-    float alpha = 0.f, amul = 1.f, dz = 0.f, t = 0.f;
-    if (lane < cnt) {
-      const int pos = base + lane;
-      v = __ldg(p.indices + pos);
-      const float4 rec = __ldg(drec_h + v);
-      float z = el_u + rec.x;
-      if (eb_h) z += __ldg(eb_h + pos);
-      const float s = leaky_relu(z, p.slope);
-      alpha = (s == -INFINITY) ? 0.f : expf(s - rec.y) * rec.z;
-      dz = z > 0.f ? 1.f : p.slope;
-      t = rec.w;
-      if (am_h) amul = __ldg(am_h + pos);
-      else if (philox) amul = philox_dropout_mul(p.seed, (uint32_t)__ldg(p.eid + pos), (uint32_t)h, p.attn_p, p.inv_keep);
-    }
-    const float w_lane = alpha * amul;
+    vtx2 = load_index(base + 64);
+    load_operands(base + 32, vtx1, o1);
+
+    // lane = neighbour: recompute the attention weight of this edge
+    const float z = el_u + o0.rec.x + o0.eb;
+    const float s = leaky_relu(z, p.slope);
+    const float alpha = (s == -INFINITY) ? 0.f : expf(s - o0.rec.y) * o0.rec.z;
+    const float dz = z > 0.f ? 1.f : p.slope;
+    const float w_lane = alpha * o0.amul;
     float d_lane = 0.f;
-    for (int e = 0; e < cnt; e += EPS) {
-      const int my = e + grp;
-      const int vv = __shfl_sync(kFull, v, my & 31);
-      const float w = __shfl_sync(kFull, w_lane, my & 31);
-      float part = 0.f;
-      if (my < cnt) {
+
+    for (int e = 0; e < cnt; e += NS * EPS) {
+      Vec<VW> x[NS][VPL];
+      float w[NS];
+#pragma unroll
+      for (int s_ = 0; s_ < NS; ++s_) {
+        const int my = e + s_ * EPS + grp;
+        const int vv = __shfl_sync(kFull, vtx0, my & 31);
+        const float ww = __shfl_sync(kFull, w_lane, my & 31);
+        const bool ok = my < cnt;
+        w[s_] = ok ? ww : 0.f;
         const float* r = g_h + (int64_t)vv * p.ld_g;
-        Vec<VW> x[VPL];
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
-          if (act[i]) x[i].load(r + i * gstride); else x[i].zero();
-        }
-#pragma unroll
-        for (int i = 0; i < VPL; ++i) {
-          acc[i].fma(w, x[i]);
-          part = x[i].dot(fu[i], part);
+          if (ok && act[i]) x[s_][i].load_stream(r + i * gstride); else x[s_][i].zero();
         }
       }
-      for (int o = G >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
-      deliver(part, e, EPS, p.gshift, lane, d_lane);
+#pragma unroll
+      for (int s_ = 0; s_ < NS; ++s_) {
+        float part = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          acc[i].fma(w[s_], x[s_][i]);
+          part = x[s_][i].dot(fu[i], part);
+        }
+        // reduce the partial dot inside the group, then hand it to the lane that owns this neighbour
+        for (int o = G >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
+        const int e_s = e + s_ * EPS;
+        const float got = __shfl_sync(kFull, part, ((lane - e_s) << p.gshift) & 31);
+        if (lane >= e_s && lane < e_s + EPS) d_lane = got;
+      }
     }
-    // d_lane = <src_scale*ft[u], g'[v]>; softmax + leaky_relu adjoint
-    gel_lane += alpha * (d_lane * amul - t) * dz;
+    // d_lane = <src_scale*ft[u], g'[v]>; softmax + leaky_relu adjoint (App. A.3)
+    const float gz = alpha * (d_lane * o0.amul - o0.rec.w) * dz;
+    if (gz_h && lane < cnt) gz_h[base + lane] = gz;
+    gel_lane += gz;
+    vtx0 = vtx1; vtx1 = vtx2; o0 = o1;
   }
 
   for (int o = G; o < 32; o <<= 1) {
@@ -159,7 +196,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) gat_bwd_src_kernel(const 
     for (int i = 0; i < VPL; ++i) acc[i].add_shfl_xor(o);
   }
   if (grp == 0) {
-    float* o = p.grad_ft + (int64_t)row * p.ld_gft + h * p.D + j * VW;
+    float* o = p.grad_ft + (int64_t)row * p.ld_gft + h * p.D + v0 * VW;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       if (act[i]) {
@@ -173,93 +210,44 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) gat_bwd_src_kernel(const 
 }
 
 // ---------------------------------------------------------------------------
-// dst pass: one warp per (head, destination row v) over the in-CSR
+// edge phase, second half: grad_er[v,h] = sum over in-edges k of grad_ee[k,h]
+// (one warp per destination row; lanes stride the row's edges, all heads at once)
 // ---------------------------------------------------------------------------
-template <int VW, int VPL>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) gat_bwd_dst_kernel(const BwdParams p) {
+template <int HMAX>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+gat_bwd_er_kernel(int n_dst, int H, const int32_t* __restrict__ indptr, const int32_t* __restrict__ eid,
+                  const float* __restrict__ grad_ee, float* __restrict__ grad_er) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.x / p.blocks_per_slab;
-  const int row = (blockIdx.x - h * p.blocks_per_slab) * kWarpsPerBlock + warp;
-  if (row >= p.n_rows) return;
-  const int G = 1 << p.gshift;
-  const int j = lane & (G - 1);
-  const int grp = lane >> p.gshift;
-  const int EPS = 32 >> p.gshift;
-  const int gstride = G * VW;
-
-  bool act[VPL];
+  const int v = blockIdx.x * kWarpsPerBlock + warp;
+  if (v >= n_dst) return;
+  float s[HMAX];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) act[i] = (i * G + j) * VW < p.D;
-
-  const int beg = p.indptr[row], end = p.indptr[row + 1];
-  const float4 rec = p.drec[(int64_t)h * p.n_dst + row];  // {er, max, 1/sum, t}
-  Vec<VW> gv[VPL];
-  {
-    const float* g = p.g + (int64_t)row * p.ld_g + h * p.D + j * VW;
+  for (int h = 0; h < HMAX; ++h) s[h] = 0.f;
+  for (int pos = indptr[v] + lane; pos < indptr[v + 1]; pos += 32) {
+    const float* r = grad_ee + (int64_t)__ldg(eid + pos) * H;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      if (act[i]) gv[i].load(g + i * gstride); else gv[i].zero();
+    for (int h = 0; h < HMAX; ++h)
+      if (h < H) s[h] += __ldg(r + h);
+  }
+#pragma unroll
+  for (int h = 0; h < HMAX; ++h) {
+    if (h < H) {
+      const float t = warp_sum(s[h]);
+      if (lane == 0) grad_er[(int64_t)v * H + h] = t;
     }
   }
-  const float* __restrict__ ft_h = p.ft + h * p.D + j * VW;
-  const float* __restrict__ eb_h = p.eb ? p.eb + (int64_t)(p.Hb == 1 ? 0 : h) * p.n_edges : nullptr;
-  const float* __restrict__ am_h = p.am ? p.am + (int64_t)h * p.n_edges : nullptr;
-  const bool philox = (p.am == nullptr) && p.attn_p > 0.f;
-  float ger_lane = 0.f;
-
-  for (int base = beg; base < end; base += 32) {
-    const int cnt = min(32, end - base);
-    int u = 0;
-    float alpha = 0.f, mul = 1.f, dz = 0.f;
-    if (lane < cnt) {
-      const int pos = base + lane;
-      u = __ldg(p.indices + pos);
-      float z = __ldg(p.el + (int64_t)u * p.H + h) + rec.x;
-      if (eb_h) z += __ldg(eb_h + pos);
-      const float s = leaky_relu(z, p.slope);
-      alpha = (s == -INFINITY) ? 0.f : expf(s - rec.y) * rec.z;
-      dz = z > 0.f ? 1.f : p.slope;
-      if (p.cs) mul = __ldg(p.cs + u);
-      if (am_h) mul *= __ldg(am_h + pos);
-      else if (philox) mul *= philox_dropout_mul(p.seed, (uint32_t)__ldg(p.eid + pos), (uint32_t)h, p.attn_p, p.inv_keep);
-    }
-    float d_lane = 0.f;
-    for (int e = 0; e < cnt; e += EPS) {
-      const int my = e + grp;
-      const int uu = __shfl_sync(kFull, u, my & 31);
-      float part = 0.f;
-      if (my < cnt) {
-        const float* r = ft_h + (int64_t)uu * p.ld_ft;
-        Vec<VW> x[VPL];
-#pragma unroll
-        for (int i = 0; i < VPL; ++i) {
-          if (act[i]) x[i].load(r + i * gstride); else x[i].zero();
-        }
-#pragma unroll
-        for (int i = 0; i < VPL; ++i) part = x[i].dot(gv[i], part);
-      }
-      for (int o = G >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
-      deliver(part, e, EPS, p.gshift, lane, d_lane);
-    }
-    // d_lane = <ft[u], g'[v]>; mul = src_scale[u] * dropout multiplier
-    const float gz = alpha * (d_lane * mul - rec.w) * dz;
-    if (p.gz && lane < cnt) p.gz[(int64_t)h * p.n_edges + base + lane] = gz;
-    ger_lane += gz;
-  }
-  const float ger = warp_sum(ger_lane);
-  if (p.grad_er && lane == 0) p.grad_er[(int64_t)row * p.H + h] = ger;
 }
 
-#define BG_VPL_SWITCH(KERNEL, VW)                                                        \
-  switch (vpl) {                                                                         \
-    case 1: KERNEL<VW, 1><<<grid, block, 0, st>>>(p); BG_LAUNCHED(1); break;                             \
-    case 2: KERNEL<VW, 2><<<grid, block, 0, st>>>(p); BG_LAUNCHED(1); break;                             \
-    case 3: KERNEL<VW, 3><<<grid, block, 0, st>>>(p); BG_LAUNCHED(1); break;                             \
-    case 4: KERNEL<VW, 4><<<grid, block, 0, st>>>(p); BG_LAUNCHED(1); break;                             \
-    case 5: KERNEL<VW, 5><<<grid, block, 0, st>>>(p); BG_LAUNCHED(1); break;                             \
-    case 6: KERNEL<VW, 6><<<grid, block, 0, st>>>(p); BG_LAUNCHED(1); break;                             \
-    case 8: KERNEL<VW, 8><<<grid, block, 0, st>>>(p); BG_LAUNCHED(1); break;                             \
-    default: set_error("backward: unsupported vectors-per-lane %d", vpl); return -1;     \
+#define BG_VPL_SWITCH(KERNEL, VW)                                                          \
+  switch (vpl) {                                                                           \
+    case 1: KERNEL<VW, 1><<<grid, block, 0, st>>>(p); break;                               \
+    case 2: KERNEL<VW, 2><<<grid, block, 0, st>>>(p); break;                               \
+    case 3: KERNEL<VW, 3><<<grid, block, 0, st>>>(p); break;                               \
+    case 4: KERNEL<VW, 4><<<grid, block, 0, st>>>(p); break;                               \
+    case 5: KERNEL<VW, 5><<<grid, block, 0, st>>>(p); break;                               \
+    case 6: KERNEL<VW, 6><<<grid, block, 0, st>>>(p); break;                               \
+    case 8: KERNEL<VW, 8><<<grid, block, 0, st>>>(p); break;                               \
+    default: set_error("backward: unsupported vector slots per lane %d", vpl); return -1;  \
   }
 
 static int launch_src(const BwdParams& p, int vw, int vpl, dim3 grid, cudaStream_t st) {
@@ -267,13 +255,7 @@ static int launch_src(const BwdParams& p, int vw, int vpl, dim3 grid, cudaStream
   if (vw == 4) { BG_VPL_SWITCH(gat_bwd_src_kernel, 4) }
   else if (vw == 2) { BG_VPL_SWITCH(gat_bwd_src_kernel, 2) }
   else { BG_VPL_SWITCH(gat_bwd_src_kernel, 1) }
-  return 0;
-}
-static int launch_dst(const BwdParams& p, int vw, int vpl, dim3 grid, cudaStream_t st) {
-  dim3 block(kWarpsPerBlock * 32);
-  if (vw == 4) { BG_VPL_SWITCH(gat_bwd_dst_kernel, 4) }
-  else if (vw == 2) { BG_VPL_SWITCH(gat_bwd_dst_kernel, 2) }
-  else { BG_VPL_SWITCH(gat_bwd_dst_kernel, 1) }
+  BG_LAUNCHED(1);
   return 0;
 }
 
@@ -287,43 +269,41 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
   BG_REQUIRE(a->ft && a->el && a->out && a->row_max && a->row_sum && a->gout, "backward: null input");
   BG_REQUIRE(a->drec && a->grad_ft && a->grad_el, "backward: null drec/grad_ft/grad_el");
   BG_REQUIRE(!a->dst_scale || a->gprime, "backward: gprime workspace required with dst_scale");
+  BG_REQUIRE(!a->grad_er || a->grad_ee, "backward: grad_er needs the grad_ee buffer (it is reduced from it)");
+  BG_REQUIRE(!a->grad_ee || a->gz || g->n_edges == 0, "backward: grad_ee / grad_er need the gz workspace");
   const int64_t HD = (int64_t)a->H * a->D;
   BG_REQUIRE(a->ld_ft >= HD && a->ld_out >= HD && a->ld_gft >= HD, "backward: leading dimension < H*D");
   BG_REQUIRE(a->eb_out ? (a->Hb == 1 || a->Hb == a->H) : true, "backward: Hb must be 1 or H");
-  BG_REQUIRE((a->eb_in == nullptr) == (a->eb_out == nullptr) || !(a->grad_er || a->gz),
-             "backward: eb_in and eb_out must both be given");
   if (g->n_dst == 0 || g->n_src == 0) return 0;
   DeviceGuard guard(g->device);
   cudaStream_t st = (cudaStream_t)stream;
   dim3 block(kWarpsPerBlock * 32);
-
   const int phases = a->phases ? a->phases : 7;
-  // node pass
+
   if (phases & 1) {
     dim3 grid((unsigned)((g->n_dst + kWarpsPerBlock - 1) / kWarpsPerBlock));
     gat_bwd_node_kernel<<<grid, block, 0, st>>>((int)g->n_dst, a->H, a->D, a->ld_out, a->out, a->gout, a->er,
                                                 a->row_max, a->row_sum, a->dst_scale, (float4*)a->drec,
-                                                a->dst_scale ? a->gprime : nullptr); BG_LAUNCHED(1);
+                                                a->dst_scale ? a->gprime : nullptr);
+    BG_LAUNCHED(1);
     BG_CHECK(cudaGetLastError());
   }
   const float* gp = a->dst_scale ? a->gprime : a->gout;
 
-  BwdParams p;
-  p.n_dst = (int)g->n_dst; p.n_edges = g->n_edges;
-  p.H = a->H; p.D = a->D; p.ld_ft = a->ld_ft; p.ld_g = a->ld_out; p.ld_gft = a->ld_gft;
-  p.ft = a->ft; p.el = a->el; p.cs = a->src_scale; p.g = gp; p.drec = (const float4*)a->drec;
-  p.Hb = a->Hb; p.slope = a->slope; p.attn_p = a->attn_p; p.inv_keep = 1.f / (1.f - a->attn_p); p.seed = a->seed;
-  p.grad_ft = a->grad_ft; p.grad_el = a->grad_el; p.grad_er = a->grad_er; p.gz = a->gz;
-
-  // src pass (out-CSR): the gathered table is g' (ld_out), the row-local one is ft
   if (phases & 2) {
-    Tiling t = choose_tiling(a->D, a->ld_out, a->ld_ft, gp, a->ft, 1, g->n_dst, 8);
-    // grad_ft stores use the same vector width
-    if ((a->ld_gft % t.vw) != 0 || ((uintptr_t)a->grad_ft % (t.vw * 4)) != 0)
-      t = choose_tiling(a->D, 1, 1, gp, a->ft, 1, g->n_dst, 8);  // forces vw = 1
+    BwdParams p;
+    p.n_dst = (int)g->n_dst; p.n_edges = g->n_edges;
+    p.H = a->H; p.D = a->D; p.ld_ft = a->ld_ft; p.ld_g = a->ld_out; p.ld_gft = a->ld_gft;
+    p.ft = a->ft; p.el = a->el; p.cs = a->src_scale; p.g = gp; p.drec = (const float4*)a->drec;
+    p.Hb = a->Hb; p.slope = a->slope; p.attn_p = a->attn_p; p.inv_keep = 1.f / (1.f - a->attn_p); p.seed = a->seed;
+    p.grad_ft = a->grad_ft; p.grad_el = a->grad_el; p.gz = a->gz;
+    // the gathered table is g' (ld_out); ft and grad_ft are row-local and only constrain the vector width
+    const int64_t ld_o = a->ld_ft | a->ld_gft;  // low bits clear iff both are multiples of the vector width
+    const uintptr_t po = (uintptr_t)a->ft | (uintptr_t)a->grad_ft;
+    Tiling t = choose_tiling(a->H, a->D, a->ld_out, gp, ld_o, (const void*)po, 1, g->n_dst);
     BG_REQUIRE(t.col_parts == 1, "backward: D=%d too wide for one pass (max %d)", a->D, 32 * 8 * t.vw);
     p.indptr = g->out_indptr; p.indices = g->out_indices; p.eid = g->out_eid;
-    p.n_rows = (int)g->n_src; p.eb = a->eb_out; p.am = a->am_out; p.gshift = t.gshift;
+    p.n_rows = (int)g->n_src; p.eb = a->eb_out; p.am = a->am_out; p.gshift = t.gshift; p.omask = t.omask;
     p.blocks_per_slab = (p.n_rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const int64_t nblocks = (int64_t)p.blocks_per_slab * a->H;
     BG_REQUIRE(nblocks < (1ll << 31), "backward: grid too large");
@@ -331,17 +311,22 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
     if (rc) return rc;
     BG_CHECK(cudaGetLastError());
   }
-  // dst pass (in-CSR), only when something needs it
-  if ((phases & 4) && (a->grad_er || a->gz)) {
-    Tiling t = choose_tiling(a->D, a->ld_ft, a->ld_out, a->ft, gp, 1, g->n_src, 8);
-    BG_REQUIRE(t.col_parts == 1, "backward: D=%d too wide for one pass (max %d)", a->D, 32 * 8 * t.vw);
-    p.indptr = g->in_indptr; p.indices = g->in_indices; p.eid = g->in_eid;
-    p.n_rows = (int)g->n_dst; p.eb = a->eb_in; p.am = a->am_in; p.gshift = t.gshift;
-    p.blocks_per_slab = (p.n_rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    const int64_t nblocks = (int64_t)p.blocks_per_slab * a->H;
-    BG_REQUIRE(nblocks < (1ll << 31), "backward: grid too large");
-    int rc = launch_dst(p, t.vw, t.vpl, dim3((unsigned)nblocks), st);
+
+  if ((phases & 4) && a->grad_ee && g->n_edges > 0) {
+    int rc = botgat_edge_unstage(g, BOTGAT_ORDER_OUT, a->H, a->gz, a->grad_ee, stream);
     if (rc) return rc;
+  }
+  if ((phases & 4) && a->grad_er) {
+    dim3 grid((unsigned)((g->n_dst + kWarpsPerBlock - 1) / kWarpsPerBlock));
+    if (a->H <= 8)
+      gat_bwd_er_kernel<8><<<grid, block, 0, st>>>((int)g->n_dst, a->H, g->in_indptr, g->in_eid, a->grad_ee, a->grad_er);
+    else if (a->H <= 32)
+      gat_bwd_er_kernel<32><<<grid, block, 0, st>>>((int)g->n_dst, a->H, g->in_indptr, g->in_eid, a->grad_ee, a->grad_er);
+    else {
+      set_error("backward: grad_er supports at most 32 heads (got %d)", a->H);
+      return -1;
+    }
+    BG_LAUNCHED(1);
     BG_CHECK(cudaGetLastError());
   }
   return 0;

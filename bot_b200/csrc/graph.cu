@@ -36,17 +36,21 @@ static int pow2ceil(int x) {
   return p;
 }
 
-Tiling choose_tiling(int D, int64_t ld_a, int64_t ld_b, const void* pa, const void* pb, int col_parts_req,
-                     int64_t n_rows_table, int vpl_cap) {
+Tiling choose_tiling(int H, int D, int64_t ld_g, const void* pg, int64_t ld_o, const void* po, int col_parts_req,
+                     int64_t n_rows_table) {
+  constexpr int kVplCap = 8;
   Tiling t;
   auto ok = [&](int vw) {
-    return D % vw == 0 && ld_a % vw == 0 && ld_b % vw == 0 && ((uintptr_t)pa % (vw * 4)) == 0 &&
-           ((uintptr_t)pb % (vw * 4)) == 0;
+    return D % vw == 0 && ld_g % vw == 0 && ld_o % vw == 0 && ((uintptr_t)pg % (vw * 4)) == 0 &&
+           ((uintptr_t)po % (vw * 4)) == 0;
   };
   t.vw = ok(4) ? 4 : (ok(2) ? 2 : 1);
   const int force_vw = env_int("BOTGAT_VW", 0);
   if ((force_vw == 1 || force_vw == 2) && force_vw < t.vw) t.vw = force_vw;
-  const int cap_cols = 32 * vpl_cap * t.vw;  // widest part one warp covers in a single pass
+  const int gline = 32 / t.vw;  // lanes that cover one 128-byte line
+  // line-alignment shift is possible when every gathered row starts on a line boundary
+  const bool can_align = (ld_g * 4) % 128 == 0 && ((uintptr_t)pg % 128) == 0 && env_int("BOTGAT_NOALIGN", 0) == 0;
+  const int cap_cols = (32 * kVplCap - (can_align ? gline : 0)) * t.vw;  // widest part one warp covers in a pass
   int parts = col_parts_req;
   if (parts <= 0) {
     // auto: keep one (n_rows x part_cols) slab of the gathered table within the L2 budget
@@ -65,31 +69,27 @@ Tiling choose_tiling(int D, int64_t ld_a, int64_t ld_b, const void* pa, const vo
   t.part_cols = part_cols_of(parts);
   t.col_parts = (D + t.part_cols - 1) / t.part_cols;
   const int nv = (t.part_cols + t.vw - 1) / t.vw;
-  // lanes per neighbour: at least 64 contiguous bytes per group, minimal padded
-  // slots, ties broken towards ~4 vectors per lane
-  const int gmin = std::min(16 / t.vw, pow2ceil(nv));
-  int best_g = 32, best_vpl = 8, best_slots = 1 << 30, best_tie = 1 << 30;
-  static const int kVpl[] = {1, 2, 3, 4, 5, 6, 8};
-  for (int G = gmin; G <= 32; G <<= 1) {
-    const int need = (nv + G - 1) / G;
-    int vpl = -1;
-    for (int c : kVpl)
-      if (c >= need && c <= vpl_cap) { vpl = c; break; }
-    if (vpl < 0) continue;
-    const int slots = G * vpl, tie = std::abs(vpl - 4);
-    if (slots < best_slots || (slots == best_slots && tie < best_tie)) {
-      best_g = G; best_vpl = vpl; best_slots = slots; best_tie = tie;
-    }
-  }
+  // lanes per neighbour: one 128-byte line per group and instruction (fewer when the part is narrower),
+  // more only when the part needs over kVplCap slots
+  int G = std::min(gline, pow2ceil(nv));
   const int force_g = env_int("BOTGAT_G", 0);
-  if (force_g >= 1 && force_g <= 32 && (force_g & (force_g - 1)) == 0) {
-    const int need = (nv + force_g - 1) / force_g;
+  if (force_g >= 1 && force_g <= 32 && (force_g & (force_g - 1)) == 0) G = force_g;
+  static const int kVpl[] = {1, 2, 3, 4, 5, 6, 8};
+  for (;; G <<= 1) {
+    t.omask = can_align ? std::min(G, gline) - 1 : 0;
+    // worst-case shift over all (head, part) slab starts
+    int omax = 0;
+    for (int h = 0; h < H && t.omask; ++h)
+      for (int cp = 0; cp < t.col_parts; ++cp) omax = std::max(omax, ((h * D + cp * t.part_cols) / t.vw) & t.omask);
+    const int need = (nv + omax + G - 1) / G;
+    t.vpl = -1;
     for (int c : kVpl)
-      if (c >= need) { best_g = force_g; best_vpl = c; break; }
+      if (c >= need) { t.vpl = c; break; }
+    if (t.vpl > 0 || G >= 32) break;
   }
-  t.vpl = best_vpl;
+  if (t.vpl < 0) t.vpl = kVplCap;  // unreachable: cap_cols guarantees a fit at G = 32
   t.gshift = 0;
-  while ((1 << t.gshift) < best_g) ++t.gshift;
+  while ((1 << t.gshift) < G) ++t.gshift;
   return t;
 }
 
@@ -452,13 +452,16 @@ extern "C" int botgat_edge_stage(const botgat_graph* g, int order, int32_t H, co
   return 0;
 }
 
-extern "C" int botgat_edge_unstage(const botgat_graph* g, int32_t H, const float* gz, float* grad_ee, void* stream) {
+extern "C" int botgat_edge_unstage(const botgat_graph* g, int order, int32_t H, const float* gz, float* grad_ee,
+                                   void* stream) {
   BG_REQUIRE(g && H > 0, "edge_unstage: bad arguments");
+  BG_REQUIRE(order == BOTGAT_ORDER_IN || order == BOTGAT_ORDER_OUT, "edge_unstage: bad order %d", order);
   if (g->n_edges == 0) return 0;
   BG_REQUIRE(gz && grad_ee, "edge_unstage: null gz/grad_ee");
   DeviceGuard guard(g->device);
   cudaStream_t st = (cudaStream_t)stream;
-  k_edge_unstage<<<grid_for(g->n_edges), 256, 0, st>>>(g->n_edges, H, g->in_eid, gz, grad_ee); BG_LAUNCHED(1);
+  k_edge_unstage<<<grid_for(g->n_edges), 256, 0, st>>>(g->n_edges, H, order == BOTGAT_ORDER_IN ? g->in_eid : g->out_eid,
+                                                       gz, grad_ee); BG_LAUNCHED(1);
   BG_CHECK(cudaGetLastError());
   return 0;
 }

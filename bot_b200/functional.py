@@ -144,8 +144,7 @@ class GATFusedFn(torch.autograd.Function):
 
         ctx.graph = graph
         ctx.cfg = (H, D, Hb, float(slope), float(a.attn_p), int(seed))
-        ctx.has = (er is not None, ee is not None, keep is not None, attn_mul is not None)
-        ctx.save_for_backward(ft, el, er, ee, keep, attn_mul, src_scale, dst_scale, out, row_max, row_sum, eb_in, am_in)
+        ctx.save_for_backward(ft, el, er, ee, keep, attn_mul, src_scale, dst_scale, out, row_max, row_sum)
         return out
 
     @staticmethod
@@ -153,13 +152,16 @@ class GATFusedFn(torch.autograd.Function):
         lib = _lib.load()
         graph = ctx.graph
         h = graph._ensure()
-        ft, el, er, ee, keep, attn_mul, src_scale, dst_scale, out, row_max, row_sum, eb_in, am_in = ctx.saved_tensors
+        ft, el, er, ee, keep, attn_mul, src_scale, dst_scale, out, row_max, row_sum = ctx.saved_tensors
         H, D, Hb, slope, attn_p, seed = ctx.cfg
         N_s, N_d, E = ft.shape[0], out.shape[0], graph.number_of_edges()
         dev = ft.device
         need_er = er is not None and ctx.needs_input_grad[3]
         need_ee = ee is not None and ctx.needs_input_grad[4]
         gout = _f32c(gout, "grad_out")
+
+        def p(t):
+            return t.data_ptr() if t is not None else None
 
         with torch.cuda.device(dev):
             eb_out, _, am_out = edge_stage(graph, _lib.ORDER_OUT, H, ee, keep, attn_mul)
@@ -168,40 +170,29 @@ class GATFusedFn(torch.autograd.Function):
             grad_ft = torch.empty_like(ft)
             grad_el = torch.empty((N_s, H), dtype=torch.float32, device=dev)
             grad_er = torch.empty((N_d, H), dtype=torch.float32, device=dev) if need_er else None
-            gz = torch.empty((H, E), dtype=torch.float32, device=dev) if need_ee else None
+            # gz (out-CSR order) -> grad_ee (edge-id order); grad_er is reduced from grad_ee
+            gz = grad_ee = None
+            if need_er or need_ee:
+                gz = torch.empty((H, E), dtype=torch.float32, device=dev)
+                grad_ee = torch.empty((E, H), dtype=torch.float32, device=dev)
             a = _lib.BwdArgs()
             a.H, a.D, a.ld_ft, a.ld_out, a.ld_gft = H, D, H * D, H * D, H * D
-            a.ft, a.el = ft.data_ptr(), el.data_ptr()
-            a.er = er.data_ptr() if er is not None else None
-            a.eb_in = eb_in.data_ptr() if eb_in is not None else None
-            a.eb_out = eb_out.data_ptr() if eb_out is not None else None
-            a.Hb, a.phases = Hb, 0
-            a.am_in = am_in.data_ptr() if am_in is not None else None
-            a.am_out = am_out.data_ptr() if am_out is not None else None
-            a.src_scale = src_scale.data_ptr() if src_scale is not None else None
-            a.dst_scale = dst_scale.data_ptr() if dst_scale is not None else None
+            a.ft, a.el, a.er = ft.data_ptr(), el.data_ptr(), p(er)
+            a.eb_out, a.Hb, a.phases, a.am_out = p(eb_out), Hb, 0, p(am_out)
+            a.src_scale, a.dst_scale = p(src_scale), p(dst_scale)
             a.slope, a.attn_p, a.seed = slope, attn_p, seed
             a.out, a.row_max, a.row_sum, a.gout = out.data_ptr(), row_max.data_ptr(), row_sum.data_ptr(), gout.data_ptr()
-            a.drec = drec.data_ptr()
-            a.gprime = gprime.data_ptr() if gprime is not None else None
-            a.grad_ft, a.grad_el = grad_ft.data_ptr(), grad_el.data_ptr()
-            a.grad_er = grad_er.data_ptr() if grad_er is not None else None
-            a.gz = gz.data_ptr() if gz is not None else None
+            a.drec, a.gprime, a.gz = drec.data_ptr(), p(gprime), p(gz)
+            a.grad_ft, a.grad_el, a.grad_ee, a.grad_er = grad_ft.data_ptr(), grad_el.data_ptr(), p(grad_ee), p(grad_er)
             if timer is None:
                 _lib.check(lib.botgat_gat_backward(h, C.byref(a), _stream()), "botgat_gat_backward")
             else:
-                for bit, name in ((1, "gat_bwd_node"), (2, "gat_bwd_src"), (4, "gat_bwd_dst")):
+                for bit, name in ((1, "gat_bwd_node"), (2, "gat_bwd_src"), (4, "gat_bwd_edge")):
                     a.phases = bit
                     with _span(name):
                         rc = lib.botgat_gat_backward(h, C.byref(a), _stream())
                     _lib.check(rc, "botgat_gat_backward")
-            grad_ee = None
-            if need_ee:
-                grad_ee = torch.empty((E, H), dtype=torch.float32, device=dev)
-                with _span("edge_unstage"):
-                    rc = lib.botgat_edge_unstage(h, H, gz.data_ptr(), grad_ee.data_ptr(), _stream())
-                _lib.check(rc, "botgat_edge_unstage")
-        return None, grad_ft, grad_el, grad_er, grad_ee, None, None, None, None, None, None, None
+        return None, grad_ft, grad_el, grad_er, (grad_ee if need_ee else None), None, None, None, None, None, None, None
 
 
 def gat_fused(graph, ft, el, er=None, ee=None, keep=None, attn_mul=None, src_scale=None, dst_scale=None,

@@ -118,8 +118,8 @@ enum { BOTGAT_ORDER_IN = 0, BOTGAT_ORDER_OUT = 1 };
 int botgat_edge_stage(const botgat_graph* g, int order, int32_t H,
                       const float* ee, const uint8_t* keep, const float* attn_mul,
                       float* eb, float* am, void* stream);
-/* grad_ee[eid(p)*H + h] = gz[h][p]  (gz in in-CSR order, head-major) */
-int botgat_edge_unstage(const botgat_graph* g, int32_t H, const float* gz,
+/* grad_ee[eid(p)*H + h] = gz[h][p]  (gz head-major in the CSR order named by `order`) */
+int botgat_edge_unstage(const botgat_graph* g, int order, int32_t H, const float* gz,
                         float* grad_ee, void* stream);
 
 /* ------------------------------------------------------------------------
@@ -158,9 +158,14 @@ int botgat_gat_forward(const botgat_graph* g, const botgat_fwd_args* a /* HOST *
 /* ------------------------------------------------------------------------
  * Backward.  Replaces the autograd replay of DGL's
  * GSpMM / GSDDMM / EdgeSoftmax backward kernels.  Deterministic (no atomics).
- *   node pass : t[v,h] = <out[v,h,:], gout[v,h,:]>, packs per-dst records
- *   pass B    : out-CSR (src-major): grad_ft, grad_el
- *   pass A    : in-CSR  (dst-major): grad_er, gz (only when either is requested)
+ *   phase 1, node : t[v,h] = <out[v,h,:], gout[v,h,:]>, packs per-dst records
+ *                   {er, row_max, 1/row_sum, t}; g' = gout * dst_scale
+ *   phase 2, src  : ONE gather pass over the out-CSR (src-major): grad_ft,
+ *                   grad_el and, on request, gz = d(loss)/d(edge logit) per
+ *                   (edge, head) in out-CSR order.  The attention weights are
+ *                   recomputed from (el, er, eb, row_max, row_sum).
+ *   phase 4, edge : gz -> grad_ee (edge-id order), grad_er[v] = sum of grad_ee
+ *                   over the in-edges of v (in-CSR walk, 4*H-byte records).
  * ---------------------------------------------------------------------- */
 typedef struct {
   int32_t H, D;
@@ -168,12 +173,10 @@ typedef struct {
   const float* ft;        /* (n_src, ld_ft) */
   const float* el;        /* (n_src, H) */
   const float* er;        /* (n_dst, H) or NULL */
-  const float* eb_in;     /* (Hb, n_edges) in-CSR order or NULL */
   const float* eb_out;    /* (Hb, n_edges) out-CSR order or NULL */
   int32_t Hb;
-  int32_t phases;         /* bitmask of passes to run: 1 node, 2 src, 4 dst; 0 = all (profiling splits them) */
-  const float* am_in;    /* (H, n_edges) or NULL */
-  const float* am_out;    /* (H, n_edges) or NULL */
+  int32_t phases;         /* bitmask of phases to run (1 node, 2 src, 4 edge); 0 = all (profiling splits them) */
+  const float* am_out;    /* (H, n_edges) out-CSR order or NULL */
   const float* src_scale;
   const float* dst_scale;
   float slope;
@@ -186,11 +189,12 @@ typedef struct {
   /* workspaces */
   float* drec;            /* (H, n_dst, 4) */
   float* gprime;          /* (n_dst, ld_out); required iff dst_scale != NULL */
+  float* gz;              /* (H, n_edges); required iff grad_er or grad_ee is requested */
   /* outputs */
   float* grad_ft;         /* (n_src, ld_gft) w.r.t. the unscaled ft */
   float* grad_el;         /* (n_src, H) */
+  float* grad_ee;         /* (n_edges, H) edge-id order; required iff grad_er is requested (it is its input) */
   float* grad_er;         /* (n_dst, H) or NULL */
-  float* gz;              /* (H, n_edges) in-CSR order, or NULL (feed to botgat_edge_unstage) */
 } botgat_bwd_args;
 int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args* a /* HOST */, void* stream);
 
