@@ -105,14 +105,15 @@ __device__ __forceinline__ float philox_dropout_mul(uint64_t seed, uint32_t eid,
 // ---------------------------------------------------------------------------
 // VW-wide vectors (VW = 4, 2, 1 floats) with read-only global loads
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float4 ldg_stream4(const float* p);
-__device__ __forceinline__ float2 ldg_stream2(const float* p);
-__device__ __forceinline__ float ldg_stream1(const float* p);
 template <int VW> struct Vec;
 template <> struct Vec<4> {
   float4 v;
   __device__ __forceinline__ void load(const float* p) { v = __ldg(reinterpret_cast<const float4*>(p)); }
-  __device__ __forceinline__ void load_stream(const float* p) { v = ldg_stream4(p); }
+  // predicated load straight into the live registers: the value is KEPT when on == 0 (no select, no copy)
+  __device__ __forceinline__ void load_if(const float* p, unsigned on) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
+                 : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w) : "l"(p), "r"(on));
+  }
   __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
   __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
   __device__ __forceinline__ void fma(float w, const Vec& o) {
@@ -131,7 +132,10 @@ template <> struct Vec<4> {
 template <> struct Vec<2> {
   float2 v;
   __device__ __forceinline__ void load(const float* p) { v = __ldg(reinterpret_cast<const float2*>(p)); }
-  __device__ __forceinline__ void load_stream(const float* p) { v = ldg_stream2(p); }
+  __device__ __forceinline__ void load_if(const float* p, unsigned on) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q ld.global.nc.v2.f32 {%0,%1}, [%2];\n\t}"
+                 : "+f"(v.x), "+f"(v.y) : "l"(p), "r"(on));
+  }
   __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float2*>(p) = v; }
   __device__ __forceinline__ void zero() { v = make_float2(0.f, 0.f); }
   __device__ __forceinline__ void fma(float w, const Vec& o) { v.x = fmaf(w, o.v.x, v.x); v.y = fmaf(w, o.v.y, v.y); }
@@ -147,7 +151,10 @@ template <> struct Vec<2> {
 template <> struct Vec<1> {
   float v;
   __device__ __forceinline__ void load(const float* p) { v = __ldg(p); }
-  __device__ __forceinline__ void load_stream(const float* p) { v = ldg_stream1(p); }
+  __device__ __forceinline__ void load_if(const float* p, unsigned on) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}"
+                 : "+f"(v) : "l"(p), "r"(on));
+  }
   __device__ __forceinline__ void store(float* p) const { *p = v; }
   __device__ __forceinline__ void zero() { v = 0.f; }
   __device__ __forceinline__ void fma(float w, const Vec& o) { v = fmaf(w, o.v, v); }
@@ -185,25 +192,32 @@ struct Tiling {
 Tiling choose_tiling(int H, int D, int64_t ld_g, const void* pg, int64_t ld_o, const void* po, int col_parts_req,
                      int64_t n_rows_table);
 
-// read-only, no-L1-allocate gather loads (rows are touched once per SM: keep L1 for the index/logit streams)
-__device__ __forceinline__ float4 ldg_stream4(const float* p) {
-  float4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-  return r;
-}
-__device__ __forceinline__ float2 ldg_stream2(const float* p) {
-  float2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
-  return r;
-}
-__device__ __forceinline__ float ldg_stream1(const float* p) {
-  float r;
-  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
-  return r;
-}
+// steps (of 32/G neighbours each) whose row loads a lane keeps in flight together.
+// Measured on B200 (profiles/r01_*): at D=80 (3 slots) two steps at 3 blocks/SM beat four steps at 2 blocks/SM.
+#ifdef BG_NS
+__host__ __device__ constexpr int steps_in_flight(int vpl) { return BG_NS; }
+#else
+__host__ __device__ constexpr int steps_in_flight(int vpl) { return vpl <= 1 ? 4 : vpl <= 2 ? 3 : vpl <= 4 ? 2 : 1; }
+#endif
 
-// steps (of 32/G neighbours each) whose row loads are kept in flight together
-__host__ __device__ constexpr int steps_in_flight(int vpl) { return vpl <= 1 ? 8 : vpl <= 3 ? 4 : vpl <= 6 ? 2 : 1; }
+// (vector width, log2 lanes per neighbour, slots per lane) combinations the gather kernels are instantiated
+// for; choose_tiling() only returns members of this set.
+#define BG_VPL_SMALL(X, VW, GSH) X(VW, GSH, 1) X(VW, GSH, 2)
+#define BG_VPL_FULL(X, VW, GSH) X(VW, GSH, 1) X(VW, GSH, 2) X(VW, GSH, 3) X(VW, GSH, 4) X(VW, GSH, 5) X(VW, GSH, 6) X(VW, GSH, 7) X(VW, GSH, 8)
+#define BG_VPL_BIG(X, VW, GSH) X(VW, GSH, 5) X(VW, GSH, 6) X(VW, GSH, 7) X(VW, GSH, 8)
+#define BG_COMBOS(X)                                                                                        \
+  BG_VPL_SMALL(X, 4, 0) BG_VPL_SMALL(X, 4, 1) BG_VPL_SMALL(X, 4, 2) BG_VPL_FULL(X, 4, 3) BG_VPL_BIG(X, 4, 4)   \
+  BG_VPL_BIG(X, 4, 5)                                                                                       \
+  BG_VPL_SMALL(X, 2, 0) BG_VPL_SMALL(X, 2, 1) BG_VPL_SMALL(X, 2, 2) BG_VPL_SMALL(X, 2, 3) BG_VPL_FULL(X, 2, 4) \
+  BG_VPL_BIG(X, 2, 5)                                                                                       \
+  BG_VPL_SMALL(X, 1, 0) BG_VPL_SMALL(X, 1, 1) BG_VPL_SMALL(X, 1, 2) BG_VPL_SMALL(X, 1, 3) BG_VPL_SMALL(X, 1, 4) \
+  BG_VPL_FULL(X, 1, 5)
+
+inline bool combo_supported(int vw, int gsh, int vpl) {
+#define BG_X(VW, GSH, VPL) if (vw == VW && gsh == GSH && vpl == VPL) return true;
+  BG_COMBOS(BG_X)
+#undef BG_X
+  return false;
+}
 
 }  // namespace botgat

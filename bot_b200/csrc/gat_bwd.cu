@@ -37,7 +37,7 @@ struct BwdParams {
   float slope, attn_p, inv_keep;
   uint64_t seed;
   float *grad_ft, *grad_el, *gz;
-  int gshift, omask;
+  int omask;
   int blocks_per_slab;
 };
 
@@ -79,27 +79,39 @@ struct SrcOps {
   float eb, amul;
 };
 
-template <int VW, int VPL>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) gat_bwd_src_kernel(const BwdParams p) {
+// 3 blocks (24 warps) per SM: measured faster than 2 blocks with more loads in flight per warp (profiles/r01_*)
+#ifndef BG_MINB
+#define BG_MINB 3
+#endif
+
+template <int VW, int GSH, int VPL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB) gat_bwd_src_kernel(const BwdParams p) {
   constexpr int NS = steps_in_flight(VPL);
+  constexpr int G = 1 << GSH;
+  constexpr int EPS = 32 >> GSH;
+  constexpr int GSTRIDE = G * VW;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x / p.blocks_per_slab;
   const int row = (blockIdx.x - h * p.blocks_per_slab) * kWarpsPerBlock + warp;
   if (row >= p.n_rows) return;
-  const int G = 1 << p.gshift;
-  const int grp = lane >> p.gshift;
-  const int EPS = 32 >> p.gshift;
-  const int gstride = G * VW;
+  const int grp = lane >> GSH;
   const int v0 = (lane & (G - 1)) - (((h * p.D) / VW) & p.omask);
 
+  // per-slot base pointers into g' (bytes); out-of-slab (lane, slot) pairs are clamped onto the nearest
+  // vector of the slab (same line, no extra sector) and meet fu = 0 / an accumulator that is never stored
+  const int nv = p.D / VW;
+  const char* bp[VPL];
   bool act[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int v = v0 + i * G;
-    act[i] = v >= 0 && v * VW < p.D;
+    act[i] = v >= 0 && v < nv;
+    bp[i] = reinterpret_cast<const char*>(p.g + h * p.D + min(max(v, 0), nv - 1) * VW);
   }
+  const unsigned ldb = (unsigned)(p.ld_g * 4);
 
   const int beg = p.indptr[row], end = p.indptr[row + 1];
+  const float slope = p.slope;
   const float csu = p.cs ? p.cs[row] : 1.f;
   const float el_u = p.el[(int64_t)row * p.H + h];
   Vec<VW> fu[VPL], acc[VPL];
@@ -107,11 +119,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) gat_bwd_src_kernel(const 
     const float* f = p.ft + (int64_t)row * p.ld_ft + h * p.D + v0 * VW;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      if (act[i]) { fu[i].load(f + i * gstride); fu[i].scale(csu); } else fu[i].zero();
+      if (act[i]) { fu[i].load(f + i * GSTRIDE); fu[i].scale(csu); } else fu[i].zero();
       acc[i].zero();
     }
   }
-  const float* __restrict__ g_h = p.g + h * p.D + v0 * VW;
   const float4* __restrict__ drec_h = p.drec + (int64_t)h * p.n_dst;
   const float* __restrict__ eb_h = p.eb ? p.eb + (int64_t)(p.Hb == 1 ? 0 : h) * p.n_edges : nullptr;
   const float* __restrict__ am_h = p.am ? p.am + (int64_t)h * p.n_edges : nullptr;
@@ -136,6 +147,20 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) gat_bwd_src_kernel(const 
       else if (philox) o.amul = philox_dropout_mul(p.seed, (uint32_t)__ldg(p.eid + pos), (uint32_t)h, p.attn_p, p.inv_keep);
     }
   };
+  // one step: the group's neighbour row is in x; acc += w*x, and the dot <x, ft[u]> goes to the owner lane
+  auto consume = [&](const Vec<VW>(&x)[VPL], float w, int e_s, float& d_lane) {
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      acc[i].fma(w, x[i]);
+      part = x[i].dot(fu[i], part);  // fu is 0 on slots this lane does not own
+    }
+#pragma unroll
+    for (int o = G >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
+    const float got = __shfl_sync(kFull, part, ((lane - e_s) << GSH) & 31);
+    if (lane >= e_s && lane < e_s + EPS) d_lane = got;
+  };
+
   int vtx0 = load_index(beg), vtx1 = load_index(beg + 32), vtx2 = 0;
   SrcOps o0, o1;
   load_operands(beg, vtx0, o0);
@@ -147,42 +172,37 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) gat_bwd_src_kernel(const 
 
     // lane = neighbour: recompute the attention weight of this edge
     const float z = el_u + o0.rec.x + o0.eb;
-    const float s = leaky_relu(z, p.slope);
-    const float alpha = (s == -INFINITY) ? 0.f : expf(s - o0.rec.y) * o0.rec.z;
-    const float dz = z > 0.f ? 1.f : p.slope;
+    const float s = leaky_relu(z, slope);
+    const float alpha = (s == -INFINITY) ? 0.f : __expf(s - o0.rec.y) * o0.rec.z;
+    const float dz = z > 0.f ? 1.f : slope;
     const float w_lane = alpha * o0.amul;
     float d_lane = 0.f;
 
-    for (int e = 0; e < cnt; e += NS * EPS) {
+    int e = 0;
+    for (; e + NS * EPS <= cnt; e += NS * EPS) {
       Vec<VW> x[NS][VPL];
       float w[NS];
 #pragma unroll
       for (int s_ = 0; s_ < NS; ++s_) {
         const int my = e + s_ * EPS + grp;
-        const int vv = __shfl_sync(kFull, vtx0, my & 31);
-        const float ww = __shfl_sync(kFull, w_lane, my & 31);
-        const bool ok = my < cnt;
-        w[s_] = ok ? ww : 0.f;
-        const float* r = g_h + (int64_t)vv * p.ld_g;
+        const size_t off = (size_t)(unsigned)__shfl_sync(kFull, vtx0, my) * ldb;
+        w[s_] = __shfl_sync(kFull, w_lane, my);
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) {
-          if (ok && act[i]) x[s_][i].load_stream(r + i * gstride); else x[s_][i].zero();
-        }
+        for (int i = 0; i < VPL; ++i) x[s_][i].load(reinterpret_cast<const float*>(bp[i] + off));
       }
 #pragma unroll
-      for (int s_ = 0; s_ < NS; ++s_) {
-        float part = 0.f;
+      for (int s_ = 0; s_ < NS; ++s_) consume(x[s_], w[s_], e + s_ * EPS, d_lane);
+    }
+    for (; e < cnt; e += EPS) {
+      // a group past the end re-reads the chunk's last neighbour; its weight is 0 and its dot is not delivered
+      const int my = e + grp;
+      const int src = min(my, cnt - 1);
+      const size_t off = (size_t)(unsigned)__shfl_sync(kFull, vtx0, src) * ldb;
+      const float ww = __shfl_sync(kFull, w_lane, src);
+      Vec<VW> x[VPL];
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) {
-          acc[i].fma(w[s_], x[s_][i]);
-          part = x[s_][i].dot(fu[i], part);
-        }
-        // reduce the partial dot inside the group, then hand it to the lane that owns this neighbour
-        for (int o = G >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
-        const int e_s = e + s_ * EPS;
-        const float got = __shfl_sync(kFull, part, ((lane - e_s) << p.gshift) & 31);
-        if (lane >= e_s && lane < e_s + EPS) d_lane = got;
-      }
+      for (int i = 0; i < VPL; ++i) x[i].load(reinterpret_cast<const float*>(bp[i] + off));
+      consume(x, my < cnt ? ww : 0.f, e, d_lane);
     }
     // d_lane = <src_scale*ft[u], g'[v]>; softmax + leaky_relu adjoint (App. A.3)
     const float gz = alpha * (d_lane * o0.amul - o0.rec.w) * dz;
@@ -191,6 +211,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) gat_bwd_src_kernel(const 
     vtx0 = vtx1; vtx1 = vtx2; o0 = o1;
   }
 
+#pragma unroll
   for (int o = G; o < 32; o <<= 1) {
 #pragma unroll
     for (int i = 0; i < VPL; ++i) acc[i].add_shfl_xor(o);
@@ -201,7 +222,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) gat_bwd_src_kernel(const 
     for (int i = 0; i < VPL; ++i) {
       if (act[i]) {
         acc[i].scale(csu);
-        acc[i].store(o + i * gstride);
+        acc[i].store(o + i * GSTRIDE);
       }
     }
   }
@@ -238,25 +259,18 @@ gat_bwd_er_kernel(int n_dst, int H, const int32_t* __restrict__ indptr, const in
   }
 }
 
-#define BG_VPL_SWITCH(KERNEL, VW)                                                          \
-  switch (vpl) {                                                                           \
-    case 1: KERNEL<VW, 1><<<grid, block, 0, st>>>(p); break;                               \
-    case 2: KERNEL<VW, 2><<<grid, block, 0, st>>>(p); break;                               \
-    case 3: KERNEL<VW, 3><<<grid, block, 0, st>>>(p); break;                               \
-    case 4: KERNEL<VW, 4><<<grid, block, 0, st>>>(p); break;                               \
-    case 5: KERNEL<VW, 5><<<grid, block, 0, st>>>(p); break;                               \
-    case 6: KERNEL<VW, 6><<<grid, block, 0, st>>>(p); break;                               \
-    case 8: KERNEL<VW, 8><<<grid, block, 0, st>>>(p); break;                               \
-    default: set_error("backward: unsupported vector slots per lane %d", vpl); return -1;  \
-  }
-
-static int launch_src(const BwdParams& p, int vw, int vpl, dim3 grid, cudaStream_t st) {
+static int launch_src(const BwdParams& p, const Tiling& t, dim3 grid, cudaStream_t st) {
   dim3 block(kWarpsPerBlock * 32);
-  if (vw == 4) { BG_VPL_SWITCH(gat_bwd_src_kernel, 4) }
-  else if (vw == 2) { BG_VPL_SWITCH(gat_bwd_src_kernel, 2) }
-  else { BG_VPL_SWITCH(gat_bwd_src_kernel, 1) }
-  BG_LAUNCHED(1);
-  return 0;
+#define BG_X(VW, GSH, VPL)                                            \
+  if (t.vw == VW && t.gshift == GSH && t.vpl == VPL) {                \
+    gat_bwd_src_kernel<VW, GSH, VPL><<<grid, block, 0, st>>>(p);      \
+    BG_LAUNCHED(1);                                                   \
+    return 0;                                                         \
+  }
+  BG_COMBOS(BG_X)
+#undef BG_X
+  set_error("backward: no kernel for vw=%d lanes=%d slots=%d", t.vw, 1 << t.gshift, t.vpl);
+  return -1;
 }
 
 }  // namespace botgat
@@ -269,7 +283,8 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
   BG_REQUIRE(a->ft && a->el && a->out && a->row_max && a->row_sum && a->gout, "backward: null input");
   BG_REQUIRE(a->drec && a->grad_ft && a->grad_el, "backward: null drec/grad_ft/grad_el");
   BG_REQUIRE(!a->dst_scale || a->gprime, "backward: gprime workspace required with dst_scale");
-  BG_REQUIRE(!a->grad_er || a->grad_ee, "backward: grad_er needs the grad_ee buffer (it is reduced from it)");
+  BG_REQUIRE(!a->grad_er || a->grad_ee || g->n_edges == 0,
+             "backward: grad_er needs the grad_ee buffer (it is reduced from it)");
   BG_REQUIRE(!a->grad_ee || a->gz || g->n_edges == 0, "backward: grad_ee / grad_er need the gz workspace");
   const int64_t HD = (int64_t)a->H * a->D;
   BG_REQUIRE(a->ld_ft >= HD && a->ld_out >= HD && a->ld_gft >= HD, "backward: leading dimension < H*D");
@@ -303,11 +318,11 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
     Tiling t = choose_tiling(a->H, a->D, a->ld_out, gp, ld_o, (const void*)po, 1, g->n_dst);
     BG_REQUIRE(t.col_parts == 1, "backward: D=%d too wide for one pass (max %d)", a->D, 32 * 8 * t.vw);
     p.indptr = g->out_indptr; p.indices = g->out_indices; p.eid = g->out_eid;
-    p.n_rows = (int)g->n_src; p.eb = a->eb_out; p.am = a->am_out; p.gshift = t.gshift; p.omask = t.omask;
+    p.n_rows = (int)g->n_src; p.eb = a->eb_out; p.am = a->am_out; p.omask = t.omask;
     p.blocks_per_slab = (p.n_rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const int64_t nblocks = (int64_t)p.blocks_per_slab * a->H;
     BG_REQUIRE(nblocks < (1ll << 31), "backward: grid too large");
-    int rc = launch_src(p, t.vw, t.vpl, dim3((unsigned)nblocks), st);
+    int rc = launch_src(p, t, dim3((unsigned)nblocks), st);
     if (rc) return rc;
     BG_CHECK(cudaGetLastError());
   }

@@ -9,12 +9,16 @@
 // L2/HBM-bound gather: no tensor cores (the only dense contraction, fc, stays a
 // torch matmul).  See common.cuh "Work decomposition" for the item/lane layout.
 //
-// Latency hiding (the kernel is load-latency bound, profiles/r01_a_*):
+// What the profiles asked for (profiles/r01_*):
+//   * lane geometry (VW, G, VPL) is compile-time and every (lane, slot) has its own
+//     base pointer, so a row load is one 32x32+64 IMAD plus an UNPREDICATED LDG.128
+//     (lanes outside the slab re-read the nearest vector of the same line: no extra
+//     sector, and their accumulators are never stored);
+//   * the neighbour loop runs full steps without bounds checks and handles the row
+//     tail separately;
 //   * the per-neighbour scalars run in a 3-stage software pipeline — index of
 //     chunk c+2, logit operands of chunk c+1 and the row gathers of chunk c are in
-//     flight together, so no load waits on a load issued in the same iteration;
-//   * NS steps of row gathers (NS * VPL 128-bit loads per lane) are issued before
-//     the first FMA consumes them.
+//     flight together, so no load waits on a load issued in the same iteration.
 #include "common.cuh"
 
 namespace botgat {
@@ -32,13 +36,20 @@ struct FwdParams {
   float slope, attn_p, inv_keep;
   uint64_t seed;
   float *out, *row_max, *row_sum;
-  int col_parts, part_cols, gshift, omask;
+  int col_parts, part_cols, omask;
   int blocks_per_slab;
 };
 
-template <int VW, int VPL>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) gat_fwd_kernel(const FwdParams p) {
+// 3 blocks (24 warps) per SM: measured faster than 2 blocks with more loads in flight per warp (profiles/r01_*)
+#ifndef BG_MINB
+#define BG_MINB 3
+#endif
+
+template <int VW, int GSH, int VPL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB) gat_fwd_kernel(const FwdParams p) {
   constexpr int NS = steps_in_flight(VPL);
+  constexpr int G = 1 << GSH;     // lanes per neighbour
+  constexpr int EPS = 32 >> GSH;  // neighbours per warp step
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slab = blockIdx.x / p.blocks_per_slab;
   const int row = (blockIdx.x - slab * p.blocks_per_slab) * kWarpsPerBlock + warp;
@@ -46,28 +57,31 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) gat_fwd_kernel(const FwdP
   const int h = slab / p.col_parts;
   const int cp = slab - h * p.col_parts;
   const int c0 = cp * p.part_cols;
-  const int ncols = min(p.D - c0, p.part_cols);
-
-  const int G = 1 << p.gshift;
-  const int grp = lane >> p.gshift;
-  const int EPS = 32 >> p.gshift;  // neighbours per warp step
-  const int gstride = G * VW;      // floats between a lane's consecutive vector slots
+  const int nv = (min(p.D - c0, p.part_cols) + VW - 1) / VW;  // vectors in this slab row
+  const int grp = lane >> GSH;
   // first vector of this lane, shifted so that every slot is 128-byte-line aligned
   const int v0 = (lane & (G - 1)) - (((h * p.D + c0) / VW) & p.omask);
 
+  // per-slot base pointers (bytes).  A (lane, slot) outside the slab is clamped onto the nearest
+  // vector inside it; it then loads real data into an accumulator that is never stored.
+  const char* bp[VPL];
   bool act[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int v = v0 + i * G;
-    act[i] = v >= 0 && v * VW < ncols;
+    act[i] = v >= 0 && v < nv;
+    bp[i] = reinterpret_cast<const char*>(p.ft + h * p.D + c0 + min(max(v, 0), nv - 1) * VW);
   }
+  const unsigned ldb = (unsigned)(p.ld_ft * 4);
 
   const int beg = p.indptr[row], end = p.indptr[row + 1];
-  const float er_v = p.er ? p.er[(int64_t)row * p.H + h] : 0.f;
-  const float* __restrict__ ft_h = p.ft + h * p.D + c0 + v0 * VW;
+  const float slope = p.slope;
+  const int H = p.H;
+  const float er_v = p.er ? p.er[(int64_t)row * H + h] : 0.f;
   const float* __restrict__ el_h = p.el + h;
   const float* __restrict__ eb_h = p.eb ? p.eb + (int64_t)(p.Hb == 1 ? 0 : h) * p.n_edges : nullptr;
   const float* __restrict__ am_h = p.am ? p.am + (int64_t)h * p.n_edges : nullptr;
+  const float* __restrict__ cs = p.cs;
   const bool philox = (p.am == nullptr) && p.attn_p > 0.f;
 
   Vec<VW> acc[VPL];
@@ -78,9 +92,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) gat_fwd_kernel(const FwdP
 
   // ---- software pipeline over 32-neighbour chunks ----
   // stage 0: neighbour index; stage 1: logit operands (need the index); stage 2: row gathers
-  int u1 = 0, u2 = 0;                       // indices of chunk c+1 (u1) and c+2 (u2)
-  float z0 = -INFINITY, mul0 = 1.f;         // chunk c operands, complete
-  int u0 = 0;
   auto load_index = [&](int base) -> int {
     const int pos = base + lane;
     return pos < end ? __ldg(p.indices + pos) : 0;
@@ -90,54 +101,51 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) gat_fwd_kernel(const FwdP
     z = -INFINITY;
     mul = 1.f;
     if (pos < end) {
-      z = __ldg(el_h + (int64_t)u * p.H) + er_v;
+      z = __ldg(el_h + (int64_t)u * H) + er_v;
       if (eb_h) z += __ldg(eb_h + pos);
-      if (p.cs) mul = __ldg(p.cs + u);
+      if (cs) mul = __ldg(cs + u);
       if (am_h) mul *= __ldg(am_h + pos);
       else if (philox) mul *= philox_dropout_mul(p.seed, (uint32_t)__ldg(p.eid + pos), (uint32_t)h, p.attn_p, p.inv_keep);
     }
   };
-  u0 = load_index(beg);
-  u1 = load_index(beg + 32);
+  int u0 = load_index(beg), u1 = load_index(beg + 32), u2 = 0;
+  float z0, mul0;
   load_operands(beg, u0, z0, mul0);
 
   for (int base = beg; base < end; base += 32) {
     const int cnt = min(32, end - base);
-    // issue next stages' loads first; they are consumed one iteration later
+    // issue the next stages' loads first; they are consumed one iteration later
     u2 = load_index(base + 64);
     float z1, mul1;
     load_operands(base + 32, u1, z1, mul1);
 
     // ---- online softmax on chunk c ----
-    const float s = leaky_relu(z0, p.slope);  // -inf stays -inf (dropped edge / lane past the row end)
+    const float s = leaky_relu(z0, slope);  // -inf stays -inf (dropped edge / lane past the row end)
     const float m_new = fmaxf(m, warp_max(s));
     if (m_new > m) {
-      const float f = expf(m - m_new);  // m == -inf -> 0, and everything accumulated so far is 0
+      const float f = __expf(m - m_new);  // m == -inf -> 0, and everything accumulated so far is 0
       l_lane *= f;
 #pragma unroll
       for (int i = 0; i < VPL; ++i) acc[i].scale(f);
       m = m_new;
     }
-    const float pexp = (s == -INFINITY) ? 0.f : expf(s - m);
+    const float pexp = (s == -INFINITY) ? 0.f : __expf(s - m);
     l_lane += pexp;
     const float w_lane = pexp * mul0;
 
-    // ---- group = neighbour: gather slab rows, acc += w * row; NS steps in flight ----
-    for (int e = 0; e < cnt; e += NS * EPS) {
+    // ---- group = neighbour: gather slab rows, acc += w * row ----
+    int e = 0;
+    // full iterations: NS steps, every group has a neighbour
+    for (; e + NS * EPS <= cnt; e += NS * EPS) {
       Vec<VW> x[NS][VPL];
       float w[NS];
 #pragma unroll
       for (int s_ = 0; s_ < NS; ++s_) {
         const int my = e + s_ * EPS + grp;
-        const int uu = __shfl_sync(kFull, u0, my & 31);
-        const float ww = __shfl_sync(kFull, w_lane, my & 31);
-        const bool ok = my < cnt;
-        w[s_] = ok ? ww : 0.f;
-        const float* r = ft_h + (int64_t)uu * p.ld_ft;
+        const size_t off = (size_t)(unsigned)__shfl_sync(kFull, u0, my) * ldb;
+        w[s_] = __shfl_sync(kFull, w_lane, my);
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) {
-          if (ok && act[i]) x[s_][i].load_stream(r + i * gstride); else x[s_][i].zero();
-        }
+        for (int i = 0; i < VPL; ++i) x[s_][i].load(reinterpret_cast<const float*>(bp[i] + off));
       }
 #pragma unroll
       for (int s_ = 0; s_ < NS; ++s_) {
@@ -145,11 +153,25 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) gat_fwd_kernel(const FwdP
         for (int i = 0; i < VPL; ++i) acc[i].fma(w[s_], x[s_][i]);
       }
     }
+    // tail: single steps; a group past the end re-reads the chunk's last neighbour with weight 0
+    for (; e < cnt; e += EPS) {
+      const int my = e + grp;
+      const int src = min(my, cnt - 1);
+      const size_t off = (size_t)(unsigned)__shfl_sync(kFull, u0, src) * ldb;
+      const float ww = __shfl_sync(kFull, w_lane, src);
+      Vec<VW> x[VPL];
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) x[i].load(reinterpret_cast<const float*>(bp[i] + off));
+      const float wt = my < cnt ? ww : 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) acc[i].fma(wt, x[i]);
+    }
     u0 = u1; u1 = u2; z0 = z1; mul0 = mul1;
   }
 
   // ---- epilogue: combine the groups, normalise, degree-scale, store ----
   const float l = warp_sum(l_lane);
+#pragma unroll
   for (int o = G; o < 32; o <<= 1) {
 #pragma unroll
     for (int i = 0; i < VPL; ++i) acc[i].add_shfl_xor(o);
@@ -162,31 +184,28 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) gat_fwd_kernel(const FwdP
     for (int i = 0; i < VPL; ++i) {
       if (act[i]) {
         acc[i].scale(scale);
-        acc[i].store(o + i * gstride);
+        acc[i].store(o + i * G * VW);
       }
     }
   }
   if (cp == 0 && lane == 0) {
-    p.row_max[(int64_t)row * p.H + h] = m;
-    p.row_sum[(int64_t)row * p.H + h] = l;
+    p.row_max[(int64_t)row * H + h] = m;
+    p.row_sum[(int64_t)row * H + h] = l;
   }
 }
 
-template <int VW>
-static int launch_fwd_vw(const FwdParams& p, int vpl, dim3 grid, cudaStream_t st) {
+static int launch_fwd(const FwdParams& p, const Tiling& t, dim3 grid, cudaStream_t st) {
   dim3 block(kWarpsPerBlock * 32);
-  switch (vpl) {
-    case 1: gat_fwd_kernel<VW, 1><<<grid, block, 0, st>>>(p); break;
-    case 2: gat_fwd_kernel<VW, 2><<<grid, block, 0, st>>>(p); break;
-    case 3: gat_fwd_kernel<VW, 3><<<grid, block, 0, st>>>(p); break;
-    case 4: gat_fwd_kernel<VW, 4><<<grid, block, 0, st>>>(p); break;
-    case 5: gat_fwd_kernel<VW, 5><<<grid, block, 0, st>>>(p); break;
-    case 6: gat_fwd_kernel<VW, 6><<<grid, block, 0, st>>>(p); break;
-    case 8: gat_fwd_kernel<VW, 8><<<grid, block, 0, st>>>(p); break;
-    default: set_error("forward: unsupported vector slots per lane %d", vpl); return -1;
+#define BG_X(VW, GSH, VPL)                                        \
+  if (t.vw == VW && t.gshift == GSH && t.vpl == VPL) {            \
+    gat_fwd_kernel<VW, GSH, VPL><<<grid, block, 0, st>>>(p);      \
+    BG_LAUNCHED(1);                                               \
+    return 0;                                                     \
   }
-  BG_LAUNCHED(1);
-  return 0;
+  BG_COMBOS(BG_X)
+#undef BG_X
+  set_error("forward: no kernel for vw=%d lanes=%d slots=%d", t.vw, 1 << t.gshift, t.vpl);
+  return -1;
 }
 
 }  // namespace botgat
@@ -198,6 +217,7 @@ extern "C" int botgat_gat_forward(const botgat_graph* g, const botgat_fwd_args* 
   BG_REQUIRE(a->H > 0 && a->D > 0, "forward: bad H=%d D=%d", a->H, a->D);
   BG_REQUIRE(a->ft && a->el && a->out && a->row_max && a->row_sum, "forward: null ft/el/out/row_max/row_sum");
   BG_REQUIRE(a->ld_ft >= (int64_t)a->H * a->D && a->ld_out >= (int64_t)a->H * a->D, "forward: leading dimension < H*D");
+  BG_REQUIRE(a->ld_ft < (1ll << 30), "forward: ld_ft too large");
   BG_REQUIRE(a->eb ? (a->Hb == 1 || a->Hb == a->H) : true, "forward: Hb must be 1 or H when eb is given (got %d)", a->Hb);
   BG_REQUIRE(a->attn_p >= 0.f && a->attn_p < 1.f, "forward: attn_p must be in [0,1)");
   if (g->n_dst == 0) return 0;
@@ -213,15 +233,11 @@ extern "C" int botgat_gat_forward(const botgat_graph* g, const botgat_fwd_args* 
   p.cs = a->src_scale; p.ds = a->dst_scale; p.Hb = a->Hb;
   p.slope = a->slope; p.attn_p = a->attn_p; p.inv_keep = 1.f / (1.f - a->attn_p); p.seed = a->seed;
   p.out = a->out; p.row_max = a->row_max; p.row_sum = a->row_sum;
-  p.col_parts = t.col_parts; p.part_cols = t.part_cols; p.gshift = t.gshift; p.omask = t.omask;
+  p.col_parts = t.col_parts; p.part_cols = t.part_cols; p.omask = t.omask;
   p.blocks_per_slab = (p.n_rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int64_t nblocks = (int64_t)p.blocks_per_slab * a->H * t.col_parts;
   BG_REQUIRE(nblocks < (1ll << 31), "forward: grid too large");
-  dim3 grid((unsigned)nblocks);
-  int rc;
-  if (t.vw == 4) rc = launch_fwd_vw<4>(p, t.vpl, grid, st);
-  else if (t.vw == 2) rc = launch_fwd_vw<2>(p, t.vpl, grid, st);
-  else rc = launch_fwd_vw<1>(p, t.vpl, grid, st);
+  int rc = launch_fwd(p, t, dim3((unsigned)nblocks), st);
   if (rc) return rc;
   BG_CHECK(cudaGetLastError());
   return 0;

@@ -74,22 +74,22 @@ Tiling choose_tiling(int H, int D, int64_t ld_g, const void* pg, int64_t ld_o, c
   int G = std::min(gline, pow2ceil(nv));
   const int force_g = env_int("BOTGAT_G", 0);
   if (force_g >= 1 && force_g <= 32 && (force_g & (force_g - 1)) == 0) G = force_g;
-  static const int kVpl[] = {1, 2, 3, 4, 5, 6, 8};
   for (;; G <<= 1) {
+    t.gshift = 0;
+    while ((1 << t.gshift) < G) ++t.gshift;
     t.omask = can_align ? std::min(G, gline) - 1 : 0;
     // worst-case shift over all (head, part) slab starts
     int omax = 0;
     for (int h = 0; h < H && t.omask; ++h)
       for (int cp = 0; cp < t.col_parts; ++cp) omax = std::max(omax, ((h * D + cp * t.part_cols) / t.vw) & t.omask);
     const int need = (nv + omax + G - 1) / G;
+    // smallest instantiated slot count that covers the part at this group size (common.cuh BG_COMBOS)
     t.vpl = -1;
-    for (int c : kVpl)
-      if (c >= need) { t.vpl = c; break; }
+    for (int c = need; c <= kVplCap; ++c)
+      if (combo_supported(t.vw, t.gshift, c)) { t.vpl = c; break; }
     if (t.vpl > 0 || G >= 32) break;
   }
   if (t.vpl < 0) t.vpl = kVplCap;  // unreachable: cap_cols guarantees a fit at G = 32
-  t.gshift = 0;
-  while ((1 << t.gshift) < G) ++t.gshift;
   return t;
 }
 
