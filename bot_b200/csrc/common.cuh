@@ -60,7 +60,10 @@ struct botgat_graph {
 
 namespace botgat {
 
-constexpr int kWarpsPerBlock = 8;
+#ifndef BG_WPB
+#define BG_WPB 4
+#endif
+constexpr int kWarpsPerBlock = BG_WPB;
 constexpr unsigned kFull = 0xffffffffu;
 
 // ---------------------------------------------------------------------------

@@ -79,14 +79,22 @@ struct SrcOps {
   float eb, amul;
 };
 
-// 3 blocks (24 warps) per SM: measured faster than 2 blocks with more loads in flight per warp (profiles/r01_*)
-#ifndef BG_MINB
-#define BG_MINB 3
+// 4 blocks x 4 warps (16 warps, <= 128 registers) per SM with 4 steps in flight: the src pass carries ft[u] and the
+// dot product besides the accumulators, and prefers registers over occupancy (profiles/r01_sweeps.md)
+#ifndef BG_MINB_BWD
+#define BG_MINB_BWD 4
+#endif
+#ifndef BG_NS_BWD
+#define BG_NS_BWD 4
 #endif
 
 template <int VW, int GSH, int VPL>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB) gat_bwd_src_kernel(const BwdParams p) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB_BWD) gat_bwd_src_kernel(const BwdParams p) {
+#ifdef BG_NS_BWD
+  constexpr int NS = BG_NS_BWD;
+#else
   constexpr int NS = steps_in_flight(VPL);
+#endif
   constexpr int G = 1 << GSH;
   constexpr int EPS = 32 >> GSH;
   constexpr int GSTRIDE = G * VW;

@@ -40,9 +40,10 @@ struct FwdParams {
   int blocks_per_slab;
 };
 
-// 3 blocks (24 warps) per SM: measured faster than 2 blocks with more loads in flight per warp (profiles/r01_*)
+// 6 blocks x 4 warps (24 warps, <= 80 registers) per SM with 2 steps in flight: the best of the occupancy /
+// loads-in-flight sweep on B200 (profiles/r01_sweeps.md)
 #ifndef BG_MINB
-#define BG_MINB 3
+#define BG_MINB 6
 #endif
 
 template <int VW, int GSH, int VPL>
