@@ -34,7 +34,7 @@ class FwdArgs(C.Structure):
         ("ld_ft", C.c_int64), ("ld_out", C.c_int64),
         ("ft", c_vp), ("el", c_vp), ("er", c_vp), ("eb", c_vp),
         ("Hb", C.c_int32), ("col_parts", C.c_int32),
-        ("am", c_vp), ("src_scale", c_vp), ("dst_scale", c_vp),
+        ("am", c_vp), ("ee", c_vp), ("keep", c_vp), ("attn_mul", c_vp), ("src_scale", c_vp), ("dst_scale", c_vp),
         ("slope", C.c_float), ("attn_p", C.c_float), ("seed", C.c_uint64),
         ("out", c_vp), ("row_max", c_vp), ("row_sum", c_vp),
     ]
@@ -46,7 +46,7 @@ class BwdArgs(C.Structure):
         ("ld_ft", C.c_int64), ("ld_out", C.c_int64), ("ld_gft", C.c_int64),
         ("ft", c_vp), ("el", c_vp), ("er", c_vp), ("eb_out", c_vp),
         ("Hb", C.c_int32), ("phases", C.c_int32),
-        ("am_out", c_vp), ("src_scale", c_vp), ("dst_scale", c_vp),
+        ("am_out", c_vp), ("ee", c_vp), ("keep", c_vp), ("attn_mul", c_vp), ("src_scale", c_vp), ("dst_scale", c_vp),
         ("slope", C.c_float), ("attn_p", C.c_float), ("seed", C.c_uint64),
         ("out", c_vp), ("row_max", c_vp), ("row_sum", c_vp), ("gout", c_vp),
         ("drec", c_vp), ("gprime", c_vp), ("gz", c_vp),

@@ -31,6 +31,9 @@ struct BwdParams {
   int H, D;
   int64_t ld_ft, ld_g, ld_gft;
   const float *ft, *el, *eb, *am, *cs;
+  const float *ee, *amul_e;  // edge-id-ordered operands (direct mode)
+  const uint8_t* keep;
+  float* gz_e;         // (n_edges, H) edge-id order (direct mode), written by the src pass
   const float* g;      // g' (n_dst, ld_g)
   const float4* drec;  // (H, n_dst)
   int Hb;
@@ -135,15 +138,25 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB_BWD) gat_bwd_src_
   const float* __restrict__ eb_h = p.eb ? p.eb + (int64_t)(p.Hb == 1 ? 0 : h) * p.n_edges : nullptr;
   const float* __restrict__ am_h = p.am ? p.am + (int64_t)h * p.n_edges : nullptr;
   float* __restrict__ gz_h = p.gz ? p.gz + (int64_t)h * p.n_edges : nullptr;
-  const bool philox = (p.am == nullptr) && p.attn_p > 0.f;
+  const float* __restrict__ ee_h = p.ee ? p.ee + h : nullptr;
+  const float* __restrict__ amul_h = p.amul_e ? p.amul_e + h : nullptr;
+  const uint8_t* __restrict__ keep = p.keep;
+  float* __restrict__ gze_h = p.gz_e ? p.gz_e + h : nullptr;
+  const int H = p.H;
+  const bool philox = (p.am == nullptr) && (p.amul_e == nullptr) && p.attn_p > 0.f;
+  const bool need_eid = ee_h || amul_h || keep || philox || gze_h;
   float gel_lane = 0.f;
 
   // 3-stage software pipeline, as in the forward: index (c+2) | records (c+1) | row gathers (c)
-  auto load_index = [&](int base) -> int {
+  auto load_index = [&](int base, int& v, int& k) {
     const int pos = base + lane;
-    return pos < end ? __ldg(p.indices + pos) : 0;
+    v = k = 0;
+    if (pos < end) {
+      v = __ldg(p.indices + pos);
+      if (need_eid) k = __ldg(p.eid + pos);
+    }
   };
-  auto load_operands = [&](int base, int v, SrcOps& o) {
+  auto load_operands = [&](int base, int v, int k, SrcOps& o) {
     const int pos = base + lane;
     o.rec = make_float4(0.f, 0.f, 0.f, 0.f);
     o.eb = -INFINITY;  // lanes past the row end behave like dropped edges: alpha = 0
@@ -151,8 +164,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB_BWD) gat_bwd_src_
     if (pos < end) {
       o.rec = __ldg(drec_h + v);
       o.eb = eb_h ? __ldg(eb_h + pos) : 0.f;
+      if (ee_h) o.eb += __ldg(ee_h + (int64_t)k * H);
+      if (keep && !__ldg(keep + k)) o.eb = -INFINITY;
       if (am_h) o.amul = __ldg(am_h + pos);
-      else if (philox) o.amul = philox_dropout_mul(p.seed, (uint32_t)__ldg(p.eid + pos), (uint32_t)h, p.attn_p, p.inv_keep);
+      else if (amul_h) o.amul = __ldg(amul_h + (int64_t)k * H);
+      else if (philox) o.amul = philox_dropout_mul(p.seed, (uint32_t)k, (uint32_t)h, p.attn_p, p.inv_keep);
     }
   };
   // one step: the group's neighbour row is in x; acc += w*x, and the dot <x, ft[u]> goes to the owner lane
@@ -169,14 +185,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB_BWD) gat_bwd_src_
     if (lane >= e_s && lane < e_s + EPS) d_lane = got;
   };
 
-  int vtx0 = load_index(beg), vtx1 = load_index(beg + 32), vtx2 = 0;
+  int vtx0, vtx1, vtx2 = 0, k0, k1, k2 = 0;
+  load_index(beg, vtx0, k0);
+  load_index(beg + 32, vtx1, k1);
   SrcOps o0, o1;
-  load_operands(beg, vtx0, o0);
+  load_operands(beg, vtx0, k0, o0);
 
   for (int base = beg; base < end; base += 32) {
     const int cnt = min(32, end - base);
-    vtx2 = load_index(base + 64);
-    load_operands(base + 32, vtx1, o1);
+    load_index(base + 64, vtx2, k2);
+    load_operands(base + 32, vtx1, k1, o1);
 
     // lane = neighbour: recompute the attention weight of this edge
     const float z = el_u + o0.rec.x + o0.eb;
@@ -215,8 +233,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB_BWD) gat_bwd_src_
     // d_lane = <src_scale*ft[u], g'[v]>; softmax + leaky_relu adjoint (App. A.3)
     const float gz = alpha * (d_lane * o0.amul - o0.rec.w) * dz;
     if (gz_h && lane < cnt) gz_h[base + lane] = gz;
+    if (gze_h && lane < cnt) gze_h[(int64_t)k0 * H] = gz;
     gel_lane += gz;
-    vtx0 = vtx1; vtx1 = vtx2; o0 = o1;
+    vtx0 = vtx1; vtx1 = vtx2; k0 = k1; k1 = k2; o0 = o1;
   }
 
 #pragma unroll
@@ -293,7 +312,8 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
   BG_REQUIRE(!a->dst_scale || a->gprime, "backward: gprime workspace required with dst_scale");
   BG_REQUIRE(!a->grad_er || a->grad_ee || g->n_edges == 0,
              "backward: grad_er needs the grad_ee buffer (it is reduced from it)");
-  BG_REQUIRE(!a->grad_ee || a->gz || g->n_edges == 0, "backward: grad_ee / grad_er need the gz workspace");
+  BG_REQUIRE(!(a->eb_out && (a->ee || a->keep)), "backward: pass edge logits either staged (eb_out) or by edge id (ee/keep)");
+  BG_REQUIRE(!(a->am_out && a->attn_mul), "backward: pass the dropout multiplier either staged or by edge id");
   const int64_t HD = (int64_t)a->H * a->D;
   BG_REQUIRE(a->ld_ft >= HD && a->ld_out >= HD && a->ld_gft >= HD, "backward: leading dimension < H*D");
   BG_REQUIRE(a->eb_out ? (a->Hb == 1 || a->Hb == a->H) : true, "backward: Hb must be 1 or H");
@@ -319,7 +339,11 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
     p.H = a->H; p.D = a->D; p.ld_ft = a->ld_ft; p.ld_g = a->ld_out; p.ld_gft = a->ld_gft;
     p.ft = a->ft; p.el = a->el; p.cs = a->src_scale; p.g = gp; p.drec = (const float4*)a->drec;
     p.Hb = a->Hb; p.slope = a->slope; p.attn_p = a->attn_p; p.inv_keep = 1.f / (1.f - a->attn_p); p.seed = a->seed;
-    p.grad_ft = a->grad_ft; p.grad_el = a->grad_el; p.gz = a->gz;
+    p.grad_ft = a->grad_ft; p.grad_el = a->grad_el;
+    p.ee = a->ee; p.keep = a->keep; p.amul_e = a->attn_mul;
+    // grad_ee is written straight in edge-id order by the src pass unless the caller supplies the staged
+    // workspace gz (then phase 4 un-stages it)
+    p.gz = a->gz; p.gz_e = a->gz ? nullptr : a->grad_ee;
     // the gathered table is g' (ld_out); ft and grad_ft are row-local and only constrain the vector width
     const int64_t ld_o = a->ld_ft | a->ld_gft;  // low bits clear iff both are multiples of the vector width
     const uintptr_t po = (uintptr_t)a->ft | (uintptr_t)a->grad_ft;
@@ -335,7 +359,7 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
     BG_CHECK(cudaGetLastError());
   }
 
-  if ((phases & 4) && a->grad_ee && g->n_edges > 0) {
+  if ((phases & 4) && a->grad_ee && a->gz && g->n_edges > 0) {
     int rc = botgat_edge_unstage(g, BOTGAT_ORDER_OUT, a->H, a->gz, a->grad_ee, stream);
     if (rc) return rc;
   }

@@ -32,6 +32,8 @@ struct FwdParams {
   int H, D;
   int64_t ld_ft, ld_out;
   const float *ft, *el, *er, *eb, *am, *cs, *ds;
+  const float *ee, *amul_e;  // edge-id-ordered operands (direct mode)
+  const uint8_t* keep;
   int Hb;
   float slope, attn_p, inv_keep;
   uint64_t seed;
@@ -83,7 +85,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB) gat_fwd_kernel(c
   const float* __restrict__ eb_h = p.eb ? p.eb + (int64_t)(p.Hb == 1 ? 0 : h) * p.n_edges : nullptr;
   const float* __restrict__ am_h = p.am ? p.am + (int64_t)h * p.n_edges : nullptr;
   const float* __restrict__ cs = p.cs;
-  const bool philox = (p.am == nullptr) && p.attn_p > 0.f;
+  const float* __restrict__ ee_h = p.ee ? p.ee + h : nullptr;
+  const float* __restrict__ amul_h = p.amul_e ? p.amul_e + h : nullptr;
+  const uint8_t* __restrict__ keep = p.keep;
+  const bool philox = (p.am == nullptr) && (p.amul_e == nullptr) && p.attn_p > 0.f;
+  // direct mode: per-edge operands are indexed by edge id inside the pipeline (random 32-byte sectors from
+  // DRAM, which this L2-bound kernel leaves idle) instead of being permuted into CSR order by a staging pass
+  const bool need_eid = ee_h || amul_h || keep || philox;
 
   Vec<VW> acc[VPL];
 #pragma unroll
@@ -93,32 +101,41 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB) gat_fwd_kernel(c
 
   // ---- software pipeline over 32-neighbour chunks ----
   // stage 0: neighbour index; stage 1: logit operands (need the index); stage 2: row gathers
-  auto load_index = [&](int base) -> int {
+  auto load_index = [&](int base, int& u, int& k) {
     const int pos = base + lane;
-    return pos < end ? __ldg(p.indices + pos) : 0;
+    u = k = 0;
+    if (pos < end) {
+      u = __ldg(p.indices + pos);
+      if (need_eid) k = __ldg(p.eid + pos);
+    }
   };
-  auto load_operands = [&](int base, int u, float& z, float& mul) {
+  auto load_operands = [&](int base, int u, int k, float& z, float& mul) {
     const int pos = base + lane;
     z = -INFINITY;
     mul = 1.f;
     if (pos < end) {
       z = __ldg(el_h + (int64_t)u * H) + er_v;
       if (eb_h) z += __ldg(eb_h + pos);
+      if (ee_h) z += __ldg(ee_h + (int64_t)k * H);
+      if (keep && !__ldg(keep + k)) z = -INFINITY;
       if (cs) mul = __ldg(cs + u);
       if (am_h) mul *= __ldg(am_h + pos);
-      else if (philox) mul *= philox_dropout_mul(p.seed, (uint32_t)__ldg(p.eid + pos), (uint32_t)h, p.attn_p, p.inv_keep);
+      else if (amul_h) mul *= __ldg(amul_h + (int64_t)k * H);
+      else if (philox) mul *= philox_dropout_mul(p.seed, (uint32_t)k, (uint32_t)h, p.attn_p, p.inv_keep);
     }
   };
-  int u0 = load_index(beg), u1 = load_index(beg + 32), u2 = 0;
+  int u0, u1, u2 = 0, k0, k1, k2 = 0;
+  load_index(beg, u0, k0);
+  load_index(beg + 32, u1, k1);
   float z0, mul0;
-  load_operands(beg, u0, z0, mul0);
+  load_operands(beg, u0, k0, z0, mul0);
 
   for (int base = beg; base < end; base += 32) {
     const int cnt = min(32, end - base);
     // issue the next stages' loads first; they are consumed one iteration later
-    u2 = load_index(base + 64);
+    load_index(base + 64, u2, k2);
     float z1, mul1;
-    load_operands(base + 32, u1, z1, mul1);
+    load_operands(base + 32, u1, k1, z1, mul1);
 
     // ---- online softmax on chunk c ----
     const float s = leaky_relu(z0, slope);  // -inf stays -inf (dropped edge / lane past the row end)
@@ -167,7 +184,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB) gat_fwd_kernel(c
 #pragma unroll
       for (int i = 0; i < VPL; ++i) acc[i].fma(wt, x[i]);
     }
-    u0 = u1; u1 = u2; z0 = z1; mul0 = mul1;
+    u0 = u1; u1 = u2; k1 = k2; z0 = z1; mul0 = mul1;
   }
 
   // ---- epilogue: combine the groups, normalise, degree-scale, store ----
@@ -220,6 +237,8 @@ extern "C" int botgat_gat_forward(const botgat_graph* g, const botgat_fwd_args* 
   BG_REQUIRE(a->ld_ft >= (int64_t)a->H * a->D && a->ld_out >= (int64_t)a->H * a->D, "forward: leading dimension < H*D");
   BG_REQUIRE(a->ld_ft < (1ll << 30), "forward: ld_ft too large");
   BG_REQUIRE(a->eb ? (a->Hb == 1 || a->Hb == a->H) : true, "forward: Hb must be 1 or H when eb is given (got %d)", a->Hb);
+  BG_REQUIRE(!(a->eb && (a->ee || a->keep)), "forward: pass edge logits either staged (eb) or by edge id (ee/keep)");
+  BG_REQUIRE(!(a->am && a->attn_mul), "forward: pass the dropout multiplier either staged (am) or by edge id (attn_mul)");
   BG_REQUIRE(a->attn_p >= 0.f && a->attn_p < 1.f, "forward: attn_p must be in [0,1)");
   if (g->n_dst == 0) return 0;
   DeviceGuard guard(g->device);
@@ -232,6 +251,7 @@ extern "C" int botgat_gat_forward(const botgat_graph* g, const botgat_fwd_args* 
   p.H = a->H; p.D = a->D; p.ld_ft = a->ld_ft; p.ld_out = a->ld_out;
   p.ft = a->ft; p.el = a->el; p.er = a->er; p.eb = a->eb; p.am = a->am;
   p.cs = a->src_scale; p.ds = a->dst_scale; p.Hb = a->Hb;
+  p.ee = a->ee; p.keep = a->keep; p.amul_e = a->attn_mul;
   p.slope = a->slope; p.attn_p = a->attn_p; p.inv_keep = 1.f / (1.f - a->attn_p); p.seed = a->seed;
   p.out = a->out; p.row_max = a->row_max; p.row_sum = a->row_sum;
   p.col_parts = t.col_parts; p.part_cols = t.part_cols; p.omask = t.omask;

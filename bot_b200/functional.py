@@ -53,6 +53,11 @@ class _Span:
 
 timer = None  # set to a KernelTimer to record
 
+# How per-edge operands (edge logits, keep set, dropout multiplier) reach the kernels:
+#   "direct": indexed by edge id inside the kernels' software pipeline (no extra pass; default)
+#   "staged": permuted into CSR order, head-major, by botgat_edge_stage / botgat_edge_unstage first
+edge_mode = "direct"
+
 
 def _span(name):
     return _Span(timer, name)
@@ -124,8 +129,9 @@ class GATFusedFn(torch.autograd.Function):
                 raise ValueError("keep must have one entry per edge")
         src_scale, dst_scale = _f32c(src_scale, "src_scale"), _f32c(dst_scale, "dst_scale")
 
+        staged = edge_mode == "staged"
         with torch.cuda.device(ft.device):
-            eb_in, Hb, am_in = edge_stage(graph, _lib.ORDER_IN, H, ee, keep, attn_mul)
+            eb_in, Hb, am_in = edge_stage(graph, _lib.ORDER_IN, H, ee, keep, attn_mul) if staged else (None, 0, None)
             out = torch.empty((N_d, H, D), dtype=torch.float32, device=ft.device)
             row_max = torch.empty((N_d, H), dtype=torch.float32, device=ft.device)
             row_sum = torch.empty((N_d, H), dtype=torch.float32, device=ft.device)
@@ -134,6 +140,10 @@ class GATFusedFn(torch.autograd.Function):
             a.ft, a.el, a.er = ft.data_ptr(), el.data_ptr(), (er.data_ptr() if er is not None else None)
             a.eb, a.Hb, a.col_parts = (eb_in.data_ptr() if eb_in is not None else None), Hb, 0
             a.am = am_in.data_ptr() if am_in is not None else None
+            if not staged:
+                a.ee = ee.data_ptr() if ee is not None else None
+                a.keep = keep.data_ptr() if keep is not None else None
+                a.attn_mul = attn_mul.data_ptr() if attn_mul is not None else None
             a.src_scale = src_scale.data_ptr() if src_scale is not None else None
             a.dst_scale = dst_scale.data_ptr() if dst_scale is not None else None
             a.slope, a.attn_p, a.seed = float(slope), float(attn_p if attn_mul is None else 0.0), int(seed)
@@ -143,7 +153,7 @@ class GATFusedFn(torch.autograd.Function):
             _lib.check(rc, "botgat_gat_forward")
 
         ctx.graph = graph
-        ctx.cfg = (H, D, Hb, float(slope), float(a.attn_p), int(seed))
+        ctx.cfg = (H, D, staged, float(slope), float(a.attn_p), int(seed))
         ctx.save_for_backward(ft, el, er, ee, keep, attn_mul, src_scale, dst_scale, out, row_max, row_sum)
         return out
 
@@ -153,7 +163,7 @@ class GATFusedFn(torch.autograd.Function):
         graph = ctx.graph
         h = graph._ensure()
         ft, el, er, ee, keep, attn_mul, src_scale, dst_scale, out, row_max, row_sum = ctx.saved_tensors
-        H, D, Hb, slope, attn_p, seed = ctx.cfg
+        H, D, staged, slope, attn_p, seed = ctx.cfg
         N_s, N_d, E = ft.shape[0], out.shape[0], graph.number_of_edges()
         dev = ft.device
         need_er = er is not None and ctx.needs_input_grad[3]
@@ -164,7 +174,7 @@ class GATFusedFn(torch.autograd.Function):
             return t.data_ptr() if t is not None else None
 
         with torch.cuda.device(dev):
-            eb_out, _, am_out = edge_stage(graph, _lib.ORDER_OUT, H, ee, keep, attn_mul)
+            eb_out, Hb, am_out = edge_stage(graph, _lib.ORDER_OUT, H, ee, keep, attn_mul) if staged else (None, 0, None)
             drec = torch.empty((H, N_d, 4), dtype=torch.float32, device=dev)
             gprime = torch.empty_like(gout) if dst_scale is not None else None
             grad_ft = torch.empty_like(ft)
@@ -173,12 +183,14 @@ class GATFusedFn(torch.autograd.Function):
             # gz (out-CSR order) -> grad_ee (edge-id order); grad_er is reduced from grad_ee
             gz = grad_ee = None
             if need_er or need_ee:
-                gz = torch.empty((H, E), dtype=torch.float32, device=dev)
+                gz = torch.empty((H, E), dtype=torch.float32, device=dev) if staged else None
                 grad_ee = torch.empty((E, H), dtype=torch.float32, device=dev)
             a = _lib.BwdArgs()
             a.H, a.D, a.ld_ft, a.ld_out, a.ld_gft = H, D, H * D, H * D, H * D
             a.ft, a.el, a.er = ft.data_ptr(), el.data_ptr(), p(er)
             a.eb_out, a.Hb, a.phases, a.am_out = p(eb_out), Hb, 0, p(am_out)
+            if not staged:
+                a.ee, a.keep, a.attn_mul = p(ee), p(keep), p(attn_mul)
             a.src_scale, a.dst_scale = p(src_scale), p(dst_scale)
             a.slope, a.attn_p, a.seed = slope, attn_p, seed
             a.out, a.row_max, a.row_sum, a.gout = out.data_ptr(), row_max.data_ptr(), row_sum.data_ptr(), gout.data_ptr()

@@ -144,6 +144,10 @@ typedef struct {
   int32_t Hb;             /* 0, 1 or H */
   int32_t col_parts;      /* split each head's D columns in this many parts; 0 = auto */
   const float* am;        /* (H, n_edges) in-CSR order, or NULL */
+  /* the same operands in EDGE-ID order (direct mode, no staging pass; exclusive with eb / am): */
+  const float* ee;        /* (n_edges, H) `attn_edge_fc(feat_edge)`, or NULL */
+  const uint8_t* keep;    /* (n_edges) edge-drop keep set, or NULL */
+  const float* attn_mul;  /* (n_edges, H) attention-dropout multiplier, or NULL */
   const float* src_scale; /* (n_src) or NULL */
   const float* dst_scale; /* (n_dst) or NULL */
   float slope;            /* leaky_relu negative slope */
@@ -164,8 +168,8 @@ int botgat_gat_forward(const botgat_graph* g, const botgat_fwd_args* a /* HOST *
  *                   grad_el and, on request, gz = d(loss)/d(edge logit) per
  *                   (edge, head) in out-CSR order.  The attention weights are
  *                   recomputed from (el, er, eb, row_max, row_sum).
- *   phase 4, edge : gz -> grad_ee (edge-id order), grad_er[v] = sum of grad_ee
- *                   over the in-edges of v (in-CSR walk, 4*H-byte records).
+ *   phase 4, edge : [gz -> grad_ee (edge-id order) when staged;] grad_er[v] = sum of
+ *                   grad_ee over the in-edges of v (in-CSR walk, 4*H-byte records).
  * ---------------------------------------------------------------------- */
 typedef struct {
   int32_t H, D;
@@ -177,6 +181,9 @@ typedef struct {
   int32_t Hb;
   int32_t phases;         /* bitmask of phases to run (1 node, 2 src, 4 edge); 0 = all (profiling splits them) */
   const float* am_out;    /* (H, n_edges) out-CSR order or NULL */
+  const float* ee;        /* edge-id-order operands, as in botgat_fwd_args (exclusive with eb_out / am_out) */
+  const uint8_t* keep;
+  const float* attn_mul;
   const float* src_scale;
   const float* dst_scale;
   float slope;
@@ -189,11 +196,12 @@ typedef struct {
   /* workspaces */
   float* drec;            /* (H, n_dst, 4) */
   float* gprime;          /* (n_dst, ld_out); required iff dst_scale != NULL */
-  float* gz;              /* (H, n_edges); required iff grad_er or grad_ee is requested */
+  float* gz;              /* (H, n_edges) or NULL.  NULL: the src pass writes grad_ee directly in edge-id order;
+                             given: it writes gz in out-CSR order and phase 4 un-stages it into grad_ee */
   /* outputs */
   float* grad_ft;         /* (n_src, ld_gft) w.r.t. the unscaled ft */
   float* grad_el;         /* (n_src, H) */
-  float* grad_ee;         /* (n_edges, H) edge-id order; required iff grad_er is requested (it is its input) */
+  float* grad_ee;         /* (n_edges, H) edge-id order, or NULL; required when grad_er is requested (its input) */
   float* grad_er;         /* (n_dst, H) or NULL */
 } botgat_bwd_args;
 int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args* a /* HOST */, void* stream);
