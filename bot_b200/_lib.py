@@ -50,7 +50,7 @@ class BwdArgs(C.Structure):
         ("slope", C.c_float), ("attn_p", C.c_float), ("seed", C.c_uint64),
         ("out", c_vp), ("row_max", c_vp), ("row_sum", c_vp), ("gout", c_vp),
         ("drec", c_vp), ("gprime", c_vp), ("gz", c_vp),
-        ("grad_ft", c_vp), ("grad_el", c_vp), ("grad_ee", c_vp), ("grad_er", c_vp),
+        ("grad_ft", c_vp), ("grad_el", c_vp), ("grad_ee", c_vp), ("ld_gee", C.c_int64), ("grad_er", c_vp),
     ]
 
 
@@ -66,8 +66,9 @@ SIGNATURES = {
     "botgat_coo_to_bidirected": (C.c_int, [C.c_int64, C.c_int64, c_vp, c_vp, c_vp, c_vp, c_i64p, C.c_int, c_vp]),
     "botgat_coo_remove_self_loop": (C.c_int, [C.c_int64, c_vp, c_vp, c_vp, c_vp, c_i64p, C.c_int, c_vp]),
     "botgat_coo_add_self_loop": (C.c_int, [C.c_int64, C.c_int64, c_vp, c_vp, c_vp, c_vp, C.c_int, c_vp]),
-    "botgat_edge_stage": (C.c_int, [c_vp, C.c_int, C.c_int32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "botgat_edge_unstage": (C.c_int, [c_vp, C.c_int, C.c_int32, c_vp, c_vp, c_vp]),
+    "botgat_edge_stage": (C.c_int, [c_vp, C.c_int, C.c_int32, c_vp, C.c_int64, c_vp, c_vp, C.c_int64, c_vp, c_vp, c_vp]),
+    "botgat_edge_unstage": (C.c_int, [c_vp, C.c_int, C.c_int32, c_vp, c_vp, C.c_int64, c_vp]),
+    "botgat_edge_reduce_dst": (C.c_int, [c_vp, C.c_int32, c_vp, C.c_int64, c_vp, c_vp]),
     "botgat_gat_forward": (C.c_int, [c_vp, C.POINTER(FwdArgs), c_vp]),
     "botgat_gat_backward": (C.c_int, [c_vp, C.POINTER(BwdArgs), c_vp]),
     "botgat_partition_1d": (C.c_int, [c_vp, C.c_int32, c_i64p, c_vp]),

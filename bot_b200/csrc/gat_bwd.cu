@@ -257,35 +257,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB_BWD) gat_bwd_src_
   if (lane == 0) p.grad_el[(int64_t)row * p.H + h] = gel;
 }
 
-// ---------------------------------------------------------------------------
-// edge phase, second half: grad_er[v,h] = sum over in-edges k of grad_ee[k,h]
-// (one warp per destination row; lanes stride the row's edges, all heads at once)
-// ---------------------------------------------------------------------------
-template <int HMAX>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-gat_bwd_er_kernel(int n_dst, int H, const int32_t* __restrict__ indptr, const int32_t* __restrict__ eid,
-                  const float* __restrict__ grad_ee, float* __restrict__ grad_er) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int v = blockIdx.x * kWarpsPerBlock + warp;
-  if (v >= n_dst) return;
-  float s[HMAX];
-#pragma unroll
-  for (int h = 0; h < HMAX; ++h) s[h] = 0.f;
-  for (int pos = indptr[v] + lane; pos < indptr[v + 1]; pos += 32) {
-    const float* r = grad_ee + (int64_t)__ldg(eid + pos) * H;
-#pragma unroll
-    for (int h = 0; h < HMAX; ++h)
-      if (h < H) s[h] += __ldg(r + h);
-  }
-#pragma unroll
-  for (int h = 0; h < HMAX; ++h) {
-    if (h < H) {
-      const float t = warp_sum(s[h]);
-      if (lane == 0) grad_er[(int64_t)v * H + h] = t;
-    }
-  }
-}
-
 static int launch_src(const BwdParams& p, const Tiling& t, dim3 grid, cudaStream_t st) {
   dim3 block(kWarpsPerBlock * 32);
 #define BG_X(VW, GSH, VPL)                                            \
@@ -322,6 +293,8 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
   cudaStream_t st = (cudaStream_t)stream;
   dim3 block(kWarpsPerBlock * 32);
   const int phases = a->phases ? a->phases : 7;
+  const int64_t ld_gee = a->ld_gee > 0 ? a->ld_gee : a->H;
+  BG_REQUIRE(a->gz || ld_gee == a->H, "backward: a padded grad_ee needs the staged path (gz workspace)");
 
   if (phases & 1) {
     dim3 grid((unsigned)((g->n_dst + kWarpsPerBlock - 1) / kWarpsPerBlock));
@@ -360,21 +333,12 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
   }
 
   if ((phases & 4) && a->grad_ee && a->gz && g->n_edges > 0) {
-    int rc = botgat_edge_unstage(g, BOTGAT_ORDER_OUT, a->H, a->gz, a->grad_ee, stream);
+    int rc = botgat_edge_unstage(g, BOTGAT_ORDER_OUT, a->H, a->gz, a->grad_ee, ld_gee, stream);
     if (rc) return rc;
   }
   if ((phases & 4) && a->grad_er) {
-    dim3 grid((unsigned)((g->n_dst + kWarpsPerBlock - 1) / kWarpsPerBlock));
-    if (a->H <= 8)
-      gat_bwd_er_kernel<8><<<grid, block, 0, st>>>((int)g->n_dst, a->H, g->in_indptr, g->in_eid, a->grad_ee, a->grad_er);
-    else if (a->H <= 32)
-      gat_bwd_er_kernel<32><<<grid, block, 0, st>>>((int)g->n_dst, a->H, g->in_indptr, g->in_eid, a->grad_ee, a->grad_er);
-    else {
-      set_error("backward: grad_er supports at most 32 heads (got %d)", a->H);
-      return -1;
-    }
-    BG_LAUNCHED(1);
-    BG_CHECK(cudaGetLastError());
+    int rc = botgat_edge_reduce_dst(g, a->H, a->grad_ee, ld_gee, a->grad_er, stream);
+    if (rc) return rc;
   }
   return 0;
 }

@@ -405,68 +405,6 @@ extern "C" int botgat_coo_add_self_loop(int64_t n_nodes, int64_t n_edges, const 
 }
 
 // ---------------------------------------------------------------------------
-// per-edge operand staging (edge-id order <-> CSR order, head-major)
-// ---------------------------------------------------------------------------
-namespace botgat {
-
-__global__ void k_edge_stage(int64_t n_edges, int H, int Hb, const int32_t* __restrict__ eid,
-                             const float* __restrict__ ee, const uint8_t* __restrict__ keep,
-                             const float* __restrict__ attn_mul, float* __restrict__ eb, float* __restrict__ am) {
-  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_edges; p += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t e = eid[p];
-    if (eb) {
-      const bool dropped = keep && !keep[e];
-      for (int h = 0; h < Hb; ++h) {
-        const float v = ee ? ee[e * H + h] : 0.f;
-        eb[(int64_t)h * n_edges + p] = dropped ? -INFINITY : v;
-      }
-    }
-    if (am) {
-      for (int h = 0; h < H; ++h) am[(int64_t)h * n_edges + p] = attn_mul[e * H + h];
-    }
-  }
-}
-
-__global__ void k_edge_unstage(int64_t n_edges, int H, const int32_t* __restrict__ eid, const float* __restrict__ gz,
-                               float* __restrict__ grad_ee) {
-  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_edges; p += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t e = eid[p];
-    for (int h = 0; h < H; ++h) grad_ee[e * H + h] = gz[(int64_t)h * n_edges + p];
-  }
-}
-
-}  // namespace botgat
-
-extern "C" int botgat_edge_stage(const botgat_graph* g, int order, int32_t H, const float* ee, const uint8_t* keep,
-                                 const float* attn_mul, float* eb, float* am, void* stream) {
-  BG_REQUIRE(g && H > 0, "edge_stage: bad arguments");
-  BG_REQUIRE(order == BOTGAT_ORDER_IN || order == BOTGAT_ORDER_OUT, "edge_stage: bad order %d", order);
-  BG_REQUIRE((eb != nullptr) == (ee != nullptr || keep != nullptr), "edge_stage: eb must be given iff ee or keep is");
-  BG_REQUIRE((am != nullptr) == (attn_mul != nullptr), "edge_stage: am must be given iff attn_mul is");
-  if (g->n_edges == 0 || (!eb && !am)) return 0;
-  DeviceGuard guard(g->device);
-  cudaStream_t st = (cudaStream_t)stream;
-  const int32_t* eid = order == BOTGAT_ORDER_IN ? g->in_eid : g->out_eid;
-  k_edge_stage<<<grid_for(g->n_edges), 256, 0, st>>>(g->n_edges, H, ee ? H : 1, eid, ee, keep, attn_mul, eb, am); BG_LAUNCHED(1);
-  BG_CHECK(cudaGetLastError());
-  return 0;
-}
-
-extern "C" int botgat_edge_unstage(const botgat_graph* g, int order, int32_t H, const float* gz, float* grad_ee,
-                                   void* stream) {
-  BG_REQUIRE(g && H > 0, "edge_unstage: bad arguments");
-  BG_REQUIRE(order == BOTGAT_ORDER_IN || order == BOTGAT_ORDER_OUT, "edge_unstage: bad order %d", order);
-  if (g->n_edges == 0) return 0;
-  BG_REQUIRE(gz && grad_ee, "edge_unstage: null gz/grad_ee");
-  DeviceGuard guard(g->device);
-  cudaStream_t st = (cudaStream_t)stream;
-  k_edge_unstage<<<grid_for(g->n_edges), 256, 0, st>>>(g->n_edges, H, order == BOTGAT_ORDER_IN ? g->in_eid : g->out_eid,
-                                                       gz, grad_ee); BG_LAUNCHED(1);
-  BG_CHECK(cudaGetLastError());
-  return 0;
-}
-
-// ---------------------------------------------------------------------------
 // multi-GPU helpers: 1-D partition and halo row packing
 // ---------------------------------------------------------------------------
 namespace botgat {

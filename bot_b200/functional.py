@@ -54,9 +54,11 @@ class _Span:
 timer = None  # set to a KernelTimer to record
 
 # How per-edge operands (edge logits, keep set, dropout multiplier) reach the kernels:
-#   "direct": indexed by edge id inside the kernels' software pipeline (no extra pass; default)
-#   "staged": permuted into CSR order, head-major, by botgat_edge_stage / botgat_edge_unstage first
-edge_mode = "direct"
+#   "staged": permuted into CSR order, head-major, by botgat_edge_stage / botgat_edge_unstage first (default)
+#   "direct": indexed by edge id inside the kernels' software pipeline.  Measured 1.8x SLOWER on B200 at the
+#             proteins shape (H random 32-byte DRAM sectors per edge instead of one 4*H-byte record per edge
+#             in the staging pass); kept for graphs whose edge ids already follow the CSR order.
+edge_mode = "staged"
 
 
 def _span(name):
@@ -73,9 +75,31 @@ def _f32c(t, name):
     return t.contiguous()
 
 
+def _rows(t, name, H):
+    """(tensor, row stride) of a per-edge operand whose rows may carry padding columns beyond H."""
+    if t is None:
+        return None, 0
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise TypeError(f"{name}: expected a float32 CUDA tensor")
+    if t.dim() != 2 or t.shape[1] < H:
+        raise ValueError(f"{name}: expected (E, >= {H}), got {tuple(t.shape)}")
+    if t.stride(1) != 1 or t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    return t, t.stride(0)
+
+
+def pad_heads(H):
+    """Row width (floats) that makes one H-float record an aligned power-of-two block (<= one 32-byte sector
+    for H <= 8): random record accesses then never straddle a DRAM sector."""
+    w = 1
+    while w < H and w < 8:
+        w *= 2
+    return w if H <= 8 else (H + 3) // 4 * 4
+
+
 def edge_stage(graph: Graph, order, H, ee=None, keep=None, attn_mul=None):
     """Permute per-edge operands from edge-id order to CSR order, head-major
-    (``botgat_edge_stage``).  Returns (eb, Hb, am)."""
+    (``botgat_edge_stage``).  ``ee`` / ``attn_mul`` may be (E, >=H) with padded rows.  Returns (eb, Hb, am)."""
     E = graph.number_of_edges()
     dev = graph.device
     eb = am = None
@@ -87,9 +111,11 @@ def edge_stage(graph: Graph, order, H, ee=None, keep=None, attn_mul=None):
         am = torch.empty((H, E), dtype=torch.float32, device=dev)
     if eb is None and am is None:
         return None, 0, None
+    ee, ld_ee = _rows(ee, "ee", H)
+    attn_mul, ld_am = _rows(attn_mul, "attn_mul", H)
     with _span("edge_stage"):
-        rc = _lib.load().botgat_edge_stage(graph._ensure(), order, H, _lib.ptr(ee), _lib.ptr(keep), _lib.ptr(attn_mul),
-                                           _lib.ptr(eb), _lib.ptr(am), _stream())
+        rc = _lib.load().botgat_edge_stage(graph._ensure(), order, H, _lib.ptr(ee), ld_ee, _lib.ptr(keep),
+                                           _lib.ptr(attn_mul), ld_am, _lib.ptr(eb), _lib.ptr(am), _stream())
     _lib.check(rc, "botgat_edge_stage")
     return eb, Hb, am
 
@@ -100,7 +126,9 @@ class GATFusedFn(torch.autograd.Function):
     Arguments (tensors float32 on the graph's CUDA device):
       graph      bot_b200.Graph
       ft         (N_s,H,D)  projected source features, unscaled
-      el         (N_s,H)    er (N_d,H)|None    ee (E,H)|None (edge-id order)
+      el         (N_s,H)    er (N_d,H)|None
+      ee         (E,Hp>=H)|None, edge-id order; columns >= H are padding (Hp = 8 keeps every record inside one
+                 32-byte DRAM sector, see ``pad_heads``); the gradient comes back with the same shape
       keep       (E,) bool/uint8 | None   edge-drop keep set (edge-id order)
       attn_mul   (E,H) | None   explicit attention-dropout multiplier (edge-id order)
       src_scale  (N_s,)|None   dst_scale (N_d,)|None
@@ -121,8 +149,10 @@ class GATFusedFn(torch.autograd.Function):
             raise ValueError(f"ft has {N_s} rows, graph has {graph.number_of_src_nodes()} source nodes")
         el = _f32c(el, "el").view(N_s, H)
         er = None if er is None else _f32c(er, "er").view(N_d, H)
-        ee = None if ee is None else _f32c(ee, "ee").view(E, H)
-        attn_mul = None if attn_mul is None else _f32c(attn_mul, "attn_mul").view(E, H)
+        ee, ld_ee = _rows(ee, "ee", H)
+        attn_mul, ld_am = _rows(attn_mul, "attn_mul", H)
+        if ee is not None and ee.shape[0] != E:
+            raise ValueError("ee must have one row per edge")
         if keep is not None:
             keep = keep.to(torch.uint8).contiguous()
             if keep.numel() != E:
@@ -141,6 +171,8 @@ class GATFusedFn(torch.autograd.Function):
             a.eb, a.Hb, a.col_parts = (eb_in.data_ptr() if eb_in is not None else None), Hb, 0
             a.am = am_in.data_ptr() if am_in is not None else None
             if not staged:
+                if (ee is not None and ld_ee != H) or (attn_mul is not None and ld_am != H):
+                    raise ValueError("direct edge mode needs unpadded (E,H) edge operands")
                 a.ee = ee.data_ptr() if ee is not None else None
                 a.keep = keep.data_ptr() if keep is not None else None
                 a.attn_mul = attn_mul.data_ptr() if attn_mul is not None else None
@@ -184,7 +216,9 @@ class GATFusedFn(torch.autograd.Function):
             gz = grad_ee = None
             if need_er or need_ee:
                 gz = torch.empty((H, E), dtype=torch.float32, device=dev) if staged else None
-                grad_ee = torch.empty((E, H), dtype=torch.float32, device=dev)
+                # same row width as the ee that came in (padding columns receive zeros)
+                Hp = ee.shape[1] if (ee is not None and staged) else (pad_heads(H) if staged else H)
+                grad_ee = torch.empty((E, Hp), dtype=torch.float32, device=dev)
             a = _lib.BwdArgs()
             a.H, a.D, a.ld_ft, a.ld_out, a.ld_gft = H, D, H * D, H * D, H * D
             a.ft, a.el, a.er = ft.data_ptr(), el.data_ptr(), p(er)
@@ -196,6 +230,7 @@ class GATFusedFn(torch.autograd.Function):
             a.out, a.row_max, a.row_sum, a.gout = out.data_ptr(), row_max.data_ptr(), row_sum.data_ptr(), gout.data_ptr()
             a.drec, a.gprime, a.gz = drec.data_ptr(), p(gprime), p(gz)
             a.grad_ft, a.grad_el, a.grad_ee, a.grad_er = grad_ft.data_ptr(), grad_el.data_ptr(), p(grad_ee), p(grad_er)
+            a.ld_gee = grad_ee.stride(0) if grad_ee is not None else 0
             if timer is None:
                 _lib.check(lib.botgat_gat_backward(h, C.byref(a), _stream()), "botgat_gat_backward")
             else:
@@ -213,6 +248,8 @@ def gat_fused(graph, ft, el, er=None, ee=None, keep=None, attn_mul=None, src_sca
     H = ft.shape[1]
     el = el.reshape(-1, H)
     er = None if er is None else er.reshape(-1, H)
-    ee = None if ee is None else ee.reshape(-1, H)
-    attn_mul = None if attn_mul is None else attn_mul.reshape(-1, H)
+    if ee is not None and ee.dim() == 3:
+        ee = ee.reshape(ee.shape[0], -1)
+    if attn_mul is not None and attn_mul.dim() == 3:
+        attn_mul = attn_mul.reshape(attn_mul.shape[0], -1)
     return GATFusedFn.apply(graph, ft, el, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed)

@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .functional import gat_fused
+from .functional import gat_fused, pad_heads
 from .no_sampling import draw_attn_mul, draw_edge_keep
 
 
@@ -84,7 +84,16 @@ class GATConv(nn.Module):
             resid = self.dst_fc(feat_dst).view(-1, H, D)                      # models.py:107
             el = self.attn_src_fc(feat_src)                                   # models.py:108  (N_s,H)
             er = self.attn_dst_fc(feat_dst) if self.attn_dst_fc is not None else None   # models.py:122-124
-            ee = self.attn_edge_fc(feat_edge) if feat_edge is not None else None        # models.py:130-131 (E,H)
+            ee = None
+            if feat_edge is not None:                                         # models.py:130-131
+                # same Linear, emitted with zero-weight padding columns so that each edge's H logits form one
+                # aligned 32-byte record (functional.pad_heads): the staging passes then touch one DRAM sector
+                # per edge.  Columns >= H are ignored by the kernels and get zero gradient.
+                w = self.attn_edge_fc.weight
+                pad = pad_heads(H) - H
+                if pad > 0:
+                    w = torch.cat([w, w.new_zeros(pad, w.shape[1])], 0)
+                ee = F.linear(feat_edge, w)                                   # (E, pad_heads(H))
 
             E = graph.number_of_edges()
             keep = attn_mul = eids = None

@@ -107,20 +107,27 @@ int botgat_coo_add_self_loop(int64_t n_nodes, int64_t n_edges,
  * ---------------------------------------------------------------------- */
 enum { BOTGAT_ORDER_IN = 0, BOTGAT_ORDER_OUT = 1 };
 /*
- * eb[hb][p] = (ee ? ee[eid(p)*H + hb] : 0), or -inf when keep && !keep[eid(p)]
- * am[h][p]  = attn_mul[eid(p)*H + h]
- *   ee        (n_edges,H) float or NULL — `attn_edge_fc(feat_edge)`, proteins models.py:131
- *   keep      (n_edges) uint8 or NULL   — edge-drop keep set, models.py:529-532
- *   attn_mul  (n_edges,H) float or NULL — attention-dropout multiplier, models.py:537/544
+ * eb[hb][p] = (ee ? ee[eid(p)*ld_ee + hb] : 0), or -inf when keep && !keep[eid(p)]
+ * am[h][p]  = attn_mul[eid(p)*ld_am + h]
+ *   ee        (n_edges, ld_ee>=H) float or NULL — `attn_edge_fc(feat_edge)`, proteins models.py:131
+ *   keep      (n_edges) uint8 or NULL           — edge-drop keep set, models.py:529-532
+ *   attn_mul  (n_edges, ld_am>=H) float or NULL — attention-dropout multiplier, models.py:537/544
  *   eb        (Hb,n_edges) out, Hb = H if ee else 1; NULL iff ee==NULL && keep==NULL
  *   am        (H,n_edges) out; NULL iff attn_mul==NULL
+ * A row stride of 8 floats (32 bytes) makes every H<=8 record one aligned DRAM sector; the kernels use the
+ * widest vector access the stride and alignment allow.
  */
 int botgat_edge_stage(const botgat_graph* g, int order, int32_t H,
-                      const float* ee, const uint8_t* keep, const float* attn_mul,
+                      const float* ee, int64_t ld_ee, const uint8_t* keep,
+                      const float* attn_mul, int64_t ld_am,
                       float* eb, float* am, void* stream);
-/* grad_ee[eid(p)*H + h] = gz[h][p]  (gz head-major in the CSR order named by `order`) */
+/* grad_ee[eid(p)*ld_gee + h] = gz[h][p]  (gz head-major in the CSR order named by `order`) */
 int botgat_edge_unstage(const botgat_graph* g, int order, int32_t H, const float* gz,
-                        float* grad_ee, void* stream);
+                        float* grad_ee, int64_t ld_gee, void* stream);
+/* grad_er[v,h] = sum over the in-edges k of v of grad_ee[k*ld_gee + h]   (replaces the copy_e/sum SpMM DGL
+ * runs as the backward of u_add_v) */
+int botgat_edge_reduce_dst(const botgat_graph* g, int32_t H, const float* grad_ee, int64_t ld_gee,
+                           float* grad_er, void* stream);
 
 /* ------------------------------------------------------------------------
  * Fused forward: logits -> leaky_relu -> online edge-softmax -> attention
@@ -201,7 +208,8 @@ typedef struct {
   /* outputs */
   float* grad_ft;         /* (n_src, ld_gft) w.r.t. the unscaled ft */
   float* grad_el;         /* (n_src, H) */
-  float* grad_ee;         /* (n_edges, H) edge-id order, or NULL; required when grad_er is requested (its input) */
+  float* grad_ee;         /* (n_edges, ld_gee) edge-id order, or NULL; required when grad_er is requested (its input) */
+  int64_t ld_gee;         /* row stride of grad_ee in floats; 0 = H */
   float* grad_er;         /* (n_dst, H) or NULL */
 } botgat_bwd_args;
 int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args* a /* HOST */, void* stream);

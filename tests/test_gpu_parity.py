@@ -139,3 +139,40 @@ def test_softmax_rows_sum_to_one(cuda):
     has = (g.in_degrees() > 0).cpu()
     assert torch.allclose(out.cpu()[has], torch.ones_like(out.cpu()[has]), atol=2e-6)
     assert float(out.cpu()[~has].abs().max() if (~has).any() else 0.0) == 0.0
+
+
+def test_padded_edge_records(cuda):
+    """ee given as (E, 8) with H = 6 (32-byte records): same result, gradient padded with zeros."""
+    import bot_b200
+    from bot_b200.functional import gat_fused
+
+    c = make_case(400, 400, 30000, 6, 80, ee=True, keep_p=0.1, seed=21)
+    ref_out, ref_g = oracle_run(c)
+    g = bot_b200.Graph(c["src"].to(cuda), c["dst"].to(cuda), 400)
+    ee_pad = torch.zeros(30000, 8, device=cuda)
+    ee_pad[:, :6] = c["ee"].to(cuda)
+    ee_pad[:, 6:] = 123.0  # padding content must be ignored
+    ee_pad.requires_grad_(True)
+    ft = c["ft"].to(cuda).requires_grad_(True)
+    el = c["el"].to(cuda).requires_grad_(True)
+    er = c["er"].to(cuda).requires_grad_(True)
+    out = gat_fused(g, ft, el, er, ee_pad, c["keep"].to(cuda))
+    out.backward(c["gout"].to(cuda))
+    assert rel_err(out, ref_out) <= FWD_TOL
+    assert ee_pad.grad.shape == (30000, 8)
+    assert float(ee_pad.grad[:, 6:].abs().max()) == 0.0
+    assert rel_err(ee_pad.grad[:, :6], ref_g["ee"]) <= 1e-4
+    assert rel_err(er.grad, ref_g["er"]) <= 1e-4 and rel_err(ft.grad, ref_g["ft"]) <= 1e-4
+
+
+@pytest.mark.parametrize("mode", ["staged", "direct"])
+def test_edge_modes_agree(cuda, mode):
+    from bot_b200 import functional
+
+    c = make_case(500, 500, 20000, 4, 32, ee=True, keep_p=0.2, attn_p=0.1, seed=22)
+    old = functional.edge_mode
+    functional.edge_mode = mode
+    try:
+        check_case(c, cuda)
+    finally:
+        functional.edge_mode = old

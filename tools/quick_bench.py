@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--no-bwd", action="store_true")
     ap.add_argument("--edge-drop", type=float, default=None)
     ap.add_argument("--power-law", type=float, default=0.0)
+    ap.add_argument("--pad-ee", type=int, default=0, help="row width of ee (0 = H, unpadded)")
     args = ap.parse_args()
     N, E, H, D, has_er, has_ee, symm, edrop = SHAPES[args.shape]
     if args.edge_drop is not None:
@@ -52,7 +53,7 @@ def main():
     ft = torch.randn(N, H, D, device=dev, generator=g).requires_grad_(True)
     el = torch.randn(N, H, device=dev, generator=g).requires_grad_(True)
     er = torch.randn(N, H, device=dev, generator=g).requires_grad_(True) if has_er else None
-    ee = torch.randn(E, H, device=dev, generator=g).requires_grad_(True) if has_ee else None
+    ee = torch.randn(E, args.pad_ee or H, device=dev, generator=g).requires_grad_(True) if has_ee else None
     keep = None
     if edrop > 0:
         keep = (torch.rand(E, device=dev, generator=g) >= edrop).to(torch.uint8)
