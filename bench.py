@@ -216,7 +216,8 @@ def run_ours(args):
     ft_own = torch.randn(n_own, HEADS, HID, device=dev, generator=gen).requires_grad_(True)
     el_own = torch.randn(n_own, HEADS, device=dev, generator=gen).requires_grad_(True)
     er = torch.randn(n_dst_l, HEADS, device=dev, generator=gen).requires_grad_(True)
-    ee = torch.randn(E_local, HEADS, device=dev, generator=gen).requires_grad_(True)
+    # edge logits as the drop-in GATConv emits them: (E, pad_heads(H)) = (E, 8), one 32-byte record per edge
+    ee = torch.randn(E_local, functional.pad_heads(HEADS), device=dev, generator=gen).requires_grad_(True)
     gout = torch.randn(n_dst_l, HEADS, HID, device=dev, generator=gen)
 
     def step_resident():
