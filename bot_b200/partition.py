@@ -1,0 +1,184 @@
+"""Multi-GPU path: 1-D destination-row partition + halo exchange (one process per GPU).
+
+The reference is single-GPU (no distributed code at all), so this
+module has no reference counterpart; its contract is "partitioned result == single-GPU
+result" and the partition maps are bit-exact against ``oracle/graph_ref.py``.
+
+* Destination rows are split into P contiguous ranges balanced on EDGE count
+  (``partition_bounds``: bounds[p] = first row r with in_indptr[r] >= floor(p*E/P)).
+* Rank p owns the nodes of its range, both as destinations and as the home of their
+  source rows ``[ft | el]``.  Per layer and direction there is exactly one exchange:
+  forward  — gather the source rows the local edges reference (halo),
+  backward — the transposed collective, adding partial ``grad_ft/grad_el`` back at the owners.
+* Two exchange plans, both autograd-aware and both plain ``torch.distributed`` collectives
+  (NCCL over NVLink/NVSwitch on GPUs; gloo in the CPU tests):
+  "dense"  — ``all_gather_into_tensor`` of the whole row-sharded table (equal-sized padded
+             shards) / ``reduce_scatter_tensor`` back.  Optimal when the halo is ~everything,
+             which is the case for uniformly random edges.
+  "sparse" — ``all_to_all_single`` of only the referenced rows / the same in reverse with an
+             ``index_add_`` at the owner.  For graphs with locality.
+  The map construction is device-agnostic torch code so that it runs under gloo on CPU; the
+  per-rank compute is ``bot_b200.functional.gat_fused`` on the local block graph (CUDA only).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from .graph import Graph
+
+
+def partition_bounds(dst, n_nodes, n_parts):
+    """Edge-balanced contiguous row ranges; identical to ``oracle.graph_ref.partition_bounds``."""
+    counts = torch.bincount(dst, minlength=n_nodes)
+    indptr = torch.zeros(n_nodes + 1, dtype=torch.int64, device=dst.device)
+    indptr[1:] = torch.cumsum(counts, 0)
+    e = int(dst.numel())
+    targets = torch.tensor([(p * e) // n_parts for p in range(1, n_parts)], dtype=torch.int64, device=dst.device)
+    inner = torch.searchsorted(indptr, targets, right=False).clamp(max=n_nodes)
+    bounds = torch.cat([torch.zeros(1, dtype=torch.int64, device=dst.device), inner,
+                        torch.full((1,), n_nodes, dtype=torch.int64, device=dst.device)])
+    return torch.cummax(bounds, 0).values
+
+
+class _DenseHalo(torch.autograd.Function):
+    """all-gather of equal-sized padded shards; backward = reduce-scatter (sum)."""
+
+    @staticmethod
+    def forward(ctx, shard, group):
+        ctx.group = group
+        world = dist.get_world_size(group)
+        out = shard.new_empty((world * shard.shape[0],) + tuple(shard.shape[1:]))
+        dist.all_gather_into_tensor(out, shard.contiguous(), group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        world = dist.get_world_size(ctx.group)
+        out = grad.new_empty((grad.shape[0] // world,) + tuple(grad.shape[1:]))
+        dist.reduce_scatter_tensor(out, grad.contiguous(), op=dist.ReduceOp.SUM, group=ctx.group)
+        return out, None
+
+
+class _SparseHalo(torch.autograd.Function):
+    """all-to-all of the referenced rows; backward sends the halo gradients home and adds them."""
+
+    @staticmethod
+    def forward(ctx, own, send_idx, send_counts, recv_counts, group):
+        ctx.group, ctx.n_own = group, own.shape[0]
+        ctx.send_counts, ctx.recv_counts = send_counts, recv_counts
+        ctx.save_for_backward(send_idx)
+        send = own.index_select(0, send_idx)
+        recv = own.new_empty((sum(recv_counts),) + tuple(own.shape[1:]))
+        dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=send_counts, group=group)
+        return torch.cat([own, recv], 0)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (send_idx,) = ctx.saved_tensors
+        g_own = grad[: ctx.n_own].clone()
+        g_halo = grad[ctx.n_own:].contiguous()
+        back = grad.new_empty((sum(ctx.send_counts),) + tuple(grad.shape[1:]))
+        dist.all_to_all_single(back, g_halo, output_split_sizes=ctx.send_counts, input_split_sizes=ctx.recv_counts,
+                               group=ctx.group)
+        g_own.index_add_(0, send_idx, back)  # several peers may reference one row: index_add_ accumulates
+        return g_own, None, None, None, None
+
+
+class PartitionedGraph:
+    """This rank's share of a homogeneous graph.
+
+    ``src``/``dst`` are the FULL graph's COO (every rank passes the same tensors); afterwards
+    only the local edge set is kept.  Attributes:
+      bounds        (P+1,) row ranges        lo, hi, n_own
+      edge_gid      global edge id of every local edge (local edge order = global edge-id order)
+      local         ``bot_b200.Graph`` block: n_dst = n_own destinations; sources are numbered
+                    dense : owner*max_own + (gid - bounds[owner])     (n_src = P*max_own)
+                    sparse: [owned rows | halo rows sorted by gid]    (n_src = n_own + n_halo)
+      halo_gid      (sparse) global ids of the halo rows
+    """
+
+    def __init__(self, src, dst, n_nodes, world=None, rank=None, group=None, plan="auto", build_graph=True):
+        self.group = group
+        self.world = dist.get_world_size(group) if world is None else world
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.n_nodes = n_nodes
+        dev = src.device
+        self.bounds = partition_bounds(dst, n_nodes, self.world)
+        b = self.bounds.tolist()
+        self.lo, self.hi = b[self.rank], b[self.rank + 1]
+        self.n_own = self.hi - self.lo
+        self.max_own = max(b[i + 1] - b[i] for i in range(self.world))
+
+        mine = torch.nonzero((dst >= self.lo) & (dst < self.hi)).flatten()
+        self.edge_gid = mine
+        s, d = src.index_select(0, mine), dst.index_select(0, mine)
+        ldst = d - self.lo
+        owned = (s >= self.lo) & (s < self.hi)
+        self.halo_gid = torch.unique(s[~owned])  # sorted
+        if plan == "auto":
+            # dense when this rank references most of the table anyway (uniformly random graphs)
+            plan = "dense" if (self.halo_gid.numel() + self.n_own) * 2 >= n_nodes else "sparse"
+            if dist.is_initialized() and self.world > 1:
+                flag = torch.tensor([1 if plan == "dense" else 0], device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)  # ranks must agree
+                plan = "dense" if int(flag.item()) else "sparse"
+        self.plan = plan
+
+        if plan == "dense":
+            owner = torch.searchsorted(self.bounds, s, right=True) - 1
+            lsrc = owner * self.max_own + (s - self.bounds.index_select(0, owner))
+            n_src = self.world * self.max_own
+            self.send_idx = self.send_counts = self.recv_counts = None
+        else:
+            lsrc = torch.where(owned, s - self.lo, self.n_own + torch.searchsorted(self.halo_gid, s))
+            n_src = self.n_own + self.halo_gid.numel()
+            self._plan_sparse(dev)
+        self.lsrc, self.ldst, self.n_src_local = lsrc, ldst, n_src
+        self.local = Graph(lsrc, ldst, n_src, self.n_own, is_block=True) if build_graph else None
+
+    def _plan_sparse(self, dev):
+        """Tell every owner which of its rows this rank needs (one all-to-all of id lists at setup)."""
+        halo_owner = torch.searchsorted(self.bounds, self.halo_gid, right=True) - 1
+        self.recv_counts = torch.bincount(halo_owner, minlength=self.world).tolist()
+        if self.world == 1:
+            self.send_counts, self.send_idx = [0], torch.zeros(0, dtype=torch.int64, device=dev)
+            return
+        rc = torch.tensor(self.recv_counts, dtype=torch.int64, device=dev)
+        sc = torch.empty_like(rc)
+        dist.all_to_all_single(sc, rc, group=self.group)
+        self.send_counts = sc.tolist()
+        want = torch.empty(sum(self.send_counts), dtype=torch.int64, device=dev)
+        # halo_gid is sorted by gid, hence grouped by owner in rank order
+        dist.all_to_all_single(want, self.halo_gid.contiguous(), output_split_sizes=self.send_counts,
+                               input_split_sizes=self.recv_counts, group=self.group)
+        self.send_idx = want - self.lo
+
+    # ---- exchange ---------------------------------------------------------
+    def _pad(self, t):
+        if t.shape[0] == self.max_own:
+            return t
+        return torch.cat([t, t.new_zeros((self.max_own - t.shape[0],) + tuple(t.shape[1:]))], 0)
+
+    def halo_gather(self, *owned_tables):
+        """Local source tables (rows in ``local``'s source numbering) from row-sharded ones.
+
+        Every argument is (n_own, ...).  One collective per table (the big feature table lands
+        contiguous and aligned, ready for the gather kernels; the logit table is tiny).  Differentiable."""
+        outs = []
+        for t in owned_tables:
+            if self.world == 1:
+                outs.append(self._pad(t) if self.plan == "dense" else t)
+            elif self.plan == "dense":
+                outs.append(_DenseHalo.apply(self._pad(t), self.group))
+            else:
+                outs.append(_SparseHalo.apply(t, self.send_idx, self.send_counts, self.recv_counts, self.group))
+        return outs[0] if len(outs) == 1 else tuple(outs)
+
+    def owned_slice(self, full_table):
+        """Rows of a replicated (N, ...) table this rank owns."""
+        return full_table[self.lo:self.hi]
+
+    def local_edges(self, edge_table):
+        """Rows of a replicated (E, ...) edge table that belong to the local edges, local edge order."""
+        return edge_table.index_select(0, self.edge_gid)

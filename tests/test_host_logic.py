@@ -1,0 +1,121 @@
+"""Host-side mirror of the reference interface (CPU): constructors, parameter names/shapes/initialisation,
+#Params known-answer values, helper arithmetic."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import dgl_shim
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return {k: dgl_shim.import_reference(k) for k in ("no-sampling", "ogbn-proteins", "ogbn-products")}
+
+
+def n_params(m):
+    return sum(p.numel() for p in m.parameters() if p.requires_grad)
+
+
+def test_param_counts_known_answers():
+    from bot_b200.no_sampling import GAT
+    from bot_b200.ogbn_products import GAT as ProductsGAT
+    from bot_b200.ogbn_proteins import GAT as ProteinsGAT
+
+    # run.py:1009 (cmd :1002): arxiv GAT --use-labels, 3 layers, 3 heads, hidden 250, BN, linear
+    arxiv = GAT(128 + 40, 0, 40, 250, 3, 3, F.relu, norm="batch", dropout=0.75, input_drop=0.1, attn_drop=0.1,
+                edge_drop=0, use_symmetric_norm=True, linear=True)
+    assert n_params(arxiv) == 1441580
+    # proteins gat.py:377 / :385
+    assert n_params(ProteinsGAT(8, 8, 112, 6, 6, 80, 16, F.relu, 0.25, 0.1, 0.0, 0.1)) == 2475232
+    assert n_params(ProteinsGAT(8 + 112, 8, 112, 6, 6, 80, 16, F.relu, 0.25, 0.1, 0.0, 0.1)) == 2484192
+    # products gat.py:441
+    assert n_params(ProductsGAT(100, 0, 47, 3, 4, 120, 0, F.relu, 0.5, 0.1, 0.0, 0.1, allow_zero_in_degree=True)) == 1065127
+    # run.py:902 / :974 were logged when every layer had attn_r (today's --non-interactive-attn)
+    cora = GAT(1433, 0, 7, 8, 2, 8, F.relu, norm="none", dropout=0.6, attn_drop=0.6, edge_drop=0.5, non_interactive_attn=True)
+    assert n_params(cora) == 92373
+    reddit = GAT(602, 0, 41, 64, 3, 4, F.relu, norm="batch", non_interactive_attn=True, linear=True)
+    assert n_params(reddit) == 462459
+
+
+V1_CTORS = [dict(in_feats=10, out_feats=6, num_heads=3), dict(in_feats=10, out_feats=6, num_heads=2, linear=False,
+            non_interactive_attn=True, use_symmetric_norm=True), dict(in_feats=(10, 7), out_feats=4, num_heads=2)]
+V2_CTORS = [dict(node_feats=10, edge_feats=5, out_feats=6, n_heads=3), dict(node_feats=10, edge_feats=0, out_feats=6,
+            n_heads=2, use_attn_dst=False)]
+
+
+@pytest.mark.parametrize("ctor", V1_CTORS)
+def test_v1_state_dict_and_init_match_reference(ref, ctor):
+    from bot_b200.no_sampling import GATConv
+
+    torch.manual_seed(3)
+    theirs = ref["no-sampling"].GATConv(**ctor)
+    torch.manual_seed(3)
+    ours = GATConv(**ctor)
+    sd_t, sd_o = theirs.state_dict(), ours.state_dict()
+    assert list(sd_t) == list(sd_o)
+    for k in sd_t:
+        assert torch.equal(sd_t[k], sd_o[k]), k  # same names, shapes AND values under the same seed
+    ours.load_state_dict(sd_t, strict=True)
+
+
+@pytest.mark.parametrize("ctor", V2_CTORS)
+@pytest.mark.parametrize("which", ["ogbn-proteins", "ogbn-products"])
+def test_v2_state_dict_and_init_match_reference(ref, ctor, which):
+    from bot_b200.sampled import GATConv
+
+    torch.manual_seed(4)
+    theirs = ref[which].GATConv(**ctor)
+    torch.manual_seed(4)
+    ours = GATConv(**ctor)
+    sd_t, sd_o = theirs.state_dict(), ours.state_dict()
+    assert sorted(sd_t) == sorted(sd_o)
+    for k in sd_t:
+        assert torch.equal(sd_t[k], sd_o[k]), k
+
+
+def test_model_state_dicts_interchange(ref):
+    from bot_b200.no_sampling import GAT
+    from bot_b200.ogbn_products import GAT as ProductsGAT
+    from bot_b200.ogbn_proteins import GAT as ProteinsGAT
+
+    a = (20, 0, 5, 8, 3, 2, F.relu)
+    kw = dict(norm="batch", dropout=0.5, attn_drop=0.1, use_symmetric_norm=True, linear=True, residual=True)
+    torch.manual_seed(0)
+    t = ref["no-sampling"].GAT(*a, **kw)
+    torch.manual_seed(0)
+    o = GAT(*a, **kw)
+    assert sorted(t.state_dict()) == sorted(o.state_dict())
+    o.load_state_dict(t.state_dict(), strict=True)
+    for k, v in t.state_dict().items():
+        assert torch.equal(v, o.state_dict()[k]), k
+    pa = (8, 8, 11, 2, 3, 10, 16, F.relu, 0.25, 0.1, 0.0, 0.1)
+    ProteinsGAT(*pa).load_state_dict(ref["ogbn-proteins"].GAT(*pa).state_dict(), strict=True)
+    qa = (9, 0, 7, 2, 2, 6, 0, F.relu, 0.5, 0.1, 0.0, 0.1)
+    ProductsGAT(*qa).load_state_dict(ref["ogbn-products"].GAT(*qa).state_dict(), strict=True)
+
+
+def test_v2_residual_false_is_rejected_like_the_reference(ref):
+    from bot_b200.sampled import GATConv
+
+    with pytest.raises((TypeError, AttributeError)):
+        ref["ogbn-proteins"].GATConv(4, 0, 4, residual=False)   # nn.Parameter(int) at models.py:49
+    with pytest.raises(TypeError):
+        GATConv(4, 0, 4, residual=False)
+
+
+def test_edge_keep_follows_reference_draw():
+    from bot_b200.no_sampling import draw_edge_keep
+
+    torch.manual_seed(5)
+    perm = torch.randperm(100)
+    torch.manual_seed(5)
+    keep, eids = draw_edge_keep(100, 0.37, torch.device("cpu"))
+    bound = int(100 * 0.37)
+    assert torch.equal(eids, perm[bound:]) and int(keep.sum()) == 100 - bound
+    assert not keep[perm[:bound]].any()
+
+
+def test_pad_heads():
+    from bot_b200.functional import pad_heads
+
+    assert [pad_heads(h) for h in (1, 2, 3, 4, 5, 6, 8, 9, 12)] == [1, 2, 4, 4, 8, 8, 8, 12, 12]

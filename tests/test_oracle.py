@@ -1,0 +1,111 @@
+"""Self-validation of the oracle (CPU): it is 'parity unpinned' against real DGL (not installable offline), so it
+is pinned by the golden vectors of the reference's own modules (test_golden_cpu.py) plus the invariants here."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gat_ref, graph_ref
+from util import make_case, oracle_run
+
+
+def test_hand_computed_case():
+    """H = D = 1, two edges into node 0 with logits ln(1), ln(3) after leaky_relu -> alpha = 1/4, 3/4."""
+    src = torch.tensor([0, 1, 1])
+    dst = torch.tensor([0, 0, 1])
+    ft = torch.tensor([[[2.0]], [[10.0]]])
+    el = torch.log(torch.tensor([[1.0], [3.0]]))
+    out = gat_ref.gat_sparse(src, dst, 2, ft, el)
+    assert torch.allclose(out.flatten(), torch.tensor([0.25 * 2 + 0.75 * 10, 10.0]))
+    # negative logits go through the 0.2 slope: el = -5 -> -1
+    el2 = torch.tensor([[-5.0], [0.0]])
+    a0 = torch.exp(torch.tensor(-1.0)) / (torch.exp(torch.tensor(-1.0)) + 1.0)
+    out2 = gat_ref.gat_sparse(src, dst, 2, ft, el2)
+    assert torch.allclose(out2[0, 0, 0], a0 * 2 + (1 - a0) * 10)
+
+
+def test_rows_sum_to_one_and_zero_in_degree():
+    c = make_case(40, 40, 100, 3, 5, ee=True, seed=1)
+    c["ft"] = torch.ones_like(c["ft"])
+    out, _ = oracle_run(c, torch.float64)
+    indeg = torch.bincount(c["dst"], minlength=40)
+    assert torch.allclose(out[indeg > 0], torch.ones_like(out[indeg > 0]))
+    assert float(out[indeg == 0].abs().sum()) == 0.0
+
+
+def test_edge_permutation_invariance():
+    c = make_case(50, 50, 400, 2, 6, ee=True, seed=2)
+    out, _ = oracle_run(c, torch.float64)
+    perm = torch.randperm(400, generator=torch.Generator().manual_seed(0))
+    c2 = dict(c, src=c["src"][perm], dst=c["dst"][perm], ee=c["ee"][perm])
+    out2, _ = oracle_run(c2, torch.float64)
+    assert torch.allclose(out, out2, rtol=1e-12, atol=1e-12)
+
+
+def test_edge_drop_equals_subgraph():
+    """Softmax over the kept edges only == running on the edge-induced subgraph (DGL edge_softmax(eids=...))."""
+    c = make_case(50, 50, 400, 2, 6, ee=True, keep_p=0.3, seed=3)
+    out, _ = oracle_run(c, torch.float64)
+    k = c["keep"]
+    c2 = dict(c, src=c["src"][k], dst=c["dst"][k], ee=c["ee"][k], keep=None)
+    out2, _ = oracle_run(c2, torch.float64)
+    assert torch.allclose(out, out2, rtol=1e-12, atol=1e-12)
+
+
+def test_gradcheck_fp64():
+    c = make_case(12, 12, 40, 2, 3, ee=True, symm=True, seed=4)
+    ft, el, er, ee = (c[k].double().requires_grad_(True) for k in ("ft", "el", "er", "ee"))
+    cs, ds = c["src_scale"].double(), c["dst_scale"].double()
+
+    def f(ft, el, er, ee):
+        return gat_ref.gat_sparse(c["src"], c["dst"], 12, ft, el, er, ee, None, None, 0.2, cs, ds)
+
+    assert torch.autograd.gradcheck(f, (ft, el, er, ee), eps=1e-6, atol=1e-6)
+
+
+def test_big_form_equals_materialising_form():
+    c = make_case(80, 80, 900, 3, 8, ee=True, seed=5)
+    out, g = oracle_run(c, torch.float32)
+    bg = gat_ref.BigGraph(c["src"], c["dst"], 80, 80)
+    o2, a, z = gat_ref.gat_sparse_big_forward(bg, c["ft"], c["el"], c["er"], c["ee"])
+    gft, gel, ger, gee = gat_ref.gat_sparse_big_backward(bg, c["ft"], a, z, o2, c["gout"])
+    assert torch.allclose(out, o2, rtol=1e-5, atol=1e-6)
+    for got, want in ((gft, g["ft"]), (gel, g["el"]), (ger, g["er"]), (gee, g["ee"])):
+        assert torch.allclose(got, want, rtol=1e-4, atol=1e-5)
+
+
+def test_graph_oracle_known_answers():
+    src = np.array([2, 0, 1, 0, 2, 2])
+    dst = np.array([0, 1, 1, 2, 2, 1])
+    f = graph_ref.build_formats(src, dst, 3, 3)
+    assert f["in_indptr"].tolist() == [0, 1, 4, 6]
+    assert f["in_indices"].tolist() == [2, 0, 1, 2, 0, 2]   # sources, row by row, edge-id order inside a row
+    assert f["in_eid"].tolist() == [0, 1, 2, 5, 3, 4]
+    assert f["out_indptr"].tolist() == [0, 2, 3, 6]
+    assert f["out_indices"].tolist() == [1, 2, 1, 0, 2, 1]
+    assert f["out_eid"].tolist() == [1, 3, 2, 0, 4, 5]
+    assert f["in_deg"].tolist() == [1, 3, 2] and f["out_deg"].tolist() == [2, 1, 3]
+    s, d = graph_ref.to_bidirected(np.array([0, 0, 2]), np.array([1, 1, 2]), 3)
+    assert s.tolist() == [0, 1, 2] and d.tolist() == [1, 0, 2]          # dedup, sorted by (src,dst)
+    s, d = graph_ref.add_self_loop(*graph_ref.remove_self_loop(s, d), 3)
+    assert s.tolist() == [0, 1, 0, 1, 2] and d.tolist() == [1, 0, 0, 1, 2]  # loops appended last, i = 0..N-1
+    assert np.allclose(graph_ref.deg_scale(np.array([0, 1, 4]), -0.5), [1.0, 1.0, 0.5])
+    assert np.allclose(graph_ref.deg_scale(np.array([0, 1, 4]), 0.5), [1.0, 1.0, 2.0])
+
+
+@pytest.mark.parametrize("parts", [1, 2, 4, 7])
+def test_partition_oracle_properties(parts):
+    n, e = 200, 3000
+    src, dst = graph_ref.synthetic_coo(n, e, 6, power_law=0.7)
+    f = graph_ref.build_formats(src, dst, n, n)
+    b = graph_ref.partition_bounds(f["in_indptr"], parts)
+    assert b[0] == 0 and b[-1] == n and (np.diff(b) >= 0).all()
+    seen = np.zeros(e, dtype=int)
+    for r in range(parts):
+        loc = graph_ref.partition_local(src, dst, n, b, r)
+        seen[loc["edge_gid"]] += 1
+        gsrc = np.where(loc["lsrc"] < loc["hi"] - loc["lo"], loc["lsrc"] + loc["lo"],
+                        loc["halo_gid"][np.maximum(loc["lsrc"] - (loc["hi"] - loc["lo"]), 0)] if len(loc["halo_gid"]) else 0)
+        assert np.array_equal(gsrc, src[loc["edge_gid"]])
+        assert np.array_equal(loc["ldst"] + loc["lo"], dst[loc["edge_gid"]])
+        assert loc["recv_counts"].sum() == len(loc["halo_gid"])
+    assert (seen == 1).all()  # every edge belongs to exactly one rank
