@@ -203,10 +203,9 @@ def run_ours(args):
     else:
         from bot_b200 import partition
 
-        full = bot_b200.Graph(src, dst, n_nodes)
-        layer = partition.PartitionedGraph(full, world, rank)
+        layer = partition.PartitionedGraph(src, dst, n_nodes)
         graph = layer.local
-        del full
+        graph.create_formats_()
     del src, dst
     E_local = graph.number_of_edges()
     n_src_l, n_dst_l = graph.number_of_src_nodes(), graph.number_of_dst_nodes()
