@@ -87,20 +87,19 @@ struct SrcOps {
 #ifndef BG_MINB_BWD
 #define BG_MINB_BWD 4
 #endif
-#ifndef BG_NS_BWD
-#define BG_NS_BWD 4
+#ifdef BG_NS_BWD
+__host__ __device__ constexpr int steps_in_flight_bwd(int) { return BG_NS_BWD; }
+#else
+__host__ __device__ constexpr int steps_in_flight_bwd(int vpl) { return vpl <= 3 ? 4 : vpl <= 6 ? 2 : 1; }
 #endif
 
 template <int VW, int GSH, int VPL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB_BWD) gat_bwd_src_kernel(const BwdParams p) {
-#ifdef BG_NS_BWD
-  constexpr int NS = BG_NS_BWD;
-#else
-  constexpr int NS = steps_in_flight(VPL);
-#endif
+  constexpr int NS = steps_in_flight_bwd(VPL);
   constexpr int G = 1 << GSH;
   constexpr int EPS = 32 >> GSH;
   constexpr int GSTRIDE = G * VW;
+  constexpr bool kPacked = NS > 1 && NS <= G && (NS & (NS - 1)) == 0;  // packed dot-product reduction usable
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x / p.blocks_per_slab;
   const int row = (blockIdx.x - h * p.blocks_per_slab) * kWarpsPerBlock + warp;
@@ -216,8 +215,47 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB_BWD) gat_bwd_src_
 #pragma unroll
         for (int i = 0; i < VPL; ++i) x[s_][i].load(reinterpret_cast<const float*>(bp[i] + off));
       }
+      if constexpr (kPacked) {
+        // NS partial dots per lane -> one packed butterfly over the G lanes of the group: at every level
+        // each lane hands half of its live values to its partner (k/2 shuffles) instead of reducing every
+        // value on its own (k shuffles).  Afterwards step s's sum sits in lanes [s*G/NS, (s+1)*G/NS) of
+        // the group, and ONE indexed shuffle hands all NS*EPS dots to the lanes that own those neighbours.
+        float part[NS];
 #pragma unroll
-      for (int s_ = 0; s_ < NS; ++s_) consume(x[s_], w[s_], e + s_ * EPS, d_lane);
+        for (int s_ = 0; s_ < NS; ++s_) {
+          part[s_] = 0.f;
+#pragma unroll
+          for (int i = 0; i < VPL; ++i) {
+            acc[i].fma(w[s_], x[s_][i]);
+            part[s_] = x[s_][i].dot(fu[i], part[s_]);  // fu is 0 on slots this lane does not own
+          }
+        }
+        int k = NS;
+#pragma unroll
+        for (int o = G >> 1; o > 0; o >>= 1) {
+          if (k > 1) {
+            const bool upper = (lane & o) != 0;
+#pragma unroll
+            for (int i = 0; i < NS / 2; ++i) {
+              if (i < k / 2) {
+                const float send = upper ? part[i] : part[i + k / 2];
+                const float keep = upper ? part[i + k / 2] : part[i];
+                part[i] = keep + __shfl_xor_sync(kFull, send, o);
+              }
+            }
+            k >>= 1;
+          } else {
+            part[0] += __shfl_xor_sync(kFull, part[0], o);
+          }
+        }
+        const int t = lane - e;  // which of the NS*EPS neighbours of this iteration the lane owns
+        const int from = ((t & (EPS - 1)) << GSH) + (t / EPS) * (G / NS);
+        const float got = __shfl_sync(kFull, part[0], from & 31);
+        if (t >= 0 && t < NS * EPS) d_lane = got;
+      } else {
+#pragma unroll
+        for (int s_ = 0; s_ < NS; ++s_) consume(x[s_], w[s_], e + s_ * EPS, d_lane);
+      }
     }
     for (; e < cnt; e += EPS) {
       // a group past the end re-reads the chunk's last neighbour; its weight is 0 and its dot is not delivered
