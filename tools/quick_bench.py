@@ -38,6 +38,14 @@ def main():
     if args.edge_drop is not None:
         edrop = args.edge_drop
     dev = torch.device("cuda", 0)
+    if os.environ.get("L2_FETCH"):
+        import ctypes
+        torch.cuda.init()
+        rt = ctypes.CDLL("libcudart.so.12")
+        rc = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(int(os.environ["L2_FETCH"])))  # cudaLimitMaxL2FetchGranularity
+        v = ctypes.c_size_t()
+        rt.cudaDeviceGetLimit(ctypes.byref(v), 5)
+        print("L2 fetch granularity limit ->", rc, v.value, file=sys.stderr)
     g = torch.Generator(device=dev).manual_seed(0)
     src = torch.randint(0, N, (E,), device=dev, generator=g)
     if args.power_law > 0:
