@@ -18,31 +18,10 @@
 // E-sized is saved by the forward.  No atomics: every output element is produced
 // by exactly one warp in a fixed order, so results are run-to-run deterministic.
 #include "common.cuh"
+#include "params.cuh"
 
 namespace botgat {
 
-struct BwdParams {
-  const int32_t* indptr;
-  const int32_t* indices;
-  const int32_t* eid;
-  int n_rows;  // rows of the out-CSR (= n_src)
-  int n_dst;
-  int64_t n_edges;
-  int H, D;
-  int64_t ld_ft, ld_g, ld_gft;
-  const float *ft, *el, *eb, *am, *cs;
-  const float *ee, *amul_e;  // edge-id-ordered operands (direct mode)
-  const uint8_t* keep;
-  float* gz_e;         // (n_edges, H) edge-id order (direct mode), written by the src pass
-  const float* g;      // g' (n_dst, ld_g)
-  const float4* drec;  // (H, n_dst)
-  int Hb;
-  float slope, attn_p, inv_keep;
-  uint64_t seed;
-  float *grad_ft, *grad_el, *gz;
-  int omask;
-  int blocks_per_slab;
-};
 
 // ---------------------------------------------------------------------------
 // node phase: one warp per destination row
@@ -77,10 +56,6 @@ gat_bwd_node_kernel(int n_dst, int H, int D, int64_t ld, const float* __restrict
 // ---------------------------------------------------------------------------
 // src phase: one warp per (head, source row u) over the out-CSR
 // ---------------------------------------------------------------------------
-struct SrcOps {
-  float4 rec;  // {er[v], row_max[v], 1/row_sum[v], t[v]}
-  float eb, amul;
-};
 
 // 4 blocks x 4 warps (16 warps, <= 128 registers) per SM with 4 steps in flight: the src pass carries ft[u] and the
 // dot product besides the accumulators, and prefers registers over occupancy (profiles/r01_sweeps.md)
@@ -365,7 +340,8 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
     p.blocks_per_slab = (p.n_rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const int64_t nblocks = (int64_t)p.blocks_per_slab * a->H;
     BG_REQUIRE(nblocks < (1ll << 31), "backward: grid too large");
-    int rc = launch_src(p, t, dim3((unsigned)nblocks), st);
+    int rc = use_lowdeg_kernels(g->n_edges, g->n_src) ? launch_src_lowdeg(p, t, st)
+                                                     : launch_src(p, t, dim3((unsigned)nblocks), st);
     if (rc) return rc;
     BG_CHECK(cudaGetLastError());
   }

@@ -20,27 +20,10 @@
 //     chunk c+2, logit operands of chunk c+1 and the row gathers of chunk c are in
 //     flight together, so no load waits on a load issued in the same iteration.
 #include "common.cuh"
+#include "params.cuh"
 
 namespace botgat {
 
-struct FwdParams {
-  const int32_t* indptr;
-  const int32_t* indices;
-  const int32_t* eid;
-  int n_rows;
-  int64_t n_edges;
-  int H, D;
-  int64_t ld_ft, ld_out;
-  const float *ft, *el, *er, *eb, *am, *cs, *ds;
-  const float *ee, *amul_e;  // edge-id-ordered operands (direct mode)
-  const uint8_t* keep;
-  int Hb;
-  float slope, attn_p, inv_keep;
-  uint64_t seed;
-  float *out, *row_max, *row_sum;
-  int col_parts, part_cols, omask;
-  int blocks_per_slab;
-};
 
 // 6 blocks x 4 warps (24 warps, <= 80 registers) per SM with 2 steps in flight: the best of the occupancy /
 // loads-in-flight sweep on B200 (profiles/r01_sweeps.md)
@@ -109,35 +92,38 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB) gat_fwd_kernel(c
       if (need_eid) k = __ldg(p.eid + pos);
     }
   };
-  auto load_operands = [&](int base, int u, int k, float& z, float& mul) {
+  // raw loaded values only: any arithmetic on them here would stall on the load just issued and undo the pipeline
+  struct Ops { float el, eb, cs, am; unsigned keep; };
+  auto load_operands = [&](int base, int u, int k, Ops& o) {
     const int pos = base + lane;
-    z = -INFINITY;
-    mul = 1.f;
+    o.el = -INFINITY;  // lane past the row end: logit -inf, weight 0
+    o.eb = 0.f; o.cs = 1.f; o.am = 1.f; o.keep = 1u;
     if (pos < end) {
-      z = __ldg(el_h + (int64_t)u * H) + er_v;
-      if (eb_h) z += __ldg(eb_h + pos);
-      if (ee_h) z += __ldg(ee_h + (int64_t)k * H);
-      if (keep && !__ldg(keep + k)) z = -INFINITY;
-      if (cs) mul = __ldg(cs + u);
-      if (am_h) mul *= __ldg(am_h + pos);
-      else if (amul_h) mul *= __ldg(amul_h + (int64_t)k * H);
-      else if (philox) mul *= philox_dropout_mul(p.seed, (uint32_t)k, (uint32_t)h, p.attn_p, p.inv_keep);
+      o.el = __ldg(el_h + (int64_t)u * H);
+      if (eb_h) o.eb = __ldg(eb_h + pos);
+      else if (ee_h) o.eb = __ldg(ee_h + (int64_t)k * H);
+      if (keep) o.keep = __ldg(keep + k);
+      if (cs) o.cs = __ldg(cs + u);
+      if (am_h) o.am = __ldg(am_h + pos);
+      else if (amul_h) o.am = __ldg(amul_h + (int64_t)k * H);
+      else if (philox) o.am = philox_dropout_mul(p.seed, (uint32_t)k, (uint32_t)h, p.attn_p, p.inv_keep);
     }
   };
   int u0, u1, u2 = 0, k0, k1, k2 = 0;
   load_index(beg, u0, k0);
   load_index(beg + 32, u1, k1);
-  float z0, mul0;
-  load_operands(beg, u0, k0, z0, mul0);
+  Ops o0, o1;
+  load_operands(beg, u0, k0, o0);
 
   for (int base = beg; base < end; base += 32) {
     const int cnt = min(32, end - base);
     // issue the next stages' loads first; they are consumed one iteration later
     load_index(base + 64, u2, k2);
-    float z1, mul1;
-    load_operands(base + 32, u1, k1, z1, mul1);
+    load_operands(base + 32, u1, k1, o1);
 
     // ---- online softmax on chunk c ----
+    const float z0 = o0.keep ? o0.el + er_v + o0.eb : -INFINITY;
+    const float mul0 = o0.cs * o0.am;
     const float s = leaky_relu(z0, slope);  // -inf stays -inf (dropped edge / lane past the row end)
     const float m_new = fmaxf(m, warp_max(s));
     if (m_new > m) {
@@ -184,7 +170,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB) gat_fwd_kernel(c
 #pragma unroll
       for (int i = 0; i < VPL; ++i) acc[i].fma(wt, x[i]);
     }
-    u0 = u1; u1 = u2; k1 = k2; z0 = z1; mul0 = mul1;
+    u0 = u1; u1 = u2; k1 = k2; o0 = o1;
   }
 
   // ---- epilogue: combine the groups, normalise, degree-scale, store ----
@@ -258,7 +244,11 @@ extern "C" int botgat_gat_forward(const botgat_graph* g, const botgat_fwd_args* 
   p.blocks_per_slab = (p.n_rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int64_t nblocks = (int64_t)p.blocks_per_slab * a->H * t.col_parts;
   BG_REQUIRE(nblocks < (1ll << 31), "forward: grid too large");
-  int rc = launch_fwd(p, t, dim3((unsigned)nblocks), st);
+  int rc;
+  if (use_lowdeg_kernels(g->n_edges, g->n_dst))
+    rc = launch_fwd_lowdeg(p, t, st);
+  else
+    rc = launch_fwd(p, t, dim3((unsigned)nblocks), st);
   if (rc) return rc;
   BG_CHECK(cudaGetLastError());
   return 0;

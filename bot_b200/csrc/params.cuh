@@ -1,0 +1,61 @@
+// Kernel parameter blocks shared by the warp-per-row and the group-per-row gather kernels.
+#pragma once
+#include "common.cuh"
+
+namespace botgat {
+
+struct FwdParams {
+  const int32_t* indptr;
+  const int32_t* indices;
+  const int32_t* eid;
+  int n_rows;
+  int64_t n_edges;
+  int H, D;
+  int64_t ld_ft, ld_out;
+  const float *ft, *el, *er, *eb, *am, *cs, *ds;
+  const float *ee, *amul_e;  // edge-id-ordered operands (direct mode)
+  const uint8_t* keep;
+  int Hb;
+  float slope, attn_p, inv_keep;
+  uint64_t seed;
+  float *out, *row_max, *row_sum;
+  int col_parts, part_cols, omask;
+  int blocks_per_slab;
+};
+
+struct BwdParams {
+  const int32_t* indptr;
+  const int32_t* indices;
+  const int32_t* eid;
+  int n_rows;  // rows of the out-CSR (= n_src)
+  int n_dst;
+  int64_t n_edges;
+  int H, D;
+  int64_t ld_ft, ld_g, ld_gft;
+  const float *ft, *el, *eb, *am, *cs;
+  const float *ee, *amul_e;  // edge-id-ordered operands (direct mode)
+  const uint8_t* keep;
+  float* gz_e;         // (n_edges, H) edge-id order (direct mode), written by the src pass
+  const float* g;      // g' (n_dst, ld_g)
+  const float4* drec;  // (H, n_dst)
+  int Hb;
+  float slope, attn_p, inv_keep;
+  uint64_t seed;
+  float *grad_ft, *grad_el, *gz;
+  int omask;
+  int blocks_per_slab;
+};
+
+struct SrcOps {
+  float4 rec;  // {er[v], row_max[v], 1/row_sum[v], t[v]}
+  float eb, amul;
+};
+
+// Low-degree graphs (average row shorter than one 32-neighbour chunk and a half) use the group-per-row kernels
+// (gat_lowdeg.cu): a G-lane group owns a row, so a warp works on 32/G rows at once and the per-row latency
+// chain (index -> logit operands -> row gathers) and epilogue are shared.  BOTGAT_LOWDEG overrides the threshold.
+bool use_lowdeg_kernels(int64_t n_edges, int64_t n_rows);
+int launch_fwd_lowdeg(const FwdParams& p, const Tiling& t, cudaStream_t st);
+int launch_src_lowdeg(const BwdParams& p, const Tiling& t, cudaStream_t st);
+
+}  // namespace botgat

@@ -176,3 +176,14 @@ def test_edge_modes_agree(cuda, mode):
         check_case(c, cuda)
     finally:
         functional.edge_mode = old
+
+
+@pytest.mark.parametrize("lowdeg", ["0", "1000000"])
+@pytest.mark.parametrize("name", ["proteins_like_edge_drop", "arxiv_like_H3_D250_symm", "cora_like_H8_D8", "last_layer_H1_D41_scalar",
+                                  "block_Nd_lt_Ns", "power_law_skew", "zero_in_degree_rows", "products_like_H4_D120"])
+def test_both_kernel_families(cuda, monkeypatch, name, lowdeg):
+    """Warp-per-row (BOTGAT_LOWDEG=0) and group-per-row (forced) kernels on the same cases."""
+    monkeypatch.setenv("BOTGAT_LOWDEG", lowdeg)
+    n_src, n_dst, e, H, D, kw = CASES[name]
+    c = make_case(n_src, n_dst, e, H, D, seed=hash(name) % 1000 + 1, **kw)
+    check_case(c, cuda)
