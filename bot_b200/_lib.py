@@ -25,6 +25,7 @@ class GraphInfo(C.Structure):
         ("n_src", C.c_int64), ("n_dst", C.c_int64), ("n_edges", C.c_int64),
         ("max_in_deg", C.c_int64), ("max_out_deg", C.c_int64),
         ("has_zero_in_degree", C.c_int32), ("device", C.c_int32),
+        ("n_slots_in", C.c_int64), ("n_slots_out", C.c_int64),
     ]
 
 
@@ -36,7 +37,7 @@ class FwdArgs(C.Structure):
         ("Hb", C.c_int32), ("col_parts", C.c_int32),
         ("am", c_vp), ("ee", c_vp), ("keep", c_vp), ("attn_mul", c_vp), ("src_scale", c_vp), ("dst_scale", c_vp),
         ("slope", C.c_float), ("attn_p", C.c_float), ("seed", C.c_uint64),
-        ("out", c_vp), ("row_max", c_vp), ("row_sum", c_vp),
+        ("out", c_vp), ("row_max", c_vp), ("row_sum", c_vp), ("scratch", c_vp),
     ]
 
 
@@ -49,7 +50,7 @@ class BwdArgs(C.Structure):
         ("am_out", c_vp), ("ee", c_vp), ("keep", c_vp), ("attn_mul", c_vp), ("src_scale", c_vp), ("dst_scale", c_vp),
         ("slope", C.c_float), ("attn_p", C.c_float), ("seed", C.c_uint64),
         ("out", c_vp), ("row_max", c_vp), ("row_sum", c_vp), ("gout", c_vp),
-        ("drec", c_vp), ("gprime", c_vp), ("gz", c_vp),
+        ("drec", c_vp), ("gprime", c_vp), ("scratch", c_vp), ("gz", c_vp),
         ("grad_ft", c_vp), ("grad_el", c_vp), ("grad_ee", c_vp), ("ld_gee", C.c_int64), ("grad_er", c_vp),
     ]
 

@@ -56,6 +56,16 @@ struct botgat_graph {
   int32_t *in_indptr = nullptr, *in_indices = nullptr, *in_eid = nullptr;
   int32_t *out_indptr = nullptr, *out_indices = nullptr, *out_eid = nullptr;
   int32_t *in_deg = nullptr, *out_deg = nullptr;
+  // Row splitting for heavy-tailed degree distributions.  When a CSR has a row longer than the segment length,
+  // its work items are SEGMENTS (at most seg_len neighbours of one row) instead of rows: a heavy row is spread over
+  // several warps whose partial results go to scratch slots and are merged by a combine kernel.  Empty = no split.
+  struct SegTable {
+    int n_items = 0;   // segments (>= rows)
+    int n_slots = 0;   // segments that are only part of a row (each owns one scratch slot)
+    int n_split = 0;   // rows that are split
+    int32_t *row = nullptr, *beg = nullptr, *end = nullptr, *slot = nullptr;  // per item
+    int32_t *split_rows = nullptr, *split_first = nullptr;                    // per split row (+1 sentinel)
+  } seg_in, seg_out;
 };
 
 namespace botgat {
@@ -194,6 +204,11 @@ struct Tiling {
 // `ld_o`/`po` the row-local one (only constrains the vector width).
 Tiling choose_tiling(int H, int D, int64_t ld_g, const void* pg, int64_t ld_o, const void* po, int col_parts_req,
                      int64_t n_rows_table);
+
+// host (segments.cu): build / free the segment table of one CSR; a no-op when no row exceeds the segment length
+int build_segments(int n_rows, const int32_t* indptr, const int32_t* deg, int64_t max_deg, botgat_graph::SegTable* t,
+                   cudaStream_t st);
+void free_segments(botgat_graph::SegTable* t);
 
 // steps (of 32/G neighbours each) whose row loads a lane keeps in flight together.
 // Measured on B200 (profiles/r01_*): at D=80 (3 slots) two steps at 3 blocks/SM beat four steps at 2 blocks/SM.

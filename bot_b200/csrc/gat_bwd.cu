@@ -77,8 +77,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB_BWD) gat_bwd_src_
   constexpr bool kPacked = NS > 1 && NS <= G && (NS & (NS - 1)) == 0;  // packed dot-product reduction usable
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x / p.blocks_per_slab;
-  const int row = (blockIdx.x - h * p.blocks_per_slab) * kWarpsPerBlock + warp;
-  if (row >= p.n_rows) return;
+  const int item = (blockIdx.x - h * p.blocks_per_slab) * kWarpsPerBlock + warp;
+  if (item >= p.n_items) return;
+  const int row = p.seg_row ? p.seg_row[item] : item;
+  const int slot = p.seg_row ? p.seg_slot[item] : -1;
   const int grp = lane >> GSH;
   const int v0 = (lane & (G - 1)) - (((h * p.D) / VW) & p.omask);
 
@@ -95,7 +97,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB_BWD) gat_bwd_src_
   }
   const unsigned ldb = (unsigned)(p.ld_g * 4);
 
-  const int beg = p.indptr[row], end = p.indptr[row + 1];
+  const int beg = p.seg_row ? p.seg_beg[item] : p.indptr[row];
+  const int end = p.seg_row ? p.seg_end[item] : p.indptr[row + 1];
   const float slope = p.slope;
   const float csu = p.cs ? p.cs[row] : 1.f;
   const float el_u = p.el[(int64_t)row * p.H + h];
@@ -256,6 +259,19 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB_BWD) gat_bwd_src_
 #pragma unroll
     for (int i = 0; i < VPL; ++i) acc[i].add_shfl_xor(o);
   }
+  const float gel = warp_sum(gel_lane);
+  if (slot >= 0) {
+    // segment of a split row: partial grad_el and (unscaled) partial grad_ft go to this segment's scratch slot
+    float* sl = p.scratch + (int64_t)slot * H * (p.D + 1);
+    if (grp == 0) {
+      float* o = sl + H + (int64_t)h * p.D + v0 * VW;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+        if (act[i]) acc[i].store(o + i * GSTRIDE);
+    }
+    if (lane == 0) sl[h] = gel;
+    return;
+  }
   if (grp == 0) {
     float* o = p.grad_ft + (int64_t)row * p.ld_gft + h * p.D + v0 * VW;
 #pragma unroll
@@ -266,7 +282,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB_BWD) gat_bwd_src_
       }
     }
   }
-  const float gel = warp_sum(gel_lane);
   if (lane == 0) p.grad_el[(int64_t)row * p.H + h] = gel;
 }
 
@@ -337,12 +352,21 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
     BG_REQUIRE(t.col_parts == 1, "backward: D=%d too wide for one pass (max %d)", a->D, 32 * 8 * t.vw);
     p.indptr = g->out_indptr; p.indices = g->out_indices; p.eid = g->out_eid;
     p.n_rows = (int)g->n_src; p.eb = a->eb_out; p.am = a->am_out; p.omask = t.omask;
-    p.blocks_per_slab = (p.n_rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const botgat_graph::SegTable& seg = g->seg_out;
+    const bool lowdeg = use_lowdeg_kernels(g->n_edges, g->n_src);
+    const bool split = seg.n_items > 0 && !lowdeg;
+    BG_REQUIRE(!split || seg.n_slots == 0 || a->scratch, "backward: this graph has split rows; scratch is required");
+    p.seg_row = split ? seg.row : nullptr; p.seg_beg = seg.beg; p.seg_end = seg.end; p.seg_slot = seg.slot;
+    p.n_items = split ? seg.n_items : p.n_rows; p.scratch = a->scratch;
+    p.blocks_per_slab = (p.n_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const int64_t nblocks = (int64_t)p.blocks_per_slab * a->H;
     BG_REQUIRE(nblocks < (1ll << 31), "backward: grid too large");
-    int rc = use_lowdeg_kernels(g->n_edges, g->n_src) ? launch_src_lowdeg(p, t, st)
-                                                     : launch_src(p, t, dim3((unsigned)nblocks), st);
+    int rc = lowdeg ? launch_src_lowdeg(p, t, st) : launch_src(p, t, dim3((unsigned)nblocks), st);
     if (rc) return rc;
+    if (split) {
+      rc = launch_bwd_combine(seg, a->H, a->D, a->ld_gft, a->scratch, a->src_scale, a->grad_ft, a->grad_el, st);
+      if (rc) return rc;
+    }
     BG_CHECK(cudaGetLastError());
   }
 

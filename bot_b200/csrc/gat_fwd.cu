@@ -38,8 +38,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB) gat_fwd_kernel(c
   constexpr int EPS = 32 >> GSH;  // neighbours per warp step
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slab = blockIdx.x / p.blocks_per_slab;
-  const int row = (blockIdx.x - slab * p.blocks_per_slab) * kWarpsPerBlock + warp;
-  if (row >= p.n_rows) return;
+  const int item = (blockIdx.x - slab * p.blocks_per_slab) * kWarpsPerBlock + warp;
+  if (item >= p.n_items) return;
+  // work item = a whole row, or one segment of a heavy row (segments.cu)
+  const int row = p.seg_row ? p.seg_row[item] : item;
+  const int slot = p.seg_row ? p.seg_slot[item] : -1;
   const int h = slab / p.col_parts;
   const int cp = slab - h * p.col_parts;
   const int c0 = cp * p.part_cols;
@@ -60,7 +63,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB) gat_fwd_kernel(c
   }
   const unsigned ldb = (unsigned)(p.ld_ft * 4);
 
-  const int beg = p.indptr[row], end = p.indptr[row + 1];
+  const int beg = p.seg_row ? p.seg_beg[item] : p.indptr[row];
+  const int end = p.seg_row ? p.seg_end[item] : p.indptr[row + 1];
   const float slope = p.slope;
   const int H = p.H;
   const float er_v = p.er ? p.er[(int64_t)row * H + h] : 0.f;
@@ -180,6 +184,18 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB) gat_fwd_kernel(c
 #pragma unroll
     for (int i = 0; i < VPL; ++i) acc[i].add_shfl_xor(o);
   }
+  if (slot >= 0) {
+    // segment of a split row: park (max, sum, unnormalised accumulator) in this segment's scratch slot
+    float* sl = p.scratch + (int64_t)slot * H * (p.D + 2);
+    if (grp == 0) {
+      float* o = sl + 2 * H + (int64_t)h * p.D + c0 + v0 * VW;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+        if (act[i]) acc[i].store(o + i * G * VW);
+    }
+    if (cp == 0 && lane == 0) { sl[h * 2] = m; sl[h * 2 + 1] = l; }
+    return;
+  }
   float scale = l > 0.f ? 1.f / l : 0.f;
   if (p.ds) scale *= p.ds[row];
   if (grp == 0) {
@@ -241,15 +257,25 @@ extern "C" int botgat_gat_forward(const botgat_graph* g, const botgat_fwd_args* 
   p.slope = a->slope; p.attn_p = a->attn_p; p.inv_keep = 1.f / (1.f - a->attn_p); p.seed = a->seed;
   p.out = a->out; p.row_max = a->row_max; p.row_sum = a->row_sum;
   p.col_parts = t.col_parts; p.part_cols = t.part_cols; p.omask = t.omask;
-  p.blocks_per_slab = (p.n_rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const botgat_graph::SegTable& seg = g->seg_in;
+  const bool lowdeg = use_lowdeg_kernels(g->n_edges, g->n_dst);
+  const bool split = seg.n_items > 0 && !lowdeg;
+  BG_REQUIRE(!split || seg.n_slots == 0 || a->scratch, "forward: this graph has split rows; scratch is required");
+  p.seg_row = split ? seg.row : nullptr; p.seg_beg = seg.beg; p.seg_end = seg.end; p.seg_slot = seg.slot;
+  p.n_items = split ? seg.n_items : p.n_rows; p.scratch = a->scratch;
+  p.blocks_per_slab = (p.n_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int64_t nblocks = (int64_t)p.blocks_per_slab * a->H * t.col_parts;
   BG_REQUIRE(nblocks < (1ll << 31), "forward: grid too large");
   int rc;
-  if (use_lowdeg_kernels(g->n_edges, g->n_dst))
+  if (lowdeg)
     rc = launch_fwd_lowdeg(p, t, st);
   else
     rc = launch_fwd(p, t, dim3((unsigned)nblocks), st);
   if (rc) return rc;
+  if (split) {
+    rc = launch_fwd_combine(seg, a->H, a->D, a->ld_out, a->scratch, a->dst_scale, a->out, a->row_max, a->row_sum, st);
+    if (rc) return rc;
+  }
   BG_CHECK(cudaGetLastError());
   return 0;
 }

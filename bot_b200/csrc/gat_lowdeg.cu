@@ -25,7 +25,7 @@ namespace botgat {
 
 bool use_lowdeg_kernels(int64_t n_edges, int64_t n_rows) {
   const char* s = getenv("BOTGAT_LOWDEG");
-  const int64_t thr = (s && *s) ? atoll(s) : 48;  // average neighbours per row below which a group owns a row
+  const int64_t thr = (s && *s) ? atoll(s) : 20;  // average neighbours per row below which a group owns a row (swept: profiles/r01_sweeps.md)
   return n_rows > 0 && n_edges < thr * n_rows;
 }
 

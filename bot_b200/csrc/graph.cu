@@ -192,6 +192,7 @@ extern "C" void botgat_graph_destroy(botgat_graph* g) {
   cudaFree(g->in_indptr); cudaFree(g->in_indices); cudaFree(g->in_eid);
   cudaFree(g->out_indptr); cudaFree(g->out_indices); cudaFree(g->out_eid);
   cudaFree(g->in_deg); cudaFree(g->out_deg);
+  free_segments(&g->seg_in); free_segments(&g->seg_out);
   delete g;
 }
 
@@ -249,6 +250,11 @@ extern "C" int botgat_graph_create(int64_t n_src, int64_t n_dst, int64_t n_edges
   BG_CHECK(cudaStreamSynchronize(st));
   BG_REQUIRE(h[0] == 0, "graph_create: node id out of range [0,n_src) / [0,n_dst)");
   g->max_in_deg = h[1]; g->has_zero_in_degree = h[2] > 0; g->max_out_deg = h[3];
+  // heavy rows: split into segments (no-op for graphs whose longest row fits one segment)
+  rc = build_segments((int)n_dst, g->in_indptr, g->in_deg, g->max_in_deg, &g->seg_in, st);
+  if (rc) return rc;
+  rc = build_segments((int)n_src, g->out_indptr, g->out_deg, g->max_out_deg, &g->seg_out, st);
+  if (rc) return rc;
   cleanup.armed = false;
   *out = g;
   return 0;
@@ -275,6 +281,7 @@ extern "C" int botgat_graph_get_info(const botgat_graph* g, botgat_graph_info* i
   info->n_src = g->n_src; info->n_dst = g->n_dst; info->n_edges = g->n_edges;
   info->max_in_deg = g->max_in_deg; info->max_out_deg = g->max_out_deg;
   info->has_zero_in_degree = g->has_zero_in_degree; info->device = g->device;
+  info->n_slots_in = g->seg_in.n_slots; info->n_slots_out = g->seg_out.n_slots;
   return 0;
 }
 

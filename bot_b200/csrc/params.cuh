@@ -21,6 +21,10 @@ struct FwdParams {
   float *out, *row_max, *row_sum;
   int col_parts, part_cols, omask;
   int blocks_per_slab;
+  // row splitting (segments.cu): work items are segments when seg_row != nullptr
+  const int32_t *seg_row, *seg_beg, *seg_end, *seg_slot;
+  int n_items;
+  float* scratch;
 };
 
 struct BwdParams {
@@ -44,6 +48,9 @@ struct BwdParams {
   float *grad_ft, *grad_el, *gz;
   int omask;
   int blocks_per_slab;
+  const int32_t *seg_row, *seg_beg, *seg_end, *seg_slot;
+  int n_items;
+  float* scratch;
 };
 
 struct SrcOps {
@@ -57,5 +64,10 @@ struct SrcOps {
 bool use_lowdeg_kernels(int64_t n_edges, int64_t n_rows);
 int launch_fwd_lowdeg(const FwdParams& p, const Tiling& t, cudaStream_t st);
 int launch_src_lowdeg(const BwdParams& p, const Tiling& t, cudaStream_t st);
+int segment_length();
+int launch_fwd_combine(const botgat_graph::SegTable& t, int H, int D, int64_t ld_out, const float* scratch,
+                       const float* ds, float* out, float* row_max, float* row_sum, cudaStream_t st);
+int launch_bwd_combine(const botgat_graph::SegTable& t, int H, int D, int64_t ld_gft, const float* scratch,
+                       const float* cs, float* grad_ft, float* grad_el, cudaStream_t st);
 
 }  // namespace botgat

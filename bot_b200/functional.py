@@ -180,6 +180,10 @@ class GATFusedFn(torch.autograd.Function):
             a.dst_scale = dst_scale.data_ptr() if dst_scale is not None else None
             a.slope, a.attn_p, a.seed = float(slope), float(attn_p if attn_mul is None else 0.0), int(seed)
             a.out, a.row_max, a.row_sum = out.data_ptr(), row_max.data_ptr(), row_sum.data_ptr()
+            scratch = None
+            if graph._info.n_slots_in:  # heavy rows are split over several warps (segments.cu)
+                scratch = torch.empty(graph._info.n_slots_in * H * (D + 2), dtype=torch.float32, device=ft.device)
+                a.scratch = scratch.data_ptr()
             with _span("gat_fwd"):
                 rc = lib.botgat_gat_forward(h, C.byref(a), _stream())
             _lib.check(rc, "botgat_gat_forward")
@@ -229,6 +233,10 @@ class GATFusedFn(torch.autograd.Function):
             a.slope, a.attn_p, a.seed = slope, attn_p, seed
             a.out, a.row_max, a.row_sum, a.gout = out.data_ptr(), row_max.data_ptr(), row_sum.data_ptr(), gout.data_ptr()
             a.drec, a.gprime, a.gz = drec.data_ptr(), p(gprime), p(gz)
+            scratch = None
+            if graph._info.n_slots_out:
+                scratch = torch.empty(graph._info.n_slots_out * H * (D + 1), dtype=torch.float32, device=dev)
+                a.scratch = scratch.data_ptr()
             a.grad_ft, a.grad_el, a.grad_ee, a.grad_er = grad_ft.data_ptr(), grad_el.data_ptr(), p(grad_ee), p(grad_er)
             a.ld_gee = grad_ee.stride(0) if grad_ee is not None else 0
             if timer is None:

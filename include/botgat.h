@@ -76,6 +76,10 @@ typedef struct {
   int64_t max_in_deg, max_out_deg;
   int32_t has_zero_in_degree; /* replaces `(graph.in_degrees()==0).any()`, models.py:478 */
   int32_t device;
+  /* Heavy rows (longer than the segment length, 2048 neighbours) are split over several warps; each partial
+   * segment needs one scratch slot.  Forward scratch: n_slots_in * H * (D + 2) floats; backward scratch:
+   * n_slots_out * H * (D + 1) floats.  Both are 0 for graphs without heavy rows. */
+  int64_t n_slots_in, n_slots_out;
 } botgat_graph_info;
 int botgat_graph_get_info(const botgat_graph* g, botgat_graph_info* info /* HOST */);
 
@@ -163,6 +167,7 @@ typedef struct {
   float* out;             /* (n_dst, ld_out) */
   float* row_max;         /* (n_dst, H)  saved for backward */
   float* row_sum;         /* (n_dst, H)  saved for backward */
+  float* scratch;         /* n_slots_in * H * (D + 2) floats, or NULL when n_slots_in == 0 */
 } botgat_fwd_args;
 int botgat_gat_forward(const botgat_graph* g, const botgat_fwd_args* a /* HOST */, void* stream);
 
@@ -203,6 +208,7 @@ typedef struct {
   /* workspaces */
   float* drec;            /* (H, n_dst, 4) */
   float* gprime;          /* (n_dst, ld_out); required iff dst_scale != NULL */
+  float* scratch;         /* n_slots_out * H * (D + 1) floats, or NULL when n_slots_out == 0 */
   float* gz;              /* (H, n_edges) or NULL.  NULL: the src pass writes grad_ee directly in edge-id order;
                              given: it writes gz in out-CSR order and phase 4 un-stages it into grad_ee */
   /* outputs */

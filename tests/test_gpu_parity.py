@@ -187,3 +187,29 @@ def test_both_kernel_families(cuda, monkeypatch, name, lowdeg):
     n_src, n_dst, e, H, D, kw = CASES[name]
     c = make_case(n_src, n_dst, e, H, D, seed=hash(name) % 1000 + 1, **kw)
     check_case(c, cuda)
+
+
+@pytest.mark.parametrize("seg", ["32", "64", "100"])
+def test_row_splitting(cuda, monkeypatch, seg):
+    """Heavy rows split into segments (segment length forced small): same results, still deterministic."""
+    monkeypatch.setenv("BOTGAT_SEG", seg)
+    monkeypatch.setenv("BOTGAT_LOWDEG", "0")
+    c = make_case(600, 600, 60000, 3, 40, ee=True, keep_p=0.1, power_law=1.2, symm=True, seed=31)
+    errs = check_case(c, cuda)
+    o1, g1, g = engine_run(c, cuda)
+    o2, g2, _ = engine_run(c, cuda)
+    assert g._info.n_slots_in > 0 and g._info.n_slots_out >= 0
+    assert torch.equal(o1, o2) and all(torch.equal(g1[k], g2[k]) for k in g1)
+
+
+def test_row_splitting_all_dropped_segment(cuda, monkeypatch):
+    """A whole segment of a split row dropped by edge-drop (max = -inf in that slot)."""
+    monkeypatch.setenv("BOTGAT_SEG", "32")
+    monkeypatch.setenv("BOTGAT_LOWDEG", "0")
+    c = make_case(100, 100, 3000, 2, 16, ee=True, power_law=1.5, seed=32)
+    # drop the first 40 in-edges (edge-id order = CSR order inside a row) of the heaviest row
+    keep = torch.ones(3000, dtype=torch.bool)
+    idx = torch.nonzero(c["dst"] == 0).flatten()
+    keep[idx[:40]] = False
+    c["keep"] = keep
+    check_case(c, cuda)
