@@ -128,18 +128,24 @@ __global__ void k_edge_unstage(int64_t n_edges, int h0, int Hn, int Hw, const in
   }
 }
 
-// grad_er[v,h] = sum over in-edges k of grad_ee[k,h]: one warp per destination row, lanes stride its edges
+// grad_er[v,h] = sum over in-edges k of grad_ee[k,h]: one warp per work item (a destination row, or one segment
+// of a heavy row whose partial sums go to a scratch slot), lanes stride its edges
 template <int VEC, int PF>
 __global__ void __launch_bounds__(256)
-k_edge_reduce_dst(int n_dst, int H, int h0, int Hn, const int32_t* __restrict__ indptr, const int32_t* __restrict__ eid,
-                  const float* __restrict__ grad_ee, int64_t ld, float* __restrict__ grad_er) {
+k_edge_reduce_dst(int n_items, int H, int h0, int Hn, const int32_t* __restrict__ indptr, const int32_t* __restrict__ eid,
+                  const int32_t* __restrict__ seg_row, const int32_t* __restrict__ seg_beg,
+                  const int32_t* __restrict__ seg_end, const int32_t* __restrict__ seg_slot,
+                  const float* __restrict__ grad_ee, int64_t ld, float* __restrict__ grad_er, float* __restrict__ scratch) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int v = blockIdx.x * 8 + warp;
-  if (v >= n_dst) return;
+  const int item = blockIdx.x * 8 + warp;
+  if (item >= n_items) return;
+  const int v = seg_row ? seg_row[item] : item;
+  const int beg = seg_row ? seg_beg[item] : indptr[v], end = seg_row ? seg_end[item] : indptr[v + 1];
+  const int slot = seg_row ? seg_slot[item] : -1;
   float s[kHMax];
 #pragma unroll
   for (int q = 0; q < kHMax; ++q) s[q] = 0.f;
-  for (int pos = indptr[v] + lane; pos < indptr[v + 1]; pos += 32) {
+  for (int pos = beg + lane; pos < end; pos += 32) {
     float r[kHMax];
 #pragma unroll
     for (int q = 0; q < kHMax; ++q) r[q] = 0.f;
@@ -151,9 +157,23 @@ k_edge_reduce_dst(int n_dst, int H, int h0, int Hn, const int32_t* __restrict__ 
   for (int q = 0; q < kHMax; ++q) {
     if (q < Hn) {
       const float t = warp_sum(s[q]);
-      if (lane == 0) grad_er[(int64_t)v * H + h0 + q] = t;
+      if (lane == 0) {
+        if (slot >= 0) scratch[(int64_t)slot * H + h0 + q] = t;
+        else grad_er[(int64_t)v * H + h0 + q] = t;
+      }
     }
   }
+}
+
+__global__ void k_edge_reduce_combine(int n_split, int H, const int32_t* __restrict__ split_rows,
+                                      const int32_t* __restrict__ split_first, const float* __restrict__ scratch,
+                                      float* __restrict__ grad_er) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_split * H) return;
+  const int i = t / H, h = t - i * H;
+  float a = 0.f;
+  for (int s = split_first[i]; s < split_first[i + 1]; ++s) a += scratch[(int64_t)s * H + h];
+  grad_er[(int64_t)split_rows[i] * H + h] = a;
 }
 
 static inline int grid_for(int64_t n, int block = 256) {
@@ -238,7 +258,7 @@ extern "C" int botgat_edge_unstage(const botgat_graph* g, int order, int32_t H, 
 }
 
 extern "C" int botgat_edge_reduce_dst(const botgat_graph* g, int32_t H, const float* grad_ee, int64_t ld_gee,
-                                      float* grad_er, void* stream) {
+                                      float* grad_er, float* scratch, void* stream) {
   BG_REQUIRE(g && H > 0 && grad_er, "edge_reduce_dst: bad arguments");
   BG_REQUIRE(grad_ee || g->n_edges == 0, "edge_reduce_dst: null grad_ee");
   BG_REQUIRE(ld_gee >= H || g->n_edges == 0, "edge_reduce_dst: ld_gee < H");
@@ -246,13 +266,24 @@ extern "C" int botgat_edge_reduce_dst(const botgat_graph* g, int32_t H, const fl
   DeviceGuard guard(g->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int pf = env_pf();
-  const int grid = (int)((g->n_dst + 7) / 8);
+  const botgat_graph::SegTable& seg = g->seg_in;
+  const bool split = seg.n_items > 0;
+  BG_REQUIRE(!split || seg.n_slots == 0 || scratch, "edge_reduce_dst: this graph has split rows; scratch (n_slots_in*H floats) is required");
+  const int n_items = split ? seg.n_items : (int)g->n_dst;
+  const int32_t *sr = split ? seg.row : nullptr, *sb = seg.beg, *se = seg.end, *ss = seg.slot;
+  const int grid = (n_items + 7) / 8;
   for (int h0 = 0; h0 < H; h0 += kHMax) {
     const int Hn = std::min(kHMax, H - h0);
     const int vec = g->n_edges ? record_vec(grad_ee + h0, ld_gee, Hn) : 1;
-    if (vec == 4) { BG_PF_SWITCH((k_edge_reduce_dst<4, PF><<<grid, 256, 0, st>>>((int)g->n_dst, H, h0, Hn, g->in_indptr, g->in_eid, grad_ee, ld_gee, grad_er))) }
-    else if (vec == 2) { BG_PF_SWITCH((k_edge_reduce_dst<2, PF><<<grid, 256, 0, st>>>((int)g->n_dst, H, h0, Hn, g->in_indptr, g->in_eid, grad_ee, ld_gee, grad_er))) }
-    else { BG_PF_SWITCH((k_edge_reduce_dst<1, PF><<<grid, 256, 0, st>>>((int)g->n_dst, H, h0, Hn, g->in_indptr, g->in_eid, grad_ee, ld_gee, grad_er))) }
+#define BG_RD(VEC) BG_PF_SWITCH((k_edge_reduce_dst<VEC, PF><<<grid, 256, 0, st>>>(n_items, H, h0, Hn, g->in_indptr, g->in_eid, sr, sb, se, ss, grad_ee, ld_gee, grad_er, scratch)))
+    if (vec == 4) { BG_RD(4) } else if (vec == 2) { BG_RD(2) } else { BG_RD(1) }
+#undef BG_RD
+    BG_LAUNCHED(1);
+    BG_CHECK(cudaGetLastError());
+  }
+  if (split && seg.n_split > 0) {
+    const int n = seg.n_split * H;
+    k_edge_reduce_combine<<<(n + 255) / 256, 256, 0, st>>>(seg.n_split, H, seg.split_rows, seg.split_first, scratch, grad_er);
     BG_LAUNCHED(1);
     BG_CHECK(cudaGetLastError());
   }

@@ -262,14 +262,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB_BWD) gat_bwd_src_
   const float gel = warp_sum(gel_lane);
   if (slot >= 0) {
     // segment of a split row: partial grad_el and (unscaled) partial grad_ft go to this segment's scratch slot
-    float* sl = p.scratch + (int64_t)slot * H * (p.D + 1);
+    float* sl = p.scratch + (int64_t)slot * bwd_slot_floats(H, p.D);
     if (grp == 0) {
-      float* o = sl + H + (int64_t)h * p.D + v0 * VW;
+      float* o = sl + (int64_t)h * p.D + v0 * VW;
 #pragma unroll
       for (int i = 0; i < VPL; ++i)
         if (act[i]) acc[i].store(o + i * GSTRIDE);
     }
-    if (lane == 0) sl[h] = gel;
+    if (lane == 0) sl[H * p.D + h] = gel;
     return;
   }
   if (grp == 0) {
@@ -375,7 +375,9 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
     if (rc) return rc;
   }
   if ((phases & 4) && a->grad_er) {
-    int rc = botgat_edge_reduce_dst(g, a->H, a->grad_ee, ld_gee, a->grad_er, stream);
+    // the reduce's own scratch (n_slots_in * H floats) sits behind the src pass's slots
+    float* rscratch = a->scratch ? a->scratch + (int64_t)g->seg_out.n_slots * bwd_slot_floats(a->H, a->D) : nullptr;
+    int rc = botgat_edge_reduce_dst(g, a->H, a->grad_ee, ld_gee, a->grad_er, rscratch, stream);
     if (rc) return rc;
   }
   return 0;

@@ -186,14 +186,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB) gat_fwd_kernel(c
   }
   if (slot >= 0) {
     // segment of a split row: park (max, sum, unnormalised accumulator) in this segment's scratch slot
-    float* sl = p.scratch + (int64_t)slot * H * (p.D + 2);
+    float* sl = p.scratch + (int64_t)slot * fwd_slot_floats(H, p.D);
     if (grp == 0) {
-      float* o = sl + 2 * H + (int64_t)h * p.D + c0 + v0 * VW;
+      float* o = sl + (int64_t)h * p.D + c0 + v0 * VW;
 #pragma unroll
       for (int i = 0; i < VPL; ++i)
         if (act[i]) acc[i].store(o + i * G * VW);
     }
-    if (cp == 0 && lane == 0) { sl[h * 2] = m; sl[h * 2 + 1] = l; }
+    if (cp == 0 && lane == 0) { sl[H * p.D + h * 2] = m; sl[H * p.D + h * 2 + 1] = l; }
     return;
   }
   float scale = l > 0.f ? 1.f / l : 0.f;

@@ -65,6 +65,9 @@ bool use_lowdeg_kernels(int64_t n_edges, int64_t n_rows);
 int launch_fwd_lowdeg(const FwdParams& p, const Tiling& t, cudaStream_t st);
 int launch_src_lowdeg(const BwdParams& p, const Tiling& t, cudaStream_t st);
 int segment_length();
+// floats per scratch slot (rounded to 4 so that float4 stores into a slot stay aligned)
+__host__ __device__ inline int64_t fwd_slot_floats(int H, int D) { return ((int64_t)H * (D + 2) + 3) / 4 * 4; }
+__host__ __device__ inline int64_t bwd_slot_floats(int H, int D) { return ((int64_t)H * (D + 1) + 3) / 4 * 4; }
 int launch_fwd_combine(const botgat_graph::SegTable& t, int H, int D, int64_t ld_out, const float* scratch,
                        const float* ds, float* out, float* row_max, float* row_sum, cudaStream_t st);
 int launch_bwd_combine(const botgat_graph::SegTable& t, int H, int D, int64_t ld_gft, const float* scratch,

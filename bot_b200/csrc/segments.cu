@@ -104,7 +104,8 @@ int build_segments(int n_rows, const int32_t* indptr, const int32_t* deg, int64_
 // ---------------------------------------------------------------------------
 // combine kernels: one warp per (split row, head)
 // ---------------------------------------------------------------------------
-// forward scratch slot layout (floats): [H][2] (max, sum) then [H][D] unnormalised accumulators
+// forward scratch slot layout (floats): [H][D] unnormalised accumulators, then [H][2] (max, sum); slot stride
+// rounded up to 4 floats so that vector stores into a slot stay 16-byte aligned
 __global__ void __launch_bounds__(256)
 k_fwd_combine(int n_split, int H, int D, int64_t ld_out, const int32_t* __restrict__ split_rows,
               const int32_t* __restrict__ split_first, const float* __restrict__ scratch,
@@ -114,21 +115,22 @@ k_fwd_combine(int n_split, int H, int D, int64_t ld_out, const int32_t* __restri
   if (w >= n_split * H) return;
   const int i = w / H, h = w - i * H;
   const int row = split_rows[i], s0 = split_first[i], s1 = split_first[i + 1];
-  const int64_t stride = (int64_t)H * (D + 2);
+  const int64_t stride = fwd_slot_floats(H, D);
+  const int64_t ml = (int64_t)H * D + h * 2;  // offset of (max, sum) of head h inside a slot
   float M = -INFINITY;
-  for (int s = s0; s < s1; ++s) M = fmaxf(M, scratch[s * stride + h * 2]);
+  for (int s = s0; s < s1; ++s) M = fmaxf(M, scratch[s * stride + ml]);
   float L = 0.f;
   for (int s = s0; s < s1; ++s) {
-    const float m = scratch[s * stride + h * 2];
-    if (m != -INFINITY) L += scratch[s * stride + h * 2 + 1] * __expf(m - M);
+    const float m = scratch[s * stride + ml];
+    if (m != -INFINITY) L += scratch[s * stride + ml + 1] * __expf(m - M);
   }
   float scale = L > 0.f ? 1.f / L : 0.f;
   if (ds) scale *= ds[row];
   for (int d = lane; d < D; d += 32) {
     float a = 0.f;
     for (int s = s0; s < s1; ++s) {
-      const float m = scratch[s * stride + h * 2];
-      if (m != -INFINITY) a = fmaf(scratch[s * stride + 2 * H + (int64_t)h * D + d], __expf(m - M), a);
+      const float m = scratch[s * stride + ml];
+      if (m != -INFINITY) a = fmaf(scratch[s * stride + (int64_t)h * D + d], __expf(m - M), a);
     }
     out[(int64_t)row * ld_out + h * D + d] = a * scale;
   }
@@ -138,7 +140,7 @@ k_fwd_combine(int n_split, int H, int D, int64_t ld_out, const int32_t* __restri
   }
 }
 
-// backward scratch slot layout (floats): [H] partial grad_el then [H][D] partial grad_ft (before the src scale)
+// backward scratch slot layout (floats): [H][D] partial grad_ft (before the src scale), then [H] partial grad_el
 __global__ void __launch_bounds__(256)
 k_bwd_combine(int n_split, int H, int D, int64_t ld_gft, const int32_t* __restrict__ split_rows,
               const int32_t* __restrict__ split_first, const float* __restrict__ scratch,
@@ -147,16 +149,16 @@ k_bwd_combine(int n_split, int H, int D, int64_t ld_gft, const int32_t* __restri
   if (w >= n_split * H) return;
   const int i = w / H, h = w - i * H;
   const int row = split_rows[i], s0 = split_first[i], s1 = split_first[i + 1];
-  const int64_t stride = (int64_t)H * (D + 1);
+  const int64_t stride = bwd_slot_floats(H, D);
   const float c = cs ? cs[row] : 1.f;
   for (int d = lane; d < D; d += 32) {
     float a = 0.f;
-    for (int s = s0; s < s1; ++s) a += scratch[s * stride + H + (int64_t)h * D + d];
+    for (int s = s0; s < s1; ++s) a += scratch[s * stride + (int64_t)h * D + d];
     grad_ft[(int64_t)row * ld_gft + h * D + d] = a * c;
   }
   if (lane == 0) {
     float gsum = 0.f;
-    for (int s = s0; s < s1; ++s) gsum += scratch[s * stride + h];
+    for (int s = s0; s < s1; ++s) gsum += scratch[s * stride + (int64_t)H * D + h];
     grad_el[(int64_t)row * H + h] = gsum;
   }
 }

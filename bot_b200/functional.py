@@ -65,6 +65,10 @@ def _span(name):
     return _Span(timer, name)
 
 
+def _r4(x):
+    return (x + 3) // 4 * 4
+
+
 def _f32c(t, name):
     if t is None:
         return None
@@ -182,7 +186,7 @@ class GATFusedFn(torch.autograd.Function):
             a.out, a.row_max, a.row_sum = out.data_ptr(), row_max.data_ptr(), row_sum.data_ptr()
             scratch = None
             if graph._info.n_slots_in:  # heavy rows are split over several warps (segments.cu)
-                scratch = torch.empty(graph._info.n_slots_in * H * (D + 2), dtype=torch.float32, device=ft.device)
+                scratch = torch.empty(graph._info.n_slots_in * _r4(H * (D + 2)), dtype=torch.float32, device=ft.device)
                 a.scratch = scratch.data_ptr()
             with _span("gat_fwd"):
                 rc = lib.botgat_gat_forward(h, C.byref(a), _stream())
@@ -234,8 +238,9 @@ class GATFusedFn(torch.autograd.Function):
             a.out, a.row_max, a.row_sum, a.gout = out.data_ptr(), row_max.data_ptr(), row_sum.data_ptr(), gout.data_ptr()
             a.drec, a.gprime, a.gz = drec.data_ptr(), p(gprime), p(gz)
             scratch = None
-            if graph._info.n_slots_out:
-                scratch = torch.empty(graph._info.n_slots_out * H * (D + 1), dtype=torch.float32, device=dev)
+            if graph._info.n_slots_out or graph._info.n_slots_in:
+                scratch = torch.empty(graph._info.n_slots_out * _r4(H * (D + 1)) + graph._info.n_slots_in * H,
+                                      dtype=torch.float32, device=dev)
                 a.scratch = scratch.data_ptr()
             a.grad_ft, a.grad_el, a.grad_ee, a.grad_er = grad_ft.data_ptr(), grad_el.data_ptr(), p(grad_ee), p(grad_er)
             a.ld_gee = grad_ee.stride(0) if grad_ee is not None else 0

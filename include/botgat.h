@@ -77,8 +77,10 @@ typedef struct {
   int32_t has_zero_in_degree; /* replaces `(graph.in_degrees()==0).any()`, models.py:478 */
   int32_t device;
   /* Heavy rows (longer than the segment length, 2048 neighbours) are split over several warps; each partial
-   * segment needs one scratch slot.  Forward scratch: n_slots_in * H * (D + 2) floats; backward scratch:
-   * n_slots_out * H * (D + 1) floats.  Both are 0 for graphs without heavy rows. */
+   * segment needs one scratch slot.  With r4(x) = x rounded up to a multiple of 4:
+   *   forward scratch  = n_slots_in  * r4(H * (D + 2)) floats
+   *   backward scratch = n_slots_out * r4(H * (D + 1)) + n_slots_in * H floats
+   * Both are 0 for graphs without heavy rows. */
   int64_t n_slots_in, n_slots_out;
 } botgat_graph_info;
 int botgat_graph_get_info(const botgat_graph* g, botgat_graph_info* info /* HOST */);
@@ -131,7 +133,8 @@ int botgat_edge_unstage(const botgat_graph* g, int order, int32_t H, const float
 /* grad_er[v,h] = sum over the in-edges k of v of grad_ee[k*ld_gee + h]   (replaces the copy_e/sum SpMM DGL
  * runs as the backward of u_add_v) */
 int botgat_edge_reduce_dst(const botgat_graph* g, int32_t H, const float* grad_ee, int64_t ld_gee,
-                           float* grad_er, void* stream);
+                           float* grad_er, float* scratch /* n_slots_in*H floats, NULL if n_slots_in == 0 */,
+                           void* stream);
 
 /* ------------------------------------------------------------------------
  * Fused forward: logits -> leaky_relu -> online edge-softmax -> attention
@@ -167,7 +170,7 @@ typedef struct {
   float* out;             /* (n_dst, ld_out) */
   float* row_max;         /* (n_dst, H)  saved for backward */
   float* row_sum;         /* (n_dst, H)  saved for backward */
-  float* scratch;         /* n_slots_in * H * (D + 2) floats, or NULL when n_slots_in == 0 */
+  float* scratch;         /* forward scratch (see botgat_graph_info), or NULL when n_slots_in == 0 */
 } botgat_fwd_args;
 int botgat_gat_forward(const botgat_graph* g, const botgat_fwd_args* a /* HOST */, void* stream);
 
@@ -208,7 +211,7 @@ typedef struct {
   /* workspaces */
   float* drec;            /* (H, n_dst, 4) */
   float* gprime;          /* (n_dst, ld_out); required iff dst_scale != NULL */
-  float* scratch;         /* n_slots_out * H * (D + 1) floats, or NULL when n_slots_out == 0 */
+  float* scratch;         /* backward scratch (see botgat_graph_info), or NULL when both slot counts are 0 */
   float* gz;              /* (H, n_edges) or NULL.  NULL: the src pass writes grad_ee directly in edge-id order;
                              given: it writes gz in out-CSR order and phase 4 un-stages it into grad_ee */
   /* outputs */
