@@ -10,7 +10,7 @@ or the tensors are not on a CUDA device.
 """
 from . import _lib  # noqa: F401
 from .graph import Graph, add_self_loop, create_block, graph, remove_self_loop, to_bidirected  # noqa: F401
-from .functional import GATFusedFn, gat_fused  # noqa: F401
+from .functional import Deferred, GATFusedFn, edge_logits, gat_fused  # noqa: F401
 
 __all__ = ["Graph", "graph", "create_block", "to_bidirected", "remove_self_loop", "add_self_loop",
-           "GATFusedFn", "gat_fused"]
+           "GATFusedFn", "gat_fused", "edge_logits", "Deferred"]

@@ -70,6 +70,10 @@ SIGNATURES = {
     "botgat_edge_stage": (C.c_int, [c_vp, C.c_int, C.c_int32, c_vp, C.c_int64, c_vp, c_vp, C.c_int64, c_vp, c_vp, c_vp]),
     "botgat_edge_unstage": (C.c_int, [c_vp, C.c_int, C.c_int32, c_vp, c_vp, C.c_int64, c_vp]),
     "botgat_edge_reduce_dst": (C.c_int, [c_vp, C.c_int32, c_vp, C.c_int64, c_vp, c_vp, c_vp]),
+    "botgat_edge_proj_gw_blocks": (C.c_int, []),
+    "botgat_edge_proj_forward": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, c_vp, C.c_int64, c_vp, c_vp, C.c_int64, C.c_int, c_vp]),
+    "botgat_edge_proj_backward": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, c_vp, C.c_int64, c_vp, c_vp, C.c_int64, c_vp,
+                                            C.c_int64, c_vp, c_vp, C.c_int, c_vp]),
     "botgat_gat_forward": (C.c_int, [c_vp, C.POINTER(FwdArgs), c_vp]),
     "botgat_gat_backward": (C.c_int, [c_vp, C.POINTER(BwdArgs), c_vp]),
     "botgat_partition_1d": (C.c_int, [c_vp, C.c_int32, c_i64p, c_vp]),

@@ -255,6 +255,72 @@ class GATFusedFn(torch.autograd.Function):
         return None, grad_ft, grad_el, grad_er, (grad_ee if need_ee else None), None, None, None, None, None, None, None
 
 
+class EdgeLogitProj(torch.autograd.Function):
+    """``ee = feat_edge @ W^T`` emitted with padded rows (E, pad_heads(H)) — `attn_edge_fc(feat_edge)` of
+    src/ogbn-proteins/models.py:131 as streaming kernels (``botgat_edge_proj_*``) instead of three skinny GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        lib = _lib.load()
+        x = _f32c(x, "feat_edge")
+        weight = _f32c(weight, "weight")
+        E, Cin = x.shape
+        H = weight.shape[0]
+        y = torch.empty((E, pad_heads(H)), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            with _span("edge_proj_fwd"):
+                rc = lib.botgat_edge_proj_forward(E, Cin, H, x.data_ptr(), x.stride(0), weight.data_ptr(), y.data_ptr(),
+                                                  y.stride(0), x.device.index, _stream())
+        _lib.check(rc, "botgat_edge_proj_forward")
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        x, weight = ctx.saved_tensors
+        E, Cin = x.shape
+        H = weight.shape[0]
+        gy, ld_gy = _rows(gy, "grad_ee", H)
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gw = torch.empty_like(weight) if ctx.needs_input_grad[1] else None
+        partials = torch.empty(lib.botgat_edge_proj_gw_blocks() * H * Cin, dtype=torch.float32, device=x.device) \
+            if gw is not None else None
+        with torch.cuda.device(x.device):
+            with _span("edge_proj_bwd"):
+                rc = lib.botgat_edge_proj_backward(E, Cin, H, x.data_ptr(), x.stride(0), weight.data_ptr(), gy.data_ptr(),
+                                                   ld_gy, _lib.ptr(gx), gx.stride(0) if gx is not None else 0,
+                                                   _lib.ptr(gw), _lib.ptr(partials), x.device.index, _stream())
+        _lib.check(rc, "botgat_edge_proj_backward")
+        return gx, gw
+
+
+def edge_logits(feat_edge, weight):
+    """Padded per-edge logits (E, pad_heads(H)) from edge features (E, C) and an ``nn.Linear`` weight (H, C).
+    Falls back to a torch matmul (a library GEMM, still on the GPU) for shapes the streaming kernels do not cover."""
+    H, Cin = weight.shape
+    if H <= 8 and Cin <= 64 and H * Cin <= 256 and feat_edge.dim() == 2:
+        return EdgeLogitProj.apply(feat_edge, weight)
+    pad = pad_heads(H) - H
+    w = torch.cat([weight, weight.new_zeros(pad, Cin)], 0) if pad > 0 else weight
+    return torch.nn.functional.linear(feat_edge, w)
+
+
+class Deferred:
+    """A tensor whose producer (e.g. a host-to-device copy) runs on another stream.  ``GATConv.forward`` accepts it
+    in place of ``feat_edge`` and waits for it only where the edge features are first needed, so the copy
+    overlaps the node-side projections and the edge-drop draw."""
+
+    def __init__(self, tensor, event, requires_grad=False):
+        self.tensor, self.event, self.requires_grad = tensor, event, requires_grad
+
+    def wait(self):
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.event)
+        self.tensor.record_stream(cur)
+        return self.tensor.requires_grad_(True) if self.requires_grad else self.tensor
+
+
 def gat_fused(graph, ft, el, er=None, ee=None, keep=None, attn_mul=None, src_scale=None, dst_scale=None,
               slope=0.2, attn_p=0.0, seed=0):
     """Functional form of :class:`GATFusedFn` (accepts the reference's trailing-1 shapes, e.g. el (N,H,1))."""

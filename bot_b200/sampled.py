@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .functional import gat_fused, pad_heads
+from .functional import Deferred, edge_logits, gat_fused
 from .no_sampling import draw_attn_mul, draw_edge_keep
 
 
@@ -84,17 +84,6 @@ class GATConv(nn.Module):
             resid = self.dst_fc(feat_dst).view(-1, H, D)                      # models.py:107
             el = self.attn_src_fc(feat_src)                                   # models.py:108  (N_s,H)
             er = self.attn_dst_fc(feat_dst) if self.attn_dst_fc is not None else None   # models.py:122-124
-            ee = None
-            if feat_edge is not None:                                         # models.py:130-131
-                # same Linear, emitted with zero-weight padding columns so that each edge's H logits form one
-                # aligned 32-byte record (functional.pad_heads): the staging passes then touch one DRAM sector
-                # per edge.  Columns >= H are ignored by the kernels and get zero gradient.
-                w = self.attn_edge_fc.weight
-                pad = pad_heads(H) - H
-                if pad > 0:
-                    w = torch.cat([w, w.new_zeros(pad, w.shape[1])], 0)
-                ee = F.linear(feat_edge, w)                                   # (E, pad_heads(H))
-
             E = graph.number_of_edges()
             keep = attn_mul = eids = None
             attn_p, seed = 0.0, 0
@@ -106,6 +95,14 @@ class GATConv(nn.Module):
                 else:
                     attn_p = self.attn_drop.p
                     seed = int(torch.randint(0, 2**62, (1,)).item())
+
+            ee = None
+            if feat_edge is not None:                                         # models.py:130-131
+                if isinstance(feat_edge, Deferred):   # e.g. a host-to-device copy still in flight on another stream
+                    feat_edge = feat_edge.wait()
+                # the same Linear as a streaming kernel, emitted as one aligned 32-byte record per edge
+                # (functional.pad_heads); padding columns are ignored by the kernels and get zero gradient
+                ee = edge_logits(feat_edge, self.attn_edge_fc.weight)          # (E, pad_heads(H))
 
             rst = gat_fused(graph, ft, el, er, ee, keep, attn_mul, None, dst_scale,
                             self._negative_slope, attn_p, seed)                # models.py:125-156

@@ -137,6 +137,20 @@ int botgat_edge_reduce_dst(const botgat_graph* g, int32_t H, const float* grad_e
                            void* stream);
 
 /* ------------------------------------------------------------------------
+ * Per-edge logit projection  y[k, 0:H] = x[k, 0:C] @ W^T  (W row-major (H, C); H <= 8, C <= 64, H*C <= 256).
+ * Replaces `attn_edge_fc(feat_edge)` (src/ogbn-proteins/models.py:131) and its autograd backward — three
+ * skinny cuBLAS GEMMs — by streaming kernels.  y rows have stride ld_y >= H; columns [H, min(ld_y, 8)) are
+ * written as zeros (the padded record layout of botgat_edge_stage).  Backward: gx (n, ld_gx) and/or gW (H, C);
+ * `partials` is a workspace of botgat_edge_proj_gw_blocks() * H * C floats (fixed-order reduction, no atomics).
+ * ---------------------------------------------------------------------- */
+int botgat_edge_proj_gw_blocks(void);
+int botgat_edge_proj_forward(int64_t n, int32_t C, int32_t H, const float* x, int64_t ld_x, const float* W,
+                             float* y, int64_t ld_y, int device, void* stream);
+int botgat_edge_proj_backward(int64_t n, int32_t C, int32_t H, const float* x, int64_t ld_x, const float* W,
+                              const float* gy, int64_t ld_gy, float* gx /* or NULL */, int64_t ld_gx,
+                              float* gW /* or NULL */, float* partials, int device, void* stream);
+
+/* ------------------------------------------------------------------------
  * Fused forward: logits -> leaky_relu -> online edge-softmax -> attention
  * dropout -> u_mul_e/sum SpMM -> degree scaling, one pass over the in-CSR.
  * Replaces src/no-sampling/models.py:500-505,523-555 and
