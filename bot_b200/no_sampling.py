@@ -236,3 +236,119 @@ class GAT(nn.Module):
                 h = self.dropout(self.activation(h))
         h = h.mean(1)
         return self.biases[-1](h)
+
+
+class GraphConv(nn.Module):
+    """GCN layer (src/no-sampling/models.py:114-413), SURVEY.md section 8f rank 3: the `copy_src`/`sum` aggregation
+    (models.py:374,381) is the GAT gather with uniform attention, so it runs on the same fused kernel —
+    ``softmax`` of equal logits is 1/in_degree, undone by a destination scale of in_degree."""
+
+    def __init__(self, in_feats, out_feats, norm="both", weight=True, bias=True, activation=None, allow_zero_in_degree=False):
+        super().__init__()
+        if norm not in ("none", "both", "right"):
+            raise ValueError(f'Invalid norm value. Must be either "none", "both" or "right". But got "{norm}".')
+        self._in_feats, self._out_feats, self._norm = in_feats, out_feats, norm
+        self._allow_zero_in_degree = allow_zero_in_degree
+        if weight:
+            self.weight = nn.Parameter(torch.empty(in_feats, out_feats))
+        else:
+            self.register_parameter("weight", None)
+        if bias:
+            self.bias = nn.Parameter(torch.empty(out_feats))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+        self._activation = activation
+
+    def reset_parameters(self):
+        if self.weight is not None:
+            nn.init.xavier_uniform_(self.weight)
+        if self.bias is not None:
+            nn.init.zeros_(self.bias)
+
+    def set_allow_zero_in_degree(self, set_value):
+        self._allow_zero_in_degree = set_value
+
+    def _aggregate(self, graph, x, src_scale):
+        """sum over in-edges of src_scale[u] * x[u]  (update_all(copy_src, sum), models.py:374/381)"""
+        n_src = x.shape[0]
+        flat = x.reshape(n_src, 1, -1)
+        if "gcn_zero" not in graph._cache or graph._cache["gcn_zero"].shape[0] != n_src:
+            graph._cache["gcn_zero"] = torch.zeros(n_src, 1, device=x.device)
+            graph._cache["gcn_indeg"] = graph.in_degrees().float().contiguous()
+        out = gat_fused(graph, flat, graph._cache["gcn_zero"], None, None, None, None, src_scale,
+                        graph._cache["gcn_indeg"], 0.2, 0.0, 0)
+        return out.reshape((out.shape[0],) + tuple(x.shape[1:]))
+
+    def forward(self, graph, feat, weight=None):
+        with graph.local_scope():
+            if not self._allow_zero_in_degree and graph.has_zero_in_degree:   # models.py:334-347
+                raise RuntimeError("There are 0-in-degree nodes in the graph, output for those nodes will be invalid. "
+                                   "Add self-loops or construct the module with allow_zero_in_degree=True.")
+            feat_src, feat_dst = feat if isinstance(feat, tuple) else (feat, feat)
+            src_scale = graph.deg_scale("out", -0.5) if self._norm == "both" else None      # models.py:351-356
+            if weight is not None:
+                if self.weight is not None:
+                    raise RuntimeError("External weight is provided while at the same time the module has defined its "
+                                       "own weight parameter. Please create the module with flag weight=False.")
+            else:
+                weight = self.weight
+            if self._in_feats > self._out_feats:                              # models.py:368-376: W first
+                if weight is not None:
+                    # the source scale commutes with the projection; applying it in the kernel saves a pass
+                    feat_src = torch.matmul(feat_src, weight)
+                rst = self._aggregate(graph, feat_src, src_scale)
+            else:                                                             # models.py:377-385: aggregate first
+                rst = self._aggregate(graph, feat_src, src_scale)
+                if weight is not None:
+                    rst = torch.matmul(rst, weight)
+            if self._norm != "none":                                          # models.py:387-395
+                degs = graph.in_degrees().float().clamp(min=1)
+                norm = torch.pow(degs, -0.5) if self._norm == "both" else 1.0 / degs
+                rst = rst * norm.reshape(norm.shape + (1,) * (feat_dst.dim() - 1))
+            if self.bias is not None:
+                rst = rst + self.bias
+            if self._activation is not None:
+                rst = self._activation(rst)
+            return rst
+
+
+class GCN(nn.Module):
+    """Stack of GraphConv layers (src/no-sampling/models.py:569-641)."""
+
+    def __init__(self, in_feats, n_classes, n_hidden, n_layers, activation, norm="none", norm_adj="symm", dropout=0.0,
+                 input_drop=0, residual=False, use_linear=False):
+        super().__init__()
+        self.n_layers, self.n_hidden, self.n_classes = n_layers, n_hidden, n_classes
+        self.use_linear, self.residual = use_linear, residual
+        self.convs = nn.ModuleList()
+        if use_linear:
+            self.linear = nn.ModuleList()
+        self.norms = nn.ModuleList()  # the reference's `norm != "none:"` (sic) is always true
+        for i in range(n_layers):
+            in_hidden = n_hidden if i > 0 else in_feats
+            out_hidden = n_hidden if i < n_layers - 1 else n_classes
+            bias = norm == "none" or i == n_layers - 1
+            self.convs.append(GraphConv(in_hidden, out_hidden, "both" if norm_adj == "symm" else "right", bias=bias))
+            if use_linear:
+                self.linear.append(nn.Linear(in_hidden, out_hidden, bias=False))
+            if i < n_layers - 1 and norm == "batch":
+                self.norms.append(nn.BatchNorm1d(out_hidden))
+        self.input_drop = nn.Dropout(input_drop)
+        self.dropout = nn.Dropout(dropout)
+        self.activation = activation
+
+    def forward(self, graph, feat):
+        h = self.input_drop(feat)
+        h_last = None
+        for i in range(self.n_layers):
+            conv = self.convs[i](graph, h)
+            h = conv + self.linear[i](h) if self.use_linear else conv
+            if i < self.n_layers - 1:
+                if self.residual and h_last is not None:
+                    h = h + h_last
+                h_last = h
+                if self.norms:
+                    h = self.norms[i](h)
+                h = self.dropout(self.activation(h))
+        return h

@@ -137,5 +137,83 @@ def main():
              block=25)
 
 
+def run_model_case(name, build, feed, n, e, seed, self_loops=False):
+    """Whole-model golden vector (eval mode, so no random draws): state_dict, inputs, logits."""
+    torch.manual_seed(seed)
+    src, dst = make_graph(n, e, seed, self_loops)
+    g = dgl_shim.ShimGraph(src, dst, n)
+    model = build()
+    model.eval()
+    inputs = feed(g, len(src), n)
+    with torch.no_grad():
+        y = model(*inputs["call"](g))
+    torch.save({"src": torch.as_tensor(src), "dst": torch.as_tensor(dst), "n": n,
+                "state_dict": {k: v.detach().clone() for k, v in model.state_dict().items()},
+                "tensors": inputs["tensors"], "y": y.detach().clone()}, os.path.join(OUT, name + ".pt"))
+    print(name, tuple(y.shape), float(y.abs().max()))
+
+
+def model_cases():
+    v1 = dgl_shim.import_reference("no-sampling")
+    prot = dgl_shim.import_reference("ogbn-proteins")
+    prod = dgl_shim.import_reference("ogbn-products")
+
+    def feed_v1(g, E, n):
+        x = torch.randn(n, 20)
+        return {"tensors": {"feat": x}, "call": lambda g: (g, x)}
+
+    run_model_case("model_v1_gat_bn", lambda: v1.GAT(20, 0, 5, 8, 3, 2, F.relu, norm="batch", dropout=0.5, attn_drop=0.1,
+                                                       use_symmetric_norm=True, linear=True, residual=True), feed_v1, 70, 500, 20, True)
+    run_model_case("model_v1_gat_bias", lambda: v1.GAT(20, 0, 5, 8, 2, 3, F.relu, norm="none", non_interactive_attn=True),
+                   feed_v1, 70, 500, 21, True)
+
+    def feed_prot(g, E, n):
+        x, ef = torch.randn(n, 8), torch.randn(E, 8)
+        g.srcdata["feat"] = x
+        g.edata["feat"] = ef
+        return {"tensors": {"feat": x, "efeat": ef}, "call": lambda g: (g,)}
+
+    run_model_case("model_proteins_gat", lambda: prot.GAT(8, 8, 11, 2, 3, 10, 16, F.relu, 0.25, 0.1, 0.0, 0.1), feed_prot, 60, 600, 22)
+
+    def feed_prod(g, E, n):
+        x = torch.randn(n, 9)
+        g.srcdata["feat"] = x
+        return {"tensors": {"feat": x}, "call": lambda g: (g,)}
+
+    run_model_case("model_products_gat", lambda: prod.GAT(9, 0, 7, 2, 2, 6, 0, F.relu, 0.5, 0.1, 0.0, 0.1,
+                                                          allow_zero_in_degree=True, residual=True), feed_prod, 60, 600, 23)
+
+
+def gcn_cases():
+    """GraphConv / GCN: layer outputs + input gradients, model logits."""
+    v1 = dgl_shim.import_reference("no-sampling")
+    for name, ctor, fin, seed in (("gcn_both_wfirst", dict(in_feats=24, out_feats=8, norm="both"), 24, 30),
+                                  ("gcn_right_aggfirst", dict(in_feats=8, out_feats=20, norm="right"), 8, 31),
+                                  ("gcn_none_nobias", dict(in_feats=12, out_feats=12, norm="none", bias=False), 12, 32)):
+        torch.manual_seed(seed)
+        src, dst = make_graph(60, 500, seed, True)
+        g = dgl_shim.ShimGraph(src, dst, 60)
+        conv = v1.GraphConv(**ctor)
+        x = torch.randn(60, fin, requires_grad=True)
+        y = conv(g, x)
+        w = torch.randn(y.shape, generator=torch.Generator().manual_seed(seed + 1))
+        (y * w).sum().backward()
+        torch.save({"ctor": ctor, "src": torch.as_tensor(src), "dst": torch.as_tensor(dst), "n": 60,
+                    "state_dict": {k: v.detach().clone() for k, v in conv.state_dict().items()},
+                    "x": x.detach().clone(), "w": w, "y": y.detach().clone(), "gx": x.grad.clone(),
+                    "gparams": {k: p.grad.clone() for k, p in conv.named_parameters() if p.grad is not None}},
+                   os.path.join(OUT, name + ".pt"))
+        print(name, tuple(y.shape), float(y.abs().max()))
+
+    def feed(g, E, n):
+        x = torch.randn(n, 20)
+        return {"tensors": {"feat": x}, "call": lambda g: (g, x)}
+
+    run_model_case("model_v1_gcn", lambda: v1.GCN(20, 5, 16, 3, F.relu, norm="batch", norm_adj="symm", dropout=0.5,
+                                                   residual=True, use_linear=True), feed, 70, 500, 33, True)
+
+
 if __name__ == "__main__":
     main()
+    model_cases()
+    gcn_cases()

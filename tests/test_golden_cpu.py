@@ -7,7 +7,10 @@ import torch
 
 from oracle import modules_ref
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.pt")))
+_ALL = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.pt")))
+GOLDEN = [p for p in _ALL if not os.path.basename(p).startswith(("model_", "gcn_"))]   # single GATConv layers
+GOLDEN_GCN = [p for p in _ALL if os.path.basename(p).startswith("gcn_")]               # single GraphConv layers
+GOLDEN_MODELS = [p for p in _ALL if os.path.basename(p).startswith("model_")]     # whole GAT models
 
 
 def load(path):
@@ -46,7 +49,7 @@ def oracle_forward(case, dtype=torch.float32):
 
 
 def test_golden_files_present():
-    assert len(GOLDEN) >= 12
+    assert len(GOLDEN) >= 12 and len(GOLDEN_MODELS) >= 4
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-3] for p in GOLDEN])

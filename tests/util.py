@@ -111,3 +111,30 @@ def check_case(c, device, **kw):
         errs[k] = rel_err(g[k], ref_g[k])
         assert errs[k] <= GRAD_TOL, f"grad_{k} rel err {errs[k]:.3e} > {GRAD_TOL}"
     return errs
+
+
+def philox_attn_mul(seed, n_edges, n_heads, p):
+    """numpy restatement of `philox_dropout_mul` (bot_b200/csrc/common.cuh): Philox4x32-10 keyed on the 64-bit
+    seed, counter (edge id, head >> 2, 0x9E3779B9, 0xBB67AE85), component head & 3; keep iff u >= p."""
+    import numpy as np
+
+    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
+    out = np.zeros((n_edges, n_heads), dtype=np.float32)
+    eid = np.arange(n_edges, dtype=np.uint32)
+    for h in range(n_heads):
+        c0 = eid.copy()
+        c1 = np.full(n_edges, h >> 2, dtype=np.uint32)
+        c2 = np.full(n_edges, 0x9E3779B9, dtype=np.uint32)
+        c3 = np.full(n_edges, 0xBB67AE85, dtype=np.uint32)
+        k0, k1 = np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF)
+        for _ in range(10):
+            p0 = M0 * c0.astype(np.uint64)
+            p1 = M1 * c2.astype(np.uint64)
+            hi0, lo0 = (p0 >> np.uint64(32)).astype(np.uint32), p0.astype(np.uint32)
+            hi1, lo1 = (p1 >> np.uint64(32)).astype(np.uint32), p1.astype(np.uint32)
+            c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+            k0, k1 = np.uint32((int(k0) + int(W0)) & 0xFFFFFFFF), np.uint32((int(k1) + int(W1)) & 0xFFFFFFFF)
+        x = (c0, c1, c2, c3)[h & 3]
+        u = (x >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+        out[:, h] = np.where(u >= np.float32(p), np.float32(1.0 / (1.0 - p)), np.float32(0.0))
+    return torch.from_numpy(out)
