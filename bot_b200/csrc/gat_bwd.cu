@@ -353,7 +353,7 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
     p.indptr = g->out_indptr; p.indices = g->out_indices; p.eid = g->out_eid;
     p.n_rows = (int)g->n_src; p.eb = a->eb_out; p.am = a->am_out; p.omask = t.omask;
     const botgat_graph::SegTable& seg = g->seg_out;
-    const bool lowdeg = use_lowdeg_kernels(g->n_edges, g->n_src);
+    const bool lowdeg = use_lowdeg_kernels(g->n_edges, g->n_src, true);
     const bool split = seg.n_items > 0 && !lowdeg;
     BG_REQUIRE(!split || seg.n_slots == 0 || a->scratch, "backward: this graph has split rows; scratch is required");
     p.seg_row = split ? seg.row : nullptr; p.seg_beg = seg.beg; p.seg_end = seg.end; p.seg_slot = seg.slot;

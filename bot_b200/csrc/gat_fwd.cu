@@ -258,7 +258,7 @@ extern "C" int botgat_gat_forward(const botgat_graph* g, const botgat_fwd_args* 
   p.out = a->out; p.row_max = a->row_max; p.row_sum = a->row_sum;
   p.col_parts = t.col_parts; p.part_cols = t.part_cols; p.omask = t.omask;
   const botgat_graph::SegTable& seg = g->seg_in;
-  const bool lowdeg = use_lowdeg_kernels(g->n_edges, g->n_dst);
+  const bool lowdeg = use_lowdeg_kernels(g->n_edges, g->n_dst, false);
   const bool split = seg.n_items > 0 && !lowdeg;
   BG_REQUIRE(!split || seg.n_slots == 0 || a->scratch, "forward: this graph has split rows; scratch is required");
   p.seg_row = split ? seg.row : nullptr; p.seg_beg = seg.beg; p.seg_end = seg.end; p.seg_slot = seg.slot;

@@ -23,9 +23,13 @@ namespace botgat {
 #define BG_MINB_BWD 4
 #endif
 
-bool use_lowdeg_kernels(int64_t n_edges, int64_t n_rows) {
-  const char* s = getenv("BOTGAT_LOWDEG");
-  const int64_t thr = (s && *s) ? atoll(s) : 20;  // average neighbours per row below which a group owns a row (swept: profiles/r01_sweeps.md)
+bool use_lowdeg_kernels(int64_t n_edges, int64_t n_rows, bool backward) {
+  // average neighbours per row below which a group owns a row (swept on B200, profiles/r01_sweeps.md): the
+  // forward switches late (its chunk overhead is per G neighbours instead of per 32), the backward src pass
+  // early (its per-row prologue/epilogue is heavier: ft[u] load, two outputs)
+  const char* s = getenv(backward ? "BOTGAT_LOWDEG_BWD" : "BOTGAT_LOWDEG");
+  if (!(s && *s)) s = getenv("BOTGAT_LOWDEG");
+  const int64_t thr = (s && *s) ? atoll(s) : (backward ? 96 : 20);
   return n_rows > 0 && n_edges < thr * n_rows;
 }
 

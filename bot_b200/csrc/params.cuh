@@ -61,7 +61,7 @@ struct SrcOps {
 // Low-degree graphs (average row shorter than one 32-neighbour chunk and a half) use the group-per-row kernels
 // (gat_lowdeg.cu): a G-lane group owns a row, so a warp works on 32/G rows at once and the per-row latency
 // chain (index -> logit operands -> row gathers) and epilogue are shared.  BOTGAT_LOWDEG overrides the threshold.
-bool use_lowdeg_kernels(int64_t n_edges, int64_t n_rows);
+bool use_lowdeg_kernels(int64_t n_edges, int64_t n_rows, bool backward);
 int launch_fwd_lowdeg(const FwdParams& p, const Tiling& t, cudaStream_t st);
 int launch_src_lowdeg(const BwdParams& p, const Tiling& t, cudaStream_t st);
 int segment_length();
