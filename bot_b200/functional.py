@@ -60,6 +60,18 @@ timer = None  # set to a KernelTimer to record
 #             in the staging pass); kept for graphs whose edge ids already follow the CSR order.
 edge_mode = "staged"
 
+# Stage the backward's (out-CSR-ordered) edge operands already during the forward, on a side stream: the staging
+# pass is DRAM-bound, the forward gather is L2-bound, so they overlap.  Costs one (Hb, E) buffer kept until backward.
+prestage_backward = True
+_side_streams = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
 
 def _span(name):
     return _Span(timer, name)
@@ -165,6 +177,19 @@ class GATFusedFn(torch.autograd.Function):
 
         staged = edge_mode == "staged"
         with torch.cuda.device(ft.device):
+            pre = None
+            has_edge_ops = ee is not None or keep is not None or attn_mul is not None
+            if staged and prestage_backward and has_edge_ops and any(ctx.needs_input_grad):
+                main, side = torch.cuda.current_stream(), _side_stream(ft.device)
+                side.wait_stream(main)  # ee / keep / attn_mul are produced on the main stream
+                with torch.cuda.stream(side):
+                    eb_o, _, am_o = edge_stage(graph, _lib.ORDER_OUT, H, ee, keep, attn_mul)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                for t in (ee, keep, attn_mul):
+                    if t is not None:
+                        t.record_stream(side)
+                pre = (eb_o, am_o, ev)
             eb_in, Hb, am_in = edge_stage(graph, _lib.ORDER_IN, H, ee, keep, attn_mul) if staged else (None, 0, None)
             out = torch.empty((N_d, H, D), dtype=torch.float32, device=ft.device)
             row_max = torch.empty((N_d, H), dtype=torch.float32, device=ft.device)
@@ -193,6 +218,7 @@ class GATFusedFn(torch.autograd.Function):
             _lib.check(rc, "botgat_gat_forward")
 
         ctx.graph = graph
+        ctx.pre = pre
         ctx.cfg = (H, D, staged, float(slope), float(a.attn_p), int(seed))
         ctx.save_for_backward(ft, el, er, ee, keep, attn_mul, src_scale, dst_scale, out, row_max, row_sum)
         return out
@@ -214,7 +240,16 @@ class GATFusedFn(torch.autograd.Function):
             return t.data_ptr() if t is not None else None
 
         with torch.cuda.device(dev):
-            eb_out, Hb, am_out = edge_stage(graph, _lib.ORDER_OUT, H, ee, keep, attn_mul) if staged else (None, 0, None)
+            if ctx.pre is not None:  # staged during the forward on the side stream
+                eb_out, am_out, ev = ctx.pre
+                cur = torch.cuda.current_stream()
+                cur.wait_event(ev)
+                for t in (eb_out, am_out):
+                    if t is not None:
+                        t.record_stream(cur)
+                Hb = eb_out.shape[0] if eb_out is not None else 0
+            else:
+                eb_out, Hb, am_out = edge_stage(graph, _lib.ORDER_OUT, H, ee, keep, attn_mul) if staged else (None, 0, None)
             drec = torch.empty((H, N_d, 4), dtype=torch.float32, device=dev)
             gprime = torch.empty_like(gout) if dst_scale is not None else None
             grad_ft = torch.empty_like(ft)
