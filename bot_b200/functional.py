@@ -60,9 +60,11 @@ timer = None  # set to a KernelTimer to record
 #             in the staging pass); kept for graphs whose edge ids already follow the CSR order.
 edge_mode = "staged"
 
-# Stage the backward's (out-CSR-ordered) edge operands already during the forward, on a side stream: the staging
-# pass is DRAM-bound, the forward gather is L2-bound, so they overlap.  Costs one (Hb, E) buffer kept until backward.
-prestage_backward = True
+# Optionally stage the backward's (out-CSR-ordered) edge operands already during the forward, on a side stream (the
+# staging pass is DRAM-bound, the forward gather L2-bound).  Measured NEUTRAL on B200 (18.79 ms/step either way: the
+# forward kernel fills every SM, the side-stream blocks only trickle in) and it keeps one (Hb, E) buffer alive
+# until backward, so it is off by default.
+prestage_backward = False
 _side_streams = {}
 
 
@@ -177,11 +179,13 @@ class GATFusedFn(torch.autograd.Function):
 
         staged = edge_mode == "staged"
         with torch.cuda.device(ft.device):
+            eb_in, Hb, am_in = edge_stage(graph, _lib.ORDER_IN, H, ee, keep, attn_mul) if staged else (None, 0, None)
             pre = None
             has_edge_ops = ee is not None or keep is not None or attn_mul is not None
             if staged and prestage_backward and has_edge_ops and any(ctx.needs_input_grad):
+                # after the in-order staging (both are DRAM-bound), so that it runs beside the forward gather
                 main, side = torch.cuda.current_stream(), _side_stream(ft.device)
-                side.wait_stream(main)  # ee / keep / attn_mul are produced on the main stream
+                side.wait_stream(main)
                 with torch.cuda.stream(side):
                     eb_o, _, am_o = edge_stage(graph, _lib.ORDER_OUT, H, ee, keep, attn_mul)
                     ev = torch.cuda.Event()
@@ -190,7 +194,6 @@ class GATFusedFn(torch.autograd.Function):
                     if t is not None:
                         t.record_stream(side)
                 pre = (eb_o, am_o, ev)
-            eb_in, Hb, am_in = edge_stage(graph, _lib.ORDER_IN, H, ee, keep, attn_mul) if staged else (None, 0, None)
             out = torch.empty((N_d, H, D), dtype=torch.float32, device=ft.device)
             row_max = torch.empty((N_d, H), dtype=torch.float32, device=ft.device)
             row_sum = torch.empty((N_d, H), dtype=torch.float32, device=ft.device)
