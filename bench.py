@@ -234,8 +234,7 @@ def run_ours(args):
         if world == 1:
             out = gat_fused(graph, ft_own, el_own, er, ee, keep, None, None, None, SLOPE, 0.0, 0)
         else:
-            ft_all, el_all = layer.halo_gather(ft_own, el_own)
-            out = gat_fused(graph, ft_all, el_all, er, ee, keep, None, None, None, SLOPE, 0.0, 0)
+            out = layer.gat(ft_own, el_own, er, ee, keep, None, None, None, SLOPE, 0.0, 0)
         out.backward(gout)
         for t in (ft_own, el_own, er, ee):
             t.grad = None

@@ -155,7 +155,7 @@ class GATFusedFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, graph, ft, el, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed):
+    def forward(ctx, graph, ft, el, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed, hooks=None):
         lib = _lib.load()
         h = graph._ensure()
         if ft.dim() != 3:
@@ -216,11 +216,14 @@ class GATFusedFn(torch.autograd.Function):
             if graph._info.n_slots_in:  # heavy rows are split over several warps (segments.cu)
                 scratch = torch.empty(graph._info.n_slots_in * _r4(H * (D + 2)), dtype=torch.float32, device=ft.device)
                 a.scratch = scratch.data_ptr()
+            if hooks is not None and hooks.pre_kernel is not None:
+                hooks.pre_kernel()  # e.g. wait for an asynchronous halo all-gather that fills ft / el
             with _span("gat_fwd"):
                 rc = lib.botgat_gat_forward(h, C.byref(a), _stream())
             _lib.check(rc, "botgat_gat_forward")
 
         ctx.graph = graph
+        ctx.hooks = hooks
         ctx.pre = pre
         ctx.cfg = (H, D, staged, float(slope), float(a.attn_p), int(seed))
         ctx.save_for_backward(ft, el, er, ee, keep, attn_mul, src_scale, dst_scale, out, row_max, row_sum)
@@ -282,7 +285,14 @@ class GATFusedFn(torch.autograd.Function):
                 a.scratch = scratch.data_ptr()
             a.grad_ft, a.grad_el, a.grad_ee, a.grad_er = grad_ft.data_ptr(), grad_el.data_ptr(), p(grad_ee), p(grad_er)
             a.ld_gee = grad_ee.stride(0) if grad_ee is not None else 0
-            if timer is None:
+            post_src = ctx.hooks.post_src if ctx.hooks is not None else None
+            if timer is None and post_src is None:
+                _lib.check(lib.botgat_gat_backward(h, C.byref(a), _stream()), "botgat_gat_backward")
+            elif timer is None:
+                a.phases = 3
+                _lib.check(lib.botgat_gat_backward(h, C.byref(a), _stream()), "botgat_gat_backward")
+                post_src(grad_ft, grad_el)  # e.g. start the halo reduce-scatter while the edge phase runs
+                a.phases = 4
                 _lib.check(lib.botgat_gat_backward(h, C.byref(a), _stream()), "botgat_gat_backward")
             else:
                 for bit, name in ((1, "gat_bwd_node"), (2, "gat_bwd_src"), (4, "gat_bwd_edge")):
@@ -290,7 +300,10 @@ class GATFusedFn(torch.autograd.Function):
                     with _span(name):
                         rc = lib.botgat_gat_backward(h, C.byref(a), _stream())
                     _lib.check(rc, "botgat_gat_backward")
-        return None, grad_ft, grad_el, grad_er, (grad_ee if need_ee else None), None, None, None, None, None, None, None
+                    if bit == 2 and post_src is not None:
+                        post_src(grad_ft, grad_el)
+        return (None, grad_ft, grad_el, grad_er, (grad_ee if need_ee else None), None, None, None, None, None, None, None,
+                None)
 
 
 class EdgeLogitProj(torch.autograd.Function):
@@ -359,8 +372,17 @@ class Deferred:
         return self.tensor.requires_grad_(True) if self.requires_grad else self.tensor
 
 
+class Hooks:
+    """Optional call-backs of :class:`GATFusedFn` used by the partitioned layer to overlap its collectives:
+    ``pre_kernel()`` runs after edge staging, right before the forward gather kernel is launched;
+    ``post_src(grad_ft, grad_el)`` runs in backward after the src pass, before the edge phase."""
+
+    def __init__(self, pre_kernel=None, post_src=None):
+        self.pre_kernel, self.post_src = pre_kernel, post_src
+
+
 def gat_fused(graph, ft, el, er=None, ee=None, keep=None, attn_mul=None, src_scale=None, dst_scale=None,
-              slope=0.2, attn_p=0.0, seed=0):
+              slope=0.2, attn_p=0.0, seed=0, hooks=None):
     """Functional form of :class:`GATFusedFn` (accepts the reference's trailing-1 shapes, e.g. el (N,H,1))."""
     H = ft.shape[1]
     el = el.reshape(-1, H)
@@ -369,4 +391,4 @@ def gat_fused(graph, ft, el, er=None, ee=None, keep=None, attn_mul=None, src_sca
         ee = ee.reshape(ee.shape[0], -1)
     if attn_mul is not None and attn_mul.dim() == 3:
         attn_mul = attn_mul.reshape(attn_mul.shape[0], -1)
-    return GATFusedFn.apply(graph, ft, el, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed)
+    return GATFusedFn.apply(graph, ft, el, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed, hooks)

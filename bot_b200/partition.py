@@ -60,6 +60,37 @@ class _DenseHalo(torch.autograd.Function):
         return out, None
 
 
+class _DenseHaloAsync(torch.autograd.Function):
+    """`_DenseHalo` with the collectives started asynchronously so that the caller can put work between the start
+    and the first use: forward leaves the work handle in ``state.fwd[key]``; backward uses the reduce-scatter that
+    ``state.bwd[key]`` holds if the gradient hook already started one (``PartitionedGraph.gat``)."""
+
+    @staticmethod
+    def forward(ctx, shard, group, state, key):
+        ctx.group, ctx.state, ctx.key = group, state, key
+        world = dist.get_world_size(group)
+        out = shard.new_empty((world * shard.shape[0],) + tuple(shard.shape[1:]))
+        state.fwd[key] = dist.all_gather_into_tensor(out, shard.contiguous(), group=group, async_op=True)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        pre = ctx.state.bwd.pop(ctx.key, None)
+        if pre is not None:
+            work, out = pre
+            work.wait()
+            return out, None, None, None
+        world = dist.get_world_size(ctx.group)
+        out = grad.new_empty((grad.shape[0] // world,) + tuple(grad.shape[1:]))
+        dist.reduce_scatter_tensor(out, grad.contiguous(), op=dist.ReduceOp.SUM, group=ctx.group)
+        return out, None, None, None
+
+
+class _HaloState:
+    def __init__(self):
+        self.fwd, self.bwd = {}, {}
+
+
 class _SparseHalo(torch.autograd.Function):
     """all-to-all of the referenced rows; backward sends the halo gradients home and adds them."""
 
@@ -174,6 +205,36 @@ class PartitionedGraph:
             else:
                 outs.append(_SparseHalo.apply(t, self.send_idx, self.send_counts, self.recv_counts, self.group))
         return outs[0] if len(outs) == 1 else tuple(outs)
+
+    def gat(self, ft_own, el_own, er=None, ee=None, keep=None, attn_mul=None, src_scale=None, dst_scale=None,
+            slope=0.2, attn_p=0.0, seed=0):
+        """The partitioned layer in one call: halo exchange + ``gat_fused`` on the local block, with the collectives
+        overlapped with the work that does not depend on them (dense plan):
+          forward : all-gather of [ft], [el]  ||  edge staging            -> forward gather kernel
+          backward: node + src pass -> reduce-scatter of grad_ft, grad_el  ||  edge phase (grad_ee, grad_er)
+        ``src_scale`` is given for the LOCAL source numbering (``halo_gather`` a row-sharded one)."""
+        from .functional import Hooks, gat_fused
+
+        if self.world == 1 or self.plan != "dense":
+            ft_all, el_all = self.halo_gather(ft_own, el_own)
+            return gat_fused(self.local, ft_all, el_all, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed)
+        st = _HaloState()
+        ft_all = _DenseHaloAsync.apply(self._pad(ft_own), self.group, st, "ft")
+        el_all = _DenseHaloAsync.apply(self._pad(el_own), self.group, st, "el")
+
+        def pre_kernel():
+            st.fwd.pop("ft").wait()
+            st.fwd.pop("el").wait()
+
+        def post_src(grad_ft, grad_el):
+            for key, g in (("ft", grad_ft), ("el", grad_el)):
+                out = g.new_empty((g.shape[0] // self.world,) + tuple(g.shape[1:]))
+                work = dist.reduce_scatter_tensor(out, g, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                st.bwd[key] = (work, out)
+
+        out = gat_fused(self.local, ft_all, el_all, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed,
+                        hooks=Hooks(pre_kernel, post_src))
+        return out
 
     def owned_slice(self, full_table):
         """Rows of a replicated (N, ...) table this rank owns."""

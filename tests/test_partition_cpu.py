@@ -105,6 +105,82 @@ def _worker(rank, world, port, plan, seed, ret):
         dist.destroy_process_group()
 
 
+def _fake_gat_fused(graph, ft, el, er=None, ee=None, keep=None, attn_mul=None, src_scale=None, dst_scale=None,
+                    slope=0.2, attn_p=0.0, seed=0, hooks=None):
+    """CPU stand-in for bot_b200.functional.gat_fused (oracle math) that honours the Hooks protocol, so that
+    PartitionedGraph.gat's overlap logic (async all-gather / early reduce-scatter) can run under gloo."""
+    lsrc, ldst, n_dst = graph
+
+    class Fn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, ft, el, er, ee):
+            hooks.pre_kernel()
+            with torch.enable_grad():
+                ins = [t.detach().requires_grad_(True) for t in (ft, el, er, ee)]
+                out = gat_ref.gat_sparse(lsrc, ldst, n_dst, *ins, keep, attn_mul, slope, src_scale, dst_scale)
+            ctx.ins, ctx.out = ins, out
+            return out.detach()
+
+        @staticmethod
+        def backward(ctx, g):
+            gft, gel, ger, gee = torch.autograd.grad(ctx.out, ctx.ins, g)
+            hooks.post_src(gft.contiguous(), gel.contiguous())
+            return gft, gel, ger, gee
+
+    return Fn.apply(ft, el, er, ee)
+
+
+def _worker_overlap(rank, world, port, seed, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import bot_b200.functional as F_
+        from bot_b200.partition import PartitionedGraph
+
+        n, src, dst = _graph(seed)
+        pg = PartitionedGraph(src, dst, n, plan="dense", build_graph=False)
+        pg.local = (pg.lsrc, pg.ldst, pg.n_own)
+        F_.gat_fused = _fake_gat_fused
+        H, D = 2, 4
+        g = torch.Generator().manual_seed(seed + 100)
+        ft = torch.randn(n, H, D, generator=g, dtype=torch.float64)
+        el = torch.randn(n, H, generator=g, dtype=torch.float64)
+        er = torch.randn(n, H, generator=g, dtype=torch.float64)
+        ee = torch.randn(src.numel(), H, generator=g, dtype=torch.float64)
+        gout = torch.randn(n, H, D, generator=g, dtype=torch.float64)
+        ft_o = pg.owned_slice(ft).clone().requires_grad_(True)
+        el_o = pg.owned_slice(el).clone().requires_grad_(True)
+        er_o = pg.owned_slice(er).clone().requires_grad_(True)
+        ee_l = pg.local_edges(ee).clone().requires_grad_(True)
+        out = pg.gat(ft_o, el_o, er_o, ee_l)
+        out.backward(pg.owned_slice(gout))
+        ftr, elr = ft.clone().requires_grad_(True), el.clone().requires_grad_(True)
+        err, eer = er.clone().requires_grad_(True), ee.clone().requires_grad_(True)
+        full = gat_ref.gat_sparse(src, dst, n, ftr, elr, err, eer)
+        full.backward(gout)
+        for got, want in ((out, full[pg.lo:pg.hi]), (ft_o.grad, ftr.grad[pg.lo:pg.hi]), (el_o.grad, elr.grad[pg.lo:pg.hi]),
+                          (er_o.grad, err.grad[pg.lo:pg.hi]), (ee_l.grad, eer.grad.index_select(0, pg.edge_gid))):
+            assert torch.allclose(got, want.detach(), rtol=1e-10, atol=1e-12)
+        ret[rank] = "ok"
+    except Exception as ex:
+        import traceback
+
+        ret[rank] = traceback.format_exc() + repr(ex)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_overlapped_layer_equals_single(world):
+    """PartitionedGraph.gat (collectives started asynchronously around the kernels) == single-process result."""
+    port = _free_port()
+    with mp.Manager() as m:
+        ret = m.dict()
+        mp.spawn(_worker_overlap, args=(world, port, 11, ret), nprocs=world, join=True)
+        assert all(ret.get(r) == "ok" for r in range(world)), dict(ret)
+
+
 @pytest.mark.parametrize("world,plan", [(2, "sparse"), (2, "dense"), (3, "sparse"), (3, "dense"), (2, "auto")])
 def test_partitioned_equals_single(world, plan):
     port = _free_port()
