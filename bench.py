@@ -303,6 +303,17 @@ def run_ours(args):
                                "achieved_GBs": round((bf + bb) / (ms_step * 1e-3) / 1e9, 1),
                                "frac": round((bf + bb) / (ms_step * 1e-3) / 1e9 / peak, 4)}}
 
+    # second roofline: the feature slabs are L2-resident by construction, so the gathers are
+    # bounded by L2 -> SM bandwidth, measured on this pool with tools/l2peak.cu (profiles/l2_peak.json)
+    l2path = os.path.join(ROOT, "profiles", "l2_peak.json")
+    if os.path.exists(l2path):
+        l2peak = float(json.load(open(l2path))["l2_read_gbs"])
+        roofline["l2"] = {"bound": "l2", "peak": l2peak, "unit": "GB/s", "peak_source": "profiles/l2_peak.json (measured)",
+                          "kernels": {n: {"achieved": kernels[n]["achieved_GBs"],
+                                          "frac": round(kernels[n]["achieved_GBs"] / l2peak, 4)} for n in alg if n in kernels}}
+    roofline["note"] = ("achieved = SURVEY 8d gather-model bytes / CUDA-event time; it exceeds the HBM peak because each "
+                        "(N x D) head slab stays L2-resident: `traffic` is the DRAM bytes ncu measured for the same launch")
+
     del ft_own, el_own, er, ee, gout
     torch.cuda.empty_cache()
 
