@@ -243,3 +243,36 @@ class PartitionedGraph:
     def local_edges(self, edge_table):
         """Rows of a replicated (E, ...) edge table that belong to the local edges, local edge order."""
         return edge_table.index_select(0, self.edge_gid)
+
+
+def partition_bounds_device(graph, n_parts):
+    """The same bounds from the device in-CSR of an ingested graph (``botgat_partition_1d``)."""
+    import ctypes as C
+
+    from . import _lib
+    from .graph import _stream
+
+    out = (C.c_int64 * (n_parts + 1))()
+    _lib.check(_lib.load().botgat_partition_1d(graph._ensure(), n_parts, out, _stream()), "botgat_partition_1d")
+    return torch.tensor(list(out), dtype=torch.int64)
+
+
+def partition_extract_device(graph, lo, hi):
+    """Local edge set of destination rows [lo, hi) from the device structure (``botgat_partition_extract``):
+    (global edge ids, global sources, local destinations), edge-id order."""
+    import ctypes as C
+
+    from . import _lib
+    from .graph import _stream
+
+    lib, h = _lib.load(), graph._ensure()
+    n = C.c_int64()
+    _lib.check(lib.botgat_partition_extract(h, lo, hi, None, None, None, C.byref(n), _stream()), "botgat_partition_extract")
+    dev = graph.device
+    eid = torch.empty(n.value, dtype=torch.int64, device=dev)
+    src = torch.empty_like(eid)
+    ldst = torch.empty_like(eid)
+    if n.value:
+        _lib.check(lib.botgat_partition_extract(h, lo, hi, _lib.ptr(eid), _lib.ptr(src), _lib.ptr(ldst), C.byref(n), _stream()),
+                   "botgat_partition_extract")
+    return eid, src, ldst

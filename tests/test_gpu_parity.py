@@ -283,3 +283,43 @@ def test_fused_philox_attention_dropout(cuda, H):
     assert rel_err(out, ref_out) <= FWD_TOL
     for k in ("ft", "el", "er", "ee"):
         assert rel_err(g[k], ref_g[k]) <= 1e-4, k
+
+
+@pytest.mark.parametrize("parts", [1, 2, 4, 8])
+def test_partition_abi_bit_exact(cuda, parts):
+    """botgat_partition_1d / botgat_partition_extract against the partition oracle (bit-exact)."""
+    import bot_b200
+    from bot_b200.partition import partition_bounds, partition_bounds_device, partition_extract_device
+
+    n, e = 700, 9000
+    src, dst = graph_ref.synthetic_coo(n, e, 12, power_law=0.7)
+    f = graph_ref.build_formats(src, dst, n, n)
+    ref_b = graph_ref.partition_bounds(f["in_indptr"], parts)
+    g = bot_b200.Graph(torch.from_numpy(src).to(cuda), torch.from_numpy(dst).to(cuda), n)
+    assert np.array_equal(partition_bounds_device(g, parts).numpy(), ref_b)
+    assert np.array_equal(partition_bounds(torch.from_numpy(dst).to(cuda), n, parts).cpu().numpy(), ref_b)
+    for r in range(parts):
+        loc = graph_ref.partition_local(src, dst, n, ref_b, r)
+        eid, s, ld = partition_extract_device(g, int(ref_b[r]), int(ref_b[r + 1]))
+        assert np.array_equal(eid.cpu().numpy(), loc["edge_gid"])
+        assert np.array_equal(s.cpu().numpy(), src[loc["edge_gid"]])
+        assert np.array_equal(ld.cpu().numpy(), loc["ldst"])
+
+
+def test_rows_gather_scatter_abi(cuda):
+    import ctypes as C
+
+    from bot_b200 import _lib
+    from bot_b200.graph import _stream
+
+    lib = _lib.load()
+    t = torch.randn(50, 12, device=cuda)
+    rows = torch.tensor([3, 7, 49, 0], device=cuda)
+    out = torch.empty(4, 10, device=cuda)
+    _lib.check(lib.botgat_rows_gather(_lib.ptr(t), 12, 10, _lib.ptr(rows), 4, _lib.ptr(out), _stream()), "rows_gather")
+    assert torch.equal(out, t[rows, :10])
+    before = t.clone()
+    _lib.check(lib.botgat_rows_scatter_add(_lib.ptr(t), 12, 10, _lib.ptr(rows), 4, _lib.ptr(out), _stream()), "rows_scatter_add")
+    exp = before.clone()
+    exp[rows, :10] += out
+    assert torch.equal(t, exp)
