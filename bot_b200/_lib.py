@@ -70,6 +70,14 @@ SIGNATURES = {
     "botgat_edge_stage": (C.c_int, [c_vp, C.c_int, C.c_int32, c_vp, C.c_int64, c_vp, c_vp, C.c_int64, c_vp, c_vp, c_vp]),
     "botgat_edge_unstage": (C.c_int, [c_vp, C.c_int, C.c_int32, c_vp, c_vp, C.c_int64, c_vp]),
     "botgat_edge_reduce_dst": (C.c_int, [c_vp, C.c_int32, c_vp, C.c_int64, c_vp, c_vp, c_vp]),
+    "botgat_edge_drop_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "botgat_edge_drop_draw": (C.c_int, [C.c_int64, C.c_int64, C.c_uint64, c_vp, c_vp, C.c_int, c_vp]),
+    "botgat_edge_mlp_supported": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
+    "botgat_edge_mlp_workspace_floats": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "botgat_edge_mlp_forward": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_vp, C.c_int64, c_vp, c_vp, c_vp, c_vp,
+                                          C.c_int64, C.c_int, c_vp]),
+    "botgat_edge_mlp_backward": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_vp, C.c_int64, c_vp, c_vp, c_vp, c_vp,
+                                           C.c_int64, c_vp, c_vp, c_vp, c_vp, C.c_int, c_vp]),
     "botgat_edge_proj_gw_blocks": (C.c_int, []),
     "botgat_edge_proj_forward": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, c_vp, C.c_int64, c_vp, c_vp, C.c_int64, C.c_int, c_vp]),
     "botgat_edge_proj_backward": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, c_vp, C.c_int64, c_vp, c_vp, C.c_int64, c_vp,

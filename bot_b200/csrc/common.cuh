@@ -44,6 +44,18 @@ struct DeviceGuard {
   }
 };
 
+// Grid of a grid-stride streaming kernel: whole waves of resident blocks (occupancy x SM count), never more
+// blocks than there is work for.  A partial last wave costs a full wave's time on these bandwidth-bound loops.
+template <typename K>
+static inline int resident_grid(K kernel, int block_threads, int64_t blocks_of_work) {
+  int dev = 0, sms = 148, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block_threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int64_t resident = (int64_t)sms * per_sm;
+  return (int)(blocks_of_work < 1 ? 1 : (blocks_of_work < resident ? blocks_of_work : resident));
+}
+
 }  // namespace botgat
 
 // The opaque graph handle.  Immutable after create.

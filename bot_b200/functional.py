@@ -8,6 +8,7 @@ degree scaling) and, in backward, the autograd replay of their adjoints.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -355,6 +356,85 @@ def edge_logits(feat_edge, weight):
     pad = pad_heads(H) - H
     w = torch.cat([weight, weight.new_zeros(pad, Cin)], 0) if pad > 0 else weight
     return torch.nn.functional.linear(feat_edge, w)
+
+
+def edge_drop_keep(n_edges, n_drop, seed, device):
+    """uint8 keep mask with exactly ``n_drop`` zeros at uniformly random positions (``botgat_edge_drop_draw``)."""
+    lib = _lib.load()
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("bot_b200.edge_drop_keep: no CPU path")
+    keep = torch.empty(n_edges, dtype=torch.uint8, device=device)
+    ws = torch.empty(lib.botgat_edge_drop_workspace_bytes(n_edges), dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        with _span("edge_drop_draw"):
+            rc = lib.botgat_edge_drop_draw(n_edges, n_drop, seed, keep.data_ptr(), ws.data_ptr(), device.index
+                                           if device.index is not None else torch.cuda.current_device(), _stream())
+    _lib.check(rc, "botgat_edge_drop_draw")
+    return keep
+
+
+class EdgeMLPLogits(torch.autograd.Function):
+    """``ee = relu(efeat @ W1^T + b1) @ W2^T`` in one pass per direction (``botgat_edge_mlp_*``): the model's per-layer
+    ``edge_encoder[i]`` + ReLU (src/ogbn-proteins/models.py:245-247) fused with the layer's ``attn_edge_fc``
+    (models.py:131).  The (E, edge_emb) embedding is never materialised; backward recomputes the hidden units."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2):
+        lib = _lib.load()
+        x, w1, w2 = _f32c(x, "efeat"), _f32c(w1, "edge_encoder.weight"), _f32c(w2, "attn_edge_fc.weight")
+        b1 = None if b1 is None else _f32c(b1, "edge_encoder.bias")
+        E, Cin = x.shape
+        M, H = w1.shape[0], w2.shape[0]
+        y = torch.empty((E, pad_heads(H)), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            with _span("edge_mlp_fwd"):
+                rc = lib.botgat_edge_mlp_forward(E, Cin, M, H, x.data_ptr(), x.stride(0), w1.data_ptr(), _lib.ptr(b1),
+                                                 w2.data_ptr(), y.data_ptr(), y.stride(0), x.device.index, _stream())
+        _lib.check(rc, "botgat_edge_mlp_forward")
+        ctx.save_for_backward(x, w1, b1, w2)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        x, w1, b1, w2 = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise RuntimeError("EdgeMLPLogits: raw edge features get no gradient (use edge_logits on the embedding instead)")
+        E, Cin = x.shape
+        M, H = w1.shape[0], w2.shape[0]
+        gy, ld_gy = _rows(gy, "grad_ee", H)
+        gw1 = torch.empty_like(w1) if ctx.needs_input_grad[1] else None
+        gb1 = torch.empty_like(b1) if b1 is not None and ctx.needs_input_grad[2] else None
+        gw2 = torch.empty_like(w2) if ctx.needs_input_grad[3] else None
+        ws = torch.empty(lib.botgat_edge_mlp_workspace_floats(Cin, M, H), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            with _span("edge_mlp_bwd"):
+                rc = lib.botgat_edge_mlp_backward(E, Cin, M, H, x.data_ptr(), x.stride(0), w1.data_ptr(), _lib.ptr(b1),
+                                                  w2.data_ptr(), gy.data_ptr(), ld_gy, _lib.ptr(gw1), _lib.ptr(gb1),
+                                                  _lib.ptr(gw2), ws.data_ptr(), x.device.index, _stream())
+        _lib.check(rc, "botgat_edge_mlp_backward")
+        return None, gw1, gb1, gw2
+
+
+class EdgeEmbedding:
+    """``relu(encoder(efeat))`` not yet computed.  The model wrappers pass it to ``GATConv.forward`` as ``feat_edge``;
+    the layer turns it into its logits with one fused kernel (:class:`EdgeMLPLogits`) when the shapes allow
+    (C <= 8 raw features, edge_emb <= 16, H <= 8 and ``efeat`` not requiring grad), else materialises it."""
+
+    def __init__(self, efeat, encoder):
+        self.efeat, self.encoder = efeat, encoder
+
+    def materialize(self):
+        return torch.relu(self.encoder(self.efeat))
+
+    def logits(self, attn_edge_fc_weight):
+        x, enc = self.efeat, self.encoder
+        H = attn_edge_fc_weight.shape[0]
+        if (x.dim() == 2 and x.is_cuda and not x.requires_grad and os.environ.get("BOTGAT_NO_EDGE_MLP", "0") != "1"
+                and _lib.load().botgat_edge_mlp_supported(x.shape[1], enc.weight.shape[0], H)):
+            return EdgeMLPLogits.apply(x, enc.weight, enc.bias, attn_edge_fc_weight)
+        return edge_logits(self.materialize(), attn_edge_fc_weight)
 
 
 class Deferred:

@@ -18,14 +18,43 @@ import torch.nn as nn
 from .functional import gat_fused
 
 
+edge_drop_mode = "select"   # "randperm": torch.randperm exactly as the reference calls it (replays its generator)
+
+
+class KeptEdges:
+    """The kept edge ids (ascending) of a keep mask whose population is known — materialised only when the
+    exact attention-dropout replay asks for them (``torch.nonzero_static``: no host sync)."""
+
+    def __init__(self, keep, count):
+        self.keep, self.count, self._ids = keep, count, None
+
+    def numel(self):
+        return self.count
+
+    def ids(self):
+        if self._ids is None:
+            self._ids = torch.nonzero_static(self.keep, size=self.count).flatten()
+        return self._ids
+
+
 def draw_edge_keep(n_edges, edge_drop, device):
-    """Edge-drop keep set exactly as the reference draws it (models.py:529-532):
-    ``perm = randperm(E); eids = perm[int(E*p):]`` kept, the rest dropped."""
-    perm = torch.randperm(n_edges, device=device)
+    """Edge-drop keep set with the reference's semantics (models.py:529-532): ``perm = randperm(E)``,
+    ``perm[:int(E*p)]`` dropped, ``eids = perm[int(E*p):]`` kept — a uniformly random subset of exactly
+    ``int(E*p)`` edges is dropped.  On CUDA the subset is drawn by ``botgat_edge_drop_draw`` (a selection on Philox
+    keys seeded from torch's generator) instead of a sort of E keys; ``edge_drop_mode = "randperm"`` keeps the
+    literal torch call.  Returns ``(keep uint8 (E,), kept ids)``."""
     bound = int(n_edges * edge_drop)
-    keep = torch.ones(n_edges, dtype=torch.uint8, device=device)
-    keep[perm[:bound]] = 0
-    return keep, perm[bound:]
+    device = torch.device(device)
+    if edge_drop_mode == "randperm" or device.type != "cuda":
+        perm = torch.randperm(n_edges, device=device)
+        keep = torch.ones(n_edges, dtype=torch.uint8, device=device)
+        keep[perm[:bound]] = 0
+        return keep, perm[bound:]
+    from .functional import edge_drop_keep
+
+    seed = int(torch.randint(0, 2**62, (1,)).item())
+    keep = edge_drop_keep(n_edges, bound, seed, device)
+    return keep, KeptEdges(keep, n_edges - bound)
 
 
 def draw_attn_mul(attn_drop_module, n_edges, n_heads, device, eids=None):
@@ -37,7 +66,7 @@ def draw_attn_mul(attn_drop_module, n_edges, n_heads, device, eids=None):
     if eids is None:
         return mul.view(n_edges, n_heads)
     full = torch.zeros((n_edges, n_heads), dtype=torch.float32, device=device)
-    full[eids] = mul.view(rows, n_heads)
+    full[eids.ids() if isinstance(eids, KeptEdges) else eids] = mul.view(rows, n_heads)
     return full
 
 

@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .functional import Deferred, edge_logits, gat_fused
+from .functional import Deferred, EdgeEmbedding, edge_logits, gat_fused
 from .no_sampling import draw_attn_mul, draw_edge_keep
 
 
@@ -72,6 +72,8 @@ class GATConv(nn.Module):
             if not self._allow_zero_in_degree and graph.has_zero_in_degree:   # models.py:89-91
                 assert False
             n_dst = graph.number_of_dst_nodes()
+            if isinstance(feat_src, Deferred):    # prefetched by bot_b200.HostFeed
+                feat_src = feat_src.wait()
             feat_dst = feat_src[:n_dst] if graph.is_block else feat_src       # models.py:93-96
 
             dst_scale = None
@@ -102,7 +104,10 @@ class GATConv(nn.Module):
                     feat_edge = feat_edge.wait()
                 # the same Linear as a streaming kernel, emitted as one aligned 32-byte record per edge
                 # (functional.pad_heads); padding columns are ignored by the kernels and get zero gradient
-                ee = edge_logits(feat_edge, self.attn_edge_fc.weight)          # (E, pad_heads(H))
+                if isinstance(feat_edge, EdgeEmbedding):   # encoder + ReLU + this Linear in one kernel
+                    ee = feat_edge.logits(self.attn_edge_fc.weight)
+                else:
+                    ee = edge_logits(feat_edge, self.attn_edge_fc.weight)      # (E, pad_heads(H))
 
             rst = gat_fused(graph, ft, el, er, ee, keep, attn_mul, None, dst_scale,
                             self._negative_slope, attn_p, seed)                # models.py:125-156
@@ -134,7 +139,8 @@ class _SampledGAT(nn.Module):
         for i in range(self.n_layers):
             efeat_emb = None
             if self.edge_encoder is not None:
-                efeat_emb = F.relu(self.edge_encoder[i](subgraphs[i].edata["feat"]))
+                # relu(edge_encoder[i](efeat)) (models.py:245-247), left to the layer to fuse with attn_edge_fc
+                efeat_emb = EdgeEmbedding(subgraphs[i].edata["feat"], self.edge_encoder[i])
             h = self.convs[i](subgraphs[i], h, efeat_emb).flatten(1, -1)
             if h_last is not None and (always_residual or self.residual):
                 h = h + h_last[: h.shape[0], :]

@@ -151,6 +151,36 @@ int botgat_edge_proj_backward(int64_t n, int32_t C, int32_t H, const float* x, i
                               float* gW /* or NULL */, float* partials, int device, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Edge-drop keep mask: keep[e] = 0 for a uniformly random subset of exactly n_drop edges, 1 elsewhere —
+ * the set `perm[:bound]` of `perm = torch.randperm(E); bound = int(E * edge_drop)`
+ * (src/no-sampling/models.py:528-532, src/ogbn-proteins/models.py:136-139) drawn as a selection on 64-bit
+ * Philox4x32-10 keys instead of a sort of E keys.  Deterministic in (n_edges, n_drop, seed).
+ * `workspace`: botgat_edge_drop_workspace_bytes(n_edges) bytes, 256-byte aligned.
+ * ---------------------------------------------------------------------- */
+int64_t botgat_edge_drop_workspace_bytes(int64_t n_edges);
+int botgat_edge_drop_draw(int64_t n_edges, int64_t n_drop, uint64_t seed, uint8_t* keep, void* workspace,
+                          int device, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Fused per-edge encoder + logit projection  y[k, 0:H] = relu(x[k, 0:C] @ W1^T + b1) @ W2^T
+ * (W1 row-major (M, C), b1 (M) or NULL, W2 row-major (H, M); C <= 8, M <= 16, H <= 8 —
+ * botgat_edge_mlp_supported()).  Replaces, for one layer, `F.relu(edge_encoder[i](efeat))`
+ * (src/ogbn-proteins/models.py:245-247) followed by `attn_edge_fc(feat_edge)` (models.py:131) and the
+ * autograd backward of both: the (E, M) embedding is never materialised (the reference keeps one per
+ * layer for backward).  Output rows as botgat_edge_proj_forward.  Backward recomputes the hidden units and
+ * produces gW1 (M, C), gb1 (M), gW2 (H, M) (each may be NULL); x gets no gradient (raw edge features are data).
+ * `partials`: botgat_edge_mlp_workspace_floats(C, M, H) floats (fixed-order reduction, no atomics).
+ * ---------------------------------------------------------------------- */
+int botgat_edge_mlp_supported(int32_t C, int32_t M, int32_t H);
+int64_t botgat_edge_mlp_workspace_floats(int32_t C, int32_t M, int32_t H);
+int botgat_edge_mlp_forward(int64_t n, int32_t C, int32_t M, int32_t H, const float* x, int64_t ld_x,
+                            const float* W1, const float* b1, const float* W2, float* y, int64_t ld_y,
+                            int device, void* stream);
+int botgat_edge_mlp_backward(int64_t n, int32_t C, int32_t M, int32_t H, const float* x, int64_t ld_x,
+                             const float* W1, const float* b1, const float* W2, const float* gy, int64_t ld_gy,
+                             float* gW1, float* gb1, float* gW2, float* partials, int device, void* stream);
+
+/* ------------------------------------------------------------------------
  * Fused forward: logits -> leaky_relu -> online edge-softmax -> attention
  * dropout -> u_mul_e/sum SpMM -> degree scaling, one pass over the in-CSR.
  * Replaces src/no-sampling/models.py:500-505,523-555 and

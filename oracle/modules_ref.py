@@ -70,3 +70,10 @@ def gatconv_v2(sd, src, dst, n_src, n_dst, feat_src, feat_edge=None, *, n_heads,
     ee = F.linear(feat_edge, sd["attn_edge_fc.weight"]) if feat_edge is not None else None      # :130-131
     rst = gat_ref.gat_sparse(src, dst, n_dst, ft, el, er, ee, keep, attn_mul, negative_slope, None, dst_scale)
     return rst + resid                                                        # :159-160
+
+
+def edge_mlp_logits(efeat, w1, b1, w2):
+    """Per-layer edge term of the proteins model, caller + layer side in one expression:
+    ``efeat_emb = relu(edge_encoder[i](efeat))`` (src/ogbn-proteins/models.py:245-247) then
+    ``attn_edge_fc(efeat_emb)`` (models.py:131).  (E, C) -> (E, H)."""
+    return F.linear(F.relu(F.linear(efeat, w1, b1)), w2)

@@ -215,7 +215,8 @@ def test_row_splitting_all_dropped_segment(cuda, monkeypatch):
     check_case(c, cuda)
 
 
-@pytest.mark.parametrize("E,C,H", [(0, 16, 6), (1000, 16, 6), (5000, 8, 4), (777, 5, 3), (3000, 64, 4), (2000, 16, 8), (100, 12, 1)])
+@pytest.mark.parametrize("E,C,H", [(0, 16, 6), (1000, 16, 6), (5000, 8, 4), (777, 5, 3), (3000, 64, 4), (2000, 16, 8), (100, 12, 1),
+                                   (700001, 16, 6), (40003, 48, 6), (5001, 32, 8), (9000, 20, 5)])
 def test_edge_logit_projection(cuda, E, C, H):
     """Streaming attn_edge_fc kernels (botgat_edge_proj_*) against torch's Linear, forward and backward."""
     from bot_b200.functional import edge_logits, pad_heads
@@ -264,6 +265,150 @@ def test_deferred_edge_features(cuda):
     y1 = conv(g, x, bot_b200.Deferred(fe, ev))
     torch.cuda.synchronize()
     assert torch.equal(y0, y1)
+
+
+@pytest.mark.parametrize("E,C,M,H", [(0, 8, 16, 6), (1000, 8, 16, 6), (5003, 8, 16, 8), (777, 5, 13, 3), (4000, 4, 16, 1),
+                                     (3000, 3, 7, 2), (600011, 8, 16, 6)])
+def test_edge_mlp_logits(cuda, E, C, M, H):
+    """Fused edge encoder + ReLU + attn_edge_fc (botgat_edge_mlp_*) against the oracle restatement in fp64."""
+    from bot_b200.functional import EdgeMLPLogits, pad_heads
+    from oracle.modules_ref import edge_mlp_logits
+
+    g = torch.Generator().manual_seed(E + C + M + H)
+    x = torch.randn(E, C, generator=g)
+    w1, b1, w2 = torch.randn(M, C, generator=g), torch.randn(M, generator=g), torch.randn(H, M, generator=g)
+    gy = torch.randn(E, pad_heads(H), generator=g)
+    ref_in = [t.double().requires_grad_(True) for t in (w1, b1, w2)]
+    ref = edge_mlp_logits(x.double(), *ref_in)
+    ref.backward(gy[:, :H].double())
+    dev = [t.to(cuda).requires_grad_(True) for t in (w1, b1, w2)]
+    y = EdgeMLPLogits.apply(x.to(cuda), *dev)
+    assert y.shape == (E, pad_heads(H))
+    y.backward(gy.to(cuda))
+    if E:
+        assert rel_err(y[:, :H], ref) <= 1e-6
+        if pad_heads(H) > H:
+            assert float(y[:, H:].abs().max()) == 0.0
+        for got, want in zip(dev, ref_in):
+            assert rel_err(got.grad, want.grad) <= 1e-5
+    else:
+        assert all(float(t.grad.abs().max()) == 0.0 for t in dev)
+    dev2 = [t.detach().clone().requires_grad_(True) for t in dev]   # deterministic reduction
+    EdgeMLPLogits.apply(x.to(cuda), *dev2).backward(gy.to(cuda))
+    assert all(torch.equal(a.grad, b.grad) for a, b in zip(dev, dev2))
+
+
+def test_edge_embedding_fused_equals_materialised(cuda):
+    """GATConv given a lazy EdgeEmbedding (fused kernel) == given relu(encoder(efeat)) (the reference's data flow)."""
+    import bot_b200
+    from bot_b200.ogbn_proteins import GATConv
+
+    torch.manual_seed(0)
+    n, e = 300, 8000
+    g = bot_b200.Graph(torch.randint(0, n, (e,), device=cuda), torch.randint(0, n, (e,), device=cuda), n)
+    conv = GATConv(32, 16, 8, n_heads=6).to(cuda).eval()
+    enc = torch.nn.Linear(8, 16).to(cuda)
+    x = torch.randn(n, 32, device=cuda)
+    efeat = torch.randn(e, 8, device=cuda)
+    y0 = conv(g, x, torch.relu(enc(efeat)))
+    y0.square().sum().backward()
+    g0 = [p.grad.clone() for p in list(enc.parameters()) + [conv.attn_edge_fc.weight]]
+    enc.zero_grad(), conv.zero_grad()
+    y1 = conv(g, x, bot_b200.EdgeEmbedding(efeat, enc))
+    y1.square().sum().backward()
+    g1 = [p.grad for p in list(enc.parameters()) + [conv.attn_edge_fc.weight]]
+    assert rel_err(y1, y0) <= FWD_TOL
+    for a, b in zip(g1, g0):
+        assert rel_err(a, b) <= 1e-4
+    # unsupported width (edge_emb 32): falls back to the materialised embedding
+    conv2 = GATConv(32, 32, 8, n_heads=6).to(cuda).eval()
+    enc2 = torch.nn.Linear(8, 32).to(cuda)
+    assert rel_err(conv2(g, x, bot_b200.EdgeEmbedding(efeat, enc2)), conv2(g, x, torch.relu(enc2(efeat)))) <= FWD_TOL
+
+
+@pytest.mark.parametrize("E,n_drop,seed", [(1, 0, 1), (1, 1, 2), (2, 1, 3), (1001, 370, 4), (100000, 10000, 5),
+                                           (3000001, 300000, 6), (50000, 49999, 7), (50000, 1, (1 << 61) + 12345)])
+def test_edge_drop_draw_exact(cuda, E, n_drop, seed):
+    """botgat_edge_drop_draw: exactly n_drop zeros, bit-identical to 'drop the n_drop smallest Philox keys'."""
+    from bot_b200.functional import edge_drop_keep
+    from util import philox_edge_drop_keep
+
+    keep = edge_drop_keep(E, n_drop, seed, cuda)
+    assert keep.dtype == torch.uint8 and keep.shape == (E,)
+    assert int(keep.sum()) == E - n_drop
+    assert torch.equal(keep.cpu(), philox_edge_drop_keep(seed, E, n_drop))
+    assert torch.equal(keep, edge_drop_keep(E, n_drop, seed, cuda))
+
+
+def test_edge_drop_draw_is_uniform(cuda):
+    """Every edge is dropped with probability n_drop / E (the reference's randperm prefix): 400 draws on 2000 edges."""
+    from bot_b200.functional import edge_drop_keep
+
+    E, n_drop, draws = 2000, 600, 400
+    freq = torch.zeros(E, device=cuda)
+    for s in range(draws):
+        freq += (edge_drop_keep(E, n_drop, 1000 + s, cuda) == 0).float()
+    p = n_drop / E
+    sd = (p * (1 - p) / draws) ** 0.5
+    assert abs(float(freq.mean()) / draws - p) < 1e-9 + 1e-6           # exact count in every draw
+    assert float((freq / draws - p).abs().max()) < 5.5 * sd            # no position favoured
+    z = (freq / draws - p) / sd
+    assert abs(float(z.std()) - 1.0) < 0.1
+
+
+def test_module_edge_drop_uses_selection(cuda):
+    """GATConv in training mode: the drawn mask has exactly int(E * p) zeros and follows torch's seed."""
+    from bot_b200 import no_sampling
+
+    torch.manual_seed(3)
+    k1, ids1 = no_sampling.draw_edge_keep(10000, 0.37, cuda)
+    torch.manual_seed(3)
+    k2, _ = no_sampling.draw_edge_keep(10000, 0.37, cuda)
+    k3, _ = no_sampling.draw_edge_keep(10000, 0.37, cuda)
+    assert int(k1.sum()) == 10000 - 3700 and torch.equal(k1, k2) and not torch.equal(k1, k3)
+    assert ids1.numel() == 6300 and torch.equal(ids1.ids(), torch.nonzero(k1).flatten())
+
+
+def test_host_feed_pipeline(cuda):
+    """bot_b200.HostFeed: steps prefetched one ahead through two device buffer sets give the values and
+    gradients of the same steps fed serially."""
+    import bot_b200
+    from bot_b200.ogbn_proteins import GATConv
+
+    torch.manual_seed(0)
+    n, e, steps = 300, 8000, 5
+    src = torch.randint(0, n, (e,), device=cuda)
+    dst = torch.randint(0, n, (e,), device=cuda)
+    g = bot_b200.Graph(src, dst, n)
+    conv = GATConv(32, 16, 8, n_heads=6).to(cuda).eval()
+    xs = [torch.randn(n, 32).pin_memory() for _ in range(steps)]
+    fes = [torch.randn(e, 16).pin_memory() for _ in range(steps)]
+
+    def run(x, fe):
+        y = conv(g, x, fe)
+        y.square().sum().backward()
+        return y.detach().clone()
+
+    want = []
+    for x, fe in zip(xs, fes):
+        xd, fd = x.to(cuda).requires_grad_(True), fe.to(cuda).requires_grad_(True)
+        want.append((run(xd, fd), xd.grad.clone(), fd.grad.clone()))
+
+    feed = bot_b200.HostFeed(cuda, depth=2)
+    feed.submit(xs[0], fes[0])
+    with pytest.raises(RuntimeError):
+        feed.submit(xs[0], fes[0]), feed.submit(xs[0], fes[0])
+    feed = bot_b200.HostFeed(cuda, depth=2)
+    feed.submit(xs[0], fes[0])
+    for i in range(steps):
+        if i + 1 < steps:
+            feed.submit(xs[i + 1], fes[i + 1])
+        x, fe = feed.take(requires_grad=(0, 1))
+        y = run(x, fe)
+        gx, gfe = x.tensor.grad, fe.tensor.grad
+        assert torch.equal(y, want[i][0]) and torch.equal(gx, want[i][1]) and torch.equal(gfe, want[i][2])
+    with pytest.raises(RuntimeError):
+        feed.take()
 
 
 @pytest.mark.parametrize("H", [1, 3, 6])

@@ -138,3 +138,33 @@ def philox_attn_mul(seed, n_edges, n_heads, p):
         u = (x >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
         out[:, h] = np.where(u >= np.float32(p), np.float32(1.0 / (1.0 - p)), np.float32(0.0))
     return torch.from_numpy(out)
+
+
+def philox_edge_drop_keep(seed, n_edges, n_drop):
+    """numpy restatement of `botgat_edge_drop_draw` (bot_b200/csrc/edge_drop.cu): 64-bit Philox4x32-10 keys, counter
+    (pair, 0x80000000 | pair >> 32, 0x9E3779B9, 0xBB67AE85) for the edges (2*pair, 2*pair+1) = words (0,1) / (2,3);
+    the n_drop smallest keys are dropped."""
+    import numpy as np
+
+    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), 0x9E3779B9, 0xBB67AE85
+    n_pairs = (n_edges + 1) // 2
+    pair = np.arange(n_pairs, dtype=np.uint64)
+    c0 = pair.astype(np.uint32)
+    c1 = (np.uint32(0x80000000) | (pair >> np.uint64(32)).astype(np.uint32))
+    c2 = np.full(n_pairs, W0, dtype=np.uint32)
+    c3 = np.full(n_pairs, W1, dtype=np.uint32)
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    for _ in range(10):
+        p0 = M0 * c0.astype(np.uint64)
+        p1 = M1 * c2.astype(np.uint64)
+        hi0, lo0 = (p0 >> np.uint64(32)).astype(np.uint32), p0.astype(np.uint32)
+        hi1, lo1 = (p1 >> np.uint64(32)).astype(np.uint32), p1.astype(np.uint32)
+        c0, c1, c2, c3 = hi1 ^ c1 ^ np.uint32(k0), lo1, hi0 ^ c3 ^ np.uint32(k1), lo0
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    keys = np.empty(2 * n_pairs, dtype=np.uint64)
+    keys[0::2] = (c0.astype(np.uint64) << np.uint64(32)) | c1.astype(np.uint64)
+    keys[1::2] = (c2.astype(np.uint64) << np.uint64(32)) | c3.astype(np.uint64)
+    keys = keys[:n_edges]
+    keep = np.ones(n_edges, dtype=np.uint8)
+    keep[np.argsort(keys, kind="stable")[:n_drop]] = 0
+    return torch.from_numpy(keep)
