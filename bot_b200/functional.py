@@ -139,6 +139,145 @@ def edge_stage(graph: Graph, order, H, ee=None, keep=None, attn_mul=None):
     return eb, Hb, am
 
 
+def _check_edge_operands(graph, H, ee, keep, attn_mul):
+    E = graph.number_of_edges()
+    ee, ld_ee = _rows(ee, "ee", H)
+    attn_mul, ld_am = _rows(attn_mul, "attn_mul", H)
+    if ee is not None and ee.shape[0] != E:
+        raise ValueError("ee must have one row per edge")
+    if keep is not None:
+        keep = keep.to(torch.uint8).contiguous()
+        if keep.numel() != E:
+            raise ValueError("keep must have one entry per edge")
+    return ee, ld_ee, keep, attn_mul, ld_am
+
+
+def _forward_core(graph, ft2d, H, D, el, er, ee, ld_ee, keep, attn_mul, ld_am, src_scale, dst_scale, slope, attn_p, seed,
+                  hooks, will_backward):
+    """Edge staging + the fused forward kernel.  ``ft2d``: 2-D tensor whose first H*D columns are the projected source
+    features (any 16-byte-aligned row stride: a column slice of a wider GEMM output works).  Returns
+    (out (N_d,H,D), row_max, row_sum, prestaged backward operands | None, attn_p actually used)."""
+    lib = _lib.load()
+    h = graph._ensure()
+    dev = ft2d.device
+    N_d = graph.number_of_dst_nodes()
+    staged = edge_mode == "staged"
+    eb_in, Hb, am_in = edge_stage(graph, _lib.ORDER_IN, H, ee, keep, attn_mul) if staged else (None, 0, None)
+    pre = None
+    has_edge_ops = ee is not None or keep is not None or attn_mul is not None
+    if staged and prestage_backward and has_edge_ops and will_backward:
+        # after the in-order staging (both are DRAM-bound), so that it runs beside the forward gather
+        main, side = torch.cuda.current_stream(), _side_stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            eb_o, _, am_o = edge_stage(graph, _lib.ORDER_OUT, H, ee, keep, attn_mul)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        for t in (ee, keep, attn_mul):
+            if t is not None:
+                t.record_stream(side)
+        pre = (eb_o, am_o, ev)
+    out = torch.empty((N_d, H, D), dtype=torch.float32, device=dev)
+    row_max = torch.empty((N_d, H), dtype=torch.float32, device=dev)
+    row_sum = torch.empty((N_d, H), dtype=torch.float32, device=dev)
+    a = _lib.FwdArgs()
+    a.H, a.D, a.ld_ft, a.ld_out = H, D, ft2d.stride(0), H * D
+    a.ft, a.el, a.er = ft2d.data_ptr(), el.data_ptr(), (er.data_ptr() if er is not None else None)
+    a.eb, a.Hb, a.col_parts = (eb_in.data_ptr() if eb_in is not None else None), Hb, 0
+    a.am = am_in.data_ptr() if am_in is not None else None
+    if not staged:
+        if (ee is not None and ld_ee != H) or (attn_mul is not None and ld_am != H):
+            raise ValueError("direct edge mode needs unpadded (E,H) edge operands")
+        a.ee = ee.data_ptr() if ee is not None else None
+        a.keep = keep.data_ptr() if keep is not None else None
+        a.attn_mul = attn_mul.data_ptr() if attn_mul is not None else None
+    a.src_scale = src_scale.data_ptr() if src_scale is not None else None
+    a.dst_scale = dst_scale.data_ptr() if dst_scale is not None else None
+    a.slope, a.attn_p, a.seed = float(slope), float(attn_p if attn_mul is None else 0.0), int(seed)
+    a.out, a.row_max, a.row_sum = out.data_ptr(), row_max.data_ptr(), row_sum.data_ptr()
+    scratch = None
+    if graph._info.n_slots_in:  # heavy rows are split over several warps (segments.cu)
+        scratch = torch.empty(graph._info.n_slots_in * _r4(H * (D + 2)), dtype=torch.float32, device=dev)
+        a.scratch = scratch.data_ptr()
+    if hooks is not None and hooks.pre_kernel is not None:
+        hooks.pre_kernel()  # e.g. wait for an asynchronous halo all-gather that fills ft / el
+    with _span("gat_fwd"):
+        rc = lib.botgat_gat_forward(h, C.byref(a), _stream())
+    _lib.check(rc, "botgat_gat_forward")
+    return out, row_max, row_sum, pre, float(a.attn_p)
+
+
+def _backward_core(graph, cfg, pre, hooks, ft2d, el, er, ee, keep, attn_mul, src_scale, dst_scale, out, row_max, row_sum,
+                   gout, grad_ft2d, need_er, need_ee):
+    """The three backward phases.  ``grad_ft2d``: 2-D tensor whose first H*D columns receive grad_ft (any aligned row
+    stride).  Returns (grad_el (N_s,H), grad_er | None, grad_ee | None)."""
+    lib = _lib.load()
+    h = graph._ensure()
+    H, D, staged, slope, attn_p, seed = cfg
+    N_s, N_d, E = ft2d.shape[0], out.shape[0], graph.number_of_edges()
+    dev = ft2d.device
+
+    def p(t):
+        return t.data_ptr() if t is not None else None
+
+    if pre is not None:  # staged during the forward on the side stream
+        eb_out, am_out, ev = pre
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        for t in (eb_out, am_out):
+            if t is not None:
+                t.record_stream(cur)
+        Hb = eb_out.shape[0] if eb_out is not None else 0
+    else:
+        eb_out, Hb, am_out = edge_stage(graph, _lib.ORDER_OUT, H, ee, keep, attn_mul) if staged else (None, 0, None)
+    drec = torch.empty((H, N_d, 4), dtype=torch.float32, device=dev)
+    gprime = torch.empty_like(gout) if dst_scale is not None else None
+    grad_el = torch.empty((N_s, H), dtype=torch.float32, device=dev)
+    grad_er = torch.empty((N_d, H), dtype=torch.float32, device=dev) if need_er else None
+    # gz (out-CSR order) -> grad_ee (edge-id order); grad_er is reduced from grad_ee
+    gz = grad_ee = None
+    if need_er or need_ee:
+        gz = torch.empty((H, E), dtype=torch.float32, device=dev) if staged else None
+        # same row width as the ee that came in (padding columns receive zeros)
+        Hp = ee.shape[1] if (ee is not None and staged) else (pad_heads(H) if staged else H)
+        grad_ee = torch.empty((E, Hp), dtype=torch.float32, device=dev)
+    a = _lib.BwdArgs()
+    a.H, a.D, a.ld_ft, a.ld_out, a.ld_gft = H, D, ft2d.stride(0), H * D, grad_ft2d.stride(0)
+    a.ft, a.el, a.er = ft2d.data_ptr(), el.data_ptr(), p(er)
+    a.eb_out, a.Hb, a.phases, a.am_out = p(eb_out), Hb, 0, p(am_out)
+    if not staged:
+        a.ee, a.keep, a.attn_mul = p(ee), p(keep), p(attn_mul)
+    a.src_scale, a.dst_scale = p(src_scale), p(dst_scale)
+    a.slope, a.attn_p, a.seed = slope, attn_p, seed
+    a.out, a.row_max, a.row_sum, a.gout = out.data_ptr(), row_max.data_ptr(), row_sum.data_ptr(), gout.data_ptr()
+    a.drec, a.gprime, a.gz = drec.data_ptr(), p(gprime), p(gz)
+    scratch = None
+    if graph._info.n_slots_out or graph._info.n_slots_in:
+        scratch = torch.empty(graph._info.n_slots_out * _r4(H * (D + 1)) + graph._info.n_slots_in * H,
+                              dtype=torch.float32, device=dev)
+        a.scratch = scratch.data_ptr()
+    a.grad_ft, a.grad_el, a.grad_ee, a.grad_er = grad_ft2d.data_ptr(), grad_el.data_ptr(), p(grad_ee), p(grad_er)
+    a.ld_gee = grad_ee.stride(0) if grad_ee is not None else 0
+    post_src = hooks.post_src if hooks is not None else None
+    if timer is None and post_src is None:
+        _lib.check(lib.botgat_gat_backward(h, C.byref(a), _stream()), "botgat_gat_backward")
+    elif timer is None:
+        a.phases = 3
+        _lib.check(lib.botgat_gat_backward(h, C.byref(a), _stream()), "botgat_gat_backward")
+        post_src(grad_ft2d, grad_el)  # e.g. start the halo reduce-scatter while the edge phase runs
+        a.phases = 4
+        _lib.check(lib.botgat_gat_backward(h, C.byref(a), _stream()), "botgat_gat_backward")
+    else:
+        for bit, name in ((1, "gat_bwd_node"), (2, "gat_bwd_src"), (4, "gat_bwd_edge")):
+            a.phases = bit
+            with _span(name):
+                rc = lib.botgat_gat_backward(h, C.byref(a), _stream())
+            _lib.check(rc, "botgat_gat_backward")
+            if bit == 2 and post_src is not None:
+                post_src(grad_ft2d, grad_el)
+    return grad_el, grad_er, (grad_ee if need_ee else None)
+
+
 class GATFusedFn(torch.autograd.Function):
     """out = dst_scale * sum_k softmax_v(leaky_relu(el[u]+er[v]+ee[k]))*attn_mul[k] * src_scale[u] * ft[u].
 
@@ -157,154 +296,129 @@ class GATFusedFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, graph, ft, el, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed, hooks=None):
-        lib = _lib.load()
-        h = graph._ensure()
         if ft.dim() != 3:
             raise ValueError("ft must be (N_src, H, D)")
         ft = _f32c(ft, "ft")
         N_s, H, D = ft.shape
-        N_d, E = graph.number_of_dst_nodes(), graph.number_of_edges()
+        N_d = graph.number_of_dst_nodes()
         if N_s != graph.number_of_src_nodes():
             raise ValueError(f"ft has {N_s} rows, graph has {graph.number_of_src_nodes()} source nodes")
         el = _f32c(el, "el").view(N_s, H)
         er = None if er is None else _f32c(er, "er").view(N_d, H)
-        ee, ld_ee = _rows(ee, "ee", H)
-        attn_mul, ld_am = _rows(attn_mul, "attn_mul", H)
-        if ee is not None and ee.shape[0] != E:
-            raise ValueError("ee must have one row per edge")
-        if keep is not None:
-            keep = keep.to(torch.uint8).contiguous()
-            if keep.numel() != E:
-                raise ValueError("keep must have one entry per edge")
+        ee, ld_ee, keep, attn_mul, ld_am = _check_edge_operands(graph, H, ee, keep, attn_mul)
         src_scale, dst_scale = _f32c(src_scale, "src_scale"), _f32c(dst_scale, "dst_scale")
-
-        staged = edge_mode == "staged"
         with torch.cuda.device(ft.device):
-            eb_in, Hb, am_in = edge_stage(graph, _lib.ORDER_IN, H, ee, keep, attn_mul) if staged else (None, 0, None)
-            pre = None
-            has_edge_ops = ee is not None or keep is not None or attn_mul is not None
-            if staged and prestage_backward and has_edge_ops and any(ctx.needs_input_grad):
-                # after the in-order staging (both are DRAM-bound), so that it runs beside the forward gather
-                main, side = torch.cuda.current_stream(), _side_stream(ft.device)
-                side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    eb_o, _, am_o = edge_stage(graph, _lib.ORDER_OUT, H, ee, keep, attn_mul)
-                    ev = torch.cuda.Event()
-                    ev.record(side)
-                for t in (ee, keep, attn_mul):
-                    if t is not None:
-                        t.record_stream(side)
-                pre = (eb_o, am_o, ev)
-            out = torch.empty((N_d, H, D), dtype=torch.float32, device=ft.device)
-            row_max = torch.empty((N_d, H), dtype=torch.float32, device=ft.device)
-            row_sum = torch.empty((N_d, H), dtype=torch.float32, device=ft.device)
-            a = _lib.FwdArgs()
-            a.H, a.D, a.ld_ft, a.ld_out = H, D, H * D, H * D
-            a.ft, a.el, a.er = ft.data_ptr(), el.data_ptr(), (er.data_ptr() if er is not None else None)
-            a.eb, a.Hb, a.col_parts = (eb_in.data_ptr() if eb_in is not None else None), Hb, 0
-            a.am = am_in.data_ptr() if am_in is not None else None
-            if not staged:
-                if (ee is not None and ld_ee != H) or (attn_mul is not None and ld_am != H):
-                    raise ValueError("direct edge mode needs unpadded (E,H) edge operands")
-                a.ee = ee.data_ptr() if ee is not None else None
-                a.keep = keep.data_ptr() if keep is not None else None
-                a.attn_mul = attn_mul.data_ptr() if attn_mul is not None else None
-            a.src_scale = src_scale.data_ptr() if src_scale is not None else None
-            a.dst_scale = dst_scale.data_ptr() if dst_scale is not None else None
-            a.slope, a.attn_p, a.seed = float(slope), float(attn_p if attn_mul is None else 0.0), int(seed)
-            a.out, a.row_max, a.row_sum = out.data_ptr(), row_max.data_ptr(), row_sum.data_ptr()
-            scratch = None
-            if graph._info.n_slots_in:  # heavy rows are split over several warps (segments.cu)
-                scratch = torch.empty(graph._info.n_slots_in * _r4(H * (D + 2)), dtype=torch.float32, device=ft.device)
-                a.scratch = scratch.data_ptr()
-            if hooks is not None and hooks.pre_kernel is not None:
-                hooks.pre_kernel()  # e.g. wait for an asynchronous halo all-gather that fills ft / el
-            with _span("gat_fwd"):
-                rc = lib.botgat_gat_forward(h, C.byref(a), _stream())
-            _lib.check(rc, "botgat_gat_forward")
-
+            out, row_max, row_sum, pre, attn_p_used = _forward_core(
+                graph, ft.view(N_s, H * D), H, D, el, er, ee, ld_ee, keep, attn_mul, ld_am, src_scale, dst_scale, slope,
+                attn_p, seed, hooks, any(ctx.needs_input_grad))
         ctx.graph = graph
         ctx.hooks = hooks
         ctx.pre = pre
-        ctx.cfg = (H, D, staged, float(slope), float(a.attn_p), int(seed))
+        ctx.cfg = (H, D, edge_mode == "staged", float(slope), attn_p_used, int(seed))
         ctx.save_for_backward(ft, el, er, ee, keep, attn_mul, src_scale, dst_scale, out, row_max, row_sum)
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        lib = _lib.load()
-        graph = ctx.graph
-        h = graph._ensure()
         ft, el, er, ee, keep, attn_mul, src_scale, dst_scale, out, row_max, row_sum = ctx.saved_tensors
-        H, D, staged, slope, attn_p, seed = ctx.cfg
-        N_s, N_d, E = ft.shape[0], out.shape[0], graph.number_of_edges()
-        dev = ft.device
+        H, D = ctx.cfg[0], ctx.cfg[1]
         need_er = er is not None and ctx.needs_input_grad[3]
         need_ee = ee is not None and ctx.needs_input_grad[4]
         gout = _f32c(gout, "grad_out")
+        grad_ft = torch.empty_like(ft)
+        with torch.cuda.device(ft.device):
+            grad_el, grad_er, grad_ee = _backward_core(
+                ctx.graph, ctx.cfg, ctx.pre, ctx.hooks, ft.view(-1, H * D), el, er, ee, keep, attn_mul, src_scale, dst_scale,
+                out, row_max, row_sum, gout, grad_ft.view(-1, H * D), need_er, need_ee)
+        return (None, grad_ft, grad_el, grad_er, grad_ee, None, None, None, None, None, None, None, None)
 
-        def p(t):
-            return t.data_ptr() if t is not None else None
 
+def _pad_rows(w, rows):
+    """(rows, in) copy of the weight block ``w`` with zero rows appended."""
+    if w.shape[0] == rows:
+        return w
+    return torch.cat([w, w.new_zeros(rows - w.shape[0], w.shape[1])], 0)
+
+
+class GATConvSampledFn(torch.autograd.Function):
+    """The whole sampled-variant layer body (src/ogbn-proteins/models.py:106-160) around the fused kernels with the
+    node-side projections folded into two GEMMs:
+
+        Ys = x_src @ [src_fc ; attn_src_fc]^T                       (N_s, pad32(H*D + H))
+        Yd = x_dst @ [dst_fc ; attn_dst_fc]^T + [dst_fc.bias ; 0]   (N_d, pad32(H*D + H))
+        rst = gat(ft = Ys[:, :HD], el = Ys[:, HD:HD+H], er = Yd[:, HD:HD+H], ...) + Yd[:, :HD]
+
+    instead of four GEMMs (two of them H columns wide: cuBLAS runs those as split-K kernels plus a reduction, each
+    slower than the wide ones) and, in backward, eight.  The kernels read ``ft`` and write ``grad_ft`` in place inside
+    the wide buffers (row stride = a multiple of 128 bytes, so gathered rows stay line-aligned); the backward is two
+    data-gradient and two weight-gradient GEMMs over the assembled (N, pad32) gradient blocks.
+
+    ``w_src`` = cat(src_fc.weight, attn_src_fc.weight) (HD+H, in); ``w_dst`` = cat(dst_fc.weight[, attn_dst_fc.weight]);
+    ``b_dst`` = dst_fc.bias (HD).  ``x_dst`` may be the same tensor as ``x_src`` (homogeneous graph, no input scaling).
+    """
+
+    @staticmethod
+    def forward(ctx, graph, x_src, x_dst, w_src, w_dst, b_dst, ee, keep, attn_mul, dst_scale, H, D, slope, attn_p, seed):
+        x_src, x_dst = _f32c(x_src, "feat_src"), _f32c(x_dst, "feat_dst")
+        N_s, N_d, HD = graph.number_of_src_nodes(), graph.number_of_dst_nodes(), H * D
+        if x_src.shape[0] != N_s or x_dst.shape[0] != N_d:
+            raise ValueError("feat_src / feat_dst rows do not match the graph")
+        has_er = w_dst.shape[0] == HD + H
+        P = (HD + H + 31) // 32 * 32
+        ws, wd = _pad_rows(w_src, P), _pad_rows(w_dst, P)
+        bd = torch.cat([b_dst, b_dst.new_zeros(P - HD)])
+        ee, ld_ee, keep, attn_mul, ld_am = _check_edge_operands(graph, H, ee, keep, attn_mul)
+        dst_scale = _f32c(dst_scale, "dst_scale")
+        with torch.cuda.device(x_src.device):
+            Ys = x_src @ ws.t()
+            Yd = torch.addmm(bd, x_dst, wd.t())
+            el = Ys[:, HD:HD + H].contiguous()
+            er = Yd[:, HD:HD + H].contiguous() if has_er else None
+            out, row_max, row_sum, pre, attn_p_used = _forward_core(
+                graph, Ys, H, D, el, er, ee, ld_ee, keep, attn_mul, ld_am, None, dst_scale, slope, attn_p, seed, None,
+                any(ctx.needs_input_grad))
+            rst = out + Yd[:, :HD].view(N_d, H, D)                                    # models.py:159-160
+        ctx.graph, ctx.pre, ctx.same_x = graph, pre, x_dst is x_src or x_dst.data_ptr() == x_src.data_ptr() and N_s == N_d
+        ctx.cfg = (H, D, edge_mode == "staged", float(slope), attn_p_used, int(seed))
+        ctx.dims = (P, has_er, w_src.shape[0], w_dst.shape[0])
+        ctx.save_for_backward(x_src, x_dst, ws, wd, Ys, el, er, ee, keep, attn_mul, dst_scale, out, row_max, row_sum)
+        return rst
+
+    @staticmethod
+    def backward(ctx, grst):
+        x_src, x_dst, ws, wd, Ys, el, er, ee, keep, attn_mul, dst_scale, out, row_max, row_sum = ctx.saved_tensors
+        H, D = ctx.cfg[0], ctx.cfg[1]
+        P, has_er, rows_s, rows_d = ctx.dims
+        HD = H * D
+        need = ctx.needs_input_grad
+        need_ee = ee is not None and need[6]
+        grst = _f32c(grst, "grad_out")
+        N_s, N_d = x_src.shape[0], x_dst.shape[0]
+        dev = x_src.device
         with torch.cuda.device(dev):
-            if ctx.pre is not None:  # staged during the forward on the side stream
-                eb_out, am_out, ev = ctx.pre
-                cur = torch.cuda.current_stream()
-                cur.wait_event(ev)
-                for t in (eb_out, am_out):
-                    if t is not None:
-                        t.record_stream(cur)
-                Hb = eb_out.shape[0] if eb_out is not None else 0
+            gYs = torch.empty((N_s, P), dtype=torch.float32, device=dev)
+            gYd = torch.empty((N_d, P), dtype=torch.float32, device=dev)
+            grad_el, grad_er, grad_ee = _backward_core(
+                ctx.graph, ctx.cfg, ctx.pre, None, Ys, el, er, ee, keep, attn_mul, None, dst_scale, out, row_max, row_sum,
+                grst, gYs, has_er, need_ee)
+            gYs[:, HD:HD + H] = grad_el
+            gYs[:, HD + H:].zero_()
+            gYd[:, :HD] = grst.view(N_d, HD)
+            if has_er:
+                gYd[:, HD:HD + H] = grad_er
+                gYd[:, HD + H:].zero_()
             else:
-                eb_out, Hb, am_out = edge_stage(graph, _lib.ORDER_OUT, H, ee, keep, attn_mul) if staged else (None, 0, None)
-            drec = torch.empty((H, N_d, 4), dtype=torch.float32, device=dev)
-            gprime = torch.empty_like(gout) if dst_scale is not None else None
-            grad_ft = torch.empty_like(ft)
-            grad_el = torch.empty((N_s, H), dtype=torch.float32, device=dev)
-            grad_er = torch.empty((N_d, H), dtype=torch.float32, device=dev) if need_er else None
-            # gz (out-CSR order) -> grad_ee (edge-id order); grad_er is reduced from grad_ee
-            gz = grad_ee = None
-            if need_er or need_ee:
-                gz = torch.empty((H, E), dtype=torch.float32, device=dev) if staged else None
-                # same row width as the ee that came in (padding columns receive zeros)
-                Hp = ee.shape[1] if (ee is not None and staged) else (pad_heads(H) if staged else H)
-                grad_ee = torch.empty((E, Hp), dtype=torch.float32, device=dev)
-            a = _lib.BwdArgs()
-            a.H, a.D, a.ld_ft, a.ld_out, a.ld_gft = H, D, H * D, H * D, H * D
-            a.ft, a.el, a.er = ft.data_ptr(), el.data_ptr(), p(er)
-            a.eb_out, a.Hb, a.phases, a.am_out = p(eb_out), Hb, 0, p(am_out)
-            if not staged:
-                a.ee, a.keep, a.attn_mul = p(ee), p(keep), p(attn_mul)
-            a.src_scale, a.dst_scale = p(src_scale), p(dst_scale)
-            a.slope, a.attn_p, a.seed = slope, attn_p, seed
-            a.out, a.row_max, a.row_sum, a.gout = out.data_ptr(), row_max.data_ptr(), row_sum.data_ptr(), gout.data_ptr()
-            a.drec, a.gprime, a.gz = drec.data_ptr(), p(gprime), p(gz)
-            scratch = None
-            if graph._info.n_slots_out or graph._info.n_slots_in:
-                scratch = torch.empty(graph._info.n_slots_out * _r4(H * (D + 1)) + graph._info.n_slots_in * H,
-                                      dtype=torch.float32, device=dev)
-                a.scratch = scratch.data_ptr()
-            a.grad_ft, a.grad_el, a.grad_ee, a.grad_er = grad_ft.data_ptr(), grad_el.data_ptr(), p(grad_ee), p(grad_er)
-            a.ld_gee = grad_ee.stride(0) if grad_ee is not None else 0
-            post_src = ctx.hooks.post_src if ctx.hooks is not None else None
-            if timer is None and post_src is None:
-                _lib.check(lib.botgat_gat_backward(h, C.byref(a), _stream()), "botgat_gat_backward")
-            elif timer is None:
-                a.phases = 3
-                _lib.check(lib.botgat_gat_backward(h, C.byref(a), _stream()), "botgat_gat_backward")
-                post_src(grad_ft, grad_el)  # e.g. start the halo reduce-scatter while the edge phase runs
-                a.phases = 4
-                _lib.check(lib.botgat_gat_backward(h, C.byref(a), _stream()), "botgat_gat_backward")
+                gYd[:, HD:].zero_()
+            gw_s = (gYs.t() @ x_src)[:rows_s] if need[3] else None
+            gw_d = (gYd.t() @ x_dst)[:rows_d] if need[4] else None
+            gb = grst.view(N_d, HD).sum(0) if need[5] else None
+            gx_s = gx_d = None
+            if ctx.same_x and need[1]:
+                gx_s = torch.addmm(gYs @ ws, gYd, wd)       # both projections read the same input
             else:
-                for bit, name in ((1, "gat_bwd_node"), (2, "gat_bwd_src"), (4, "gat_bwd_edge")):
-                    a.phases = bit
-                    with _span(name):
-                        rc = lib.botgat_gat_backward(h, C.byref(a), _stream())
-                    _lib.check(rc, "botgat_gat_backward")
-                    if bit == 2 and post_src is not None:
-                        post_src(grad_ft, grad_el)
-        return (None, grad_ft, grad_el, grad_er, (grad_ee if need_ee else None), None, None, None, None, None, None, None,
-                None)
+                gx_s = gYs @ ws if need[1] else None
+                gx_d = gYd @ wd if need[2] else None
+        return (None, gx_s, gx_d, gw_s, gw_d, gb, grad_ee, None, None, None, None, None, None, None, None)
 
 
 class EdgeLogitProj(torch.autograd.Function):

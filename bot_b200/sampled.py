@@ -13,12 +13,19 @@ Reference: GATConv       src/ogbn-proteins/models.py:19-168 (= products :20-167)
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .functional import Deferred, EdgeEmbedding, edge_logits, gat_fused
+from .functional import Deferred, EdgeEmbedding, GATConvSampledFn, edge_logits, gat_fused
 from .no_sampling import draw_attn_mul, draw_edge_keep
+
+
+# Fold the layer's four node-side Linears into two GEMMs (functional.GATConvSampledFn).  False: one nn.Linear call
+# each, exactly the reference's op sequence.
+fold_projections = os.environ.get("BOTGAT_FOLD", "1") != "0"
 
 
 class GATConv(nn.Module):
@@ -82,18 +89,20 @@ class GATConv(nn.Module):
                 feat_src = feat_src * torch.pow(graph.srcdata["deg"], -0.5).view(-1, *([1] * (feat_src.dim() - 1)))
                 dst_scale = torch.pow(graph.dstdata["deg"], 0.5).float().contiguous()
 
-            ft = self.src_fc(feat_src).view(-1, H, D)                         # models.py:106
-            resid = self.dst_fc(feat_dst).view(-1, H, D)                      # models.py:107
-            el = self.attn_src_fc(feat_src)                                   # models.py:108  (N_s,H)
-            er = self.attn_dst_fc(feat_dst) if self.attn_dst_fc is not None else None   # models.py:122-124
+            fold = fold_projections and feat_src.is_cuda and feat_src.dim() == 2
+            if not fold:
+                ft = self.src_fc(feat_src).view(-1, H, D)                     # models.py:106
+                resid = self.dst_fc(feat_dst).view(-1, H, D)                  # models.py:107
+                el = self.attn_src_fc(feat_src)                               # models.py:108  (N_s,H)
+                er = self.attn_dst_fc(feat_dst) if self.attn_dst_fc is not None else None   # models.py:122-124
             E = graph.number_of_edges()
             keep = attn_mul = eids = None
             attn_p, seed = 0.0, 0
             if self.training and self.edge_drop > 0:                          # models.py:136-141
-                keep, eids = draw_edge_keep(E, self.edge_drop, ft.device)
+                keep, eids = draw_edge_keep(E, self.edge_drop, feat_src.device)
             if self.training and self.attn_drop.p > 0:
                 if self.attn_dropout_mode == "exact":
-                    attn_mul = draw_attn_mul(self.attn_drop, E, H, ft.device, eids)
+                    attn_mul = draw_attn_mul(self.attn_drop, E, H, feat_src.device, eids)
                 else:
                     attn_p = self.attn_drop.p
                     seed = int(torch.randint(0, 2**62, (1,)).item())
@@ -109,9 +118,18 @@ class GATConv(nn.Module):
                 else:
                     ee = edge_logits(feat_edge, self.attn_edge_fc.weight)      # (E, pad_heads(H))
 
-            rst = gat_fused(graph, ft, el, er, ee, keep, attn_mul, None, dst_scale,
-                            self._negative_slope, attn_p, seed)                # models.py:125-156
-            rst = rst + resid                                                 # models.py:159-160
+            if fold:
+                # the four node-side Linears (models.py:106-108,122-124) as two GEMMs whose outputs the kernels
+                # read in place, the residual add (models.py:159-160) included
+                w_src = torch.cat([self.src_fc.weight, self.attn_src_fc.weight], 0)
+                w_dst = self.dst_fc.weight if self.attn_dst_fc is None else \
+                    torch.cat([self.dst_fc.weight, self.attn_dst_fc.weight], 0)
+                rst = GATConvSampledFn.apply(graph, feat_src, feat_dst, w_src, w_dst, self.dst_fc.bias, ee, keep, attn_mul,
+                                             dst_scale, H, D, self._negative_slope, attn_p, seed)
+            else:
+                rst = gat_fused(graph, ft, el, er, ee, keep, attn_mul, None, dst_scale,
+                                self._negative_slope, attn_p, seed)            # models.py:125-156
+                rst = rst + resid                                             # models.py:159-160
             if self.activation is not None:
                 rst = self.activation(rst, inplace=True)
             return rst
