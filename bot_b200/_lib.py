@@ -70,6 +70,12 @@ SIGNATURES = {
     "botgat_edge_stage": (C.c_int, [c_vp, C.c_int, C.c_int32, c_vp, C.c_int64, c_vp, c_vp, C.c_int64, c_vp, c_vp, c_vp]),
     "botgat_edge_unstage": (C.c_int, [c_vp, C.c_int, C.c_int32, c_vp, c_vp, C.c_int64, c_vp]),
     "botgat_edge_reduce_dst": (C.c_int, [c_vp, C.c_int32, c_vp, C.c_int64, c_vp, c_vp, c_vp]),
+    "botgat_sample_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "botgat_sample_count": (C.c_int, [c_vp, C.c_int64, c_vp, C.c_int32, c_vp, C.POINTER(C.c_int64), c_vp, c_vp]),
+    "botgat_sample_neighbors": (C.c_int, [c_vp, C.c_int64, c_vp, C.c_int32, C.c_uint64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "botgat_block_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "botgat_block_compact": (C.c_int, [C.c_int64, C.c_int64, c_vp, C.c_int64, c_vp, c_vp, c_vp, C.POINTER(C.c_int64), c_vp,
+                                       C.c_int, c_vp]),
     "botgat_edge_drop_workspace_bytes": (C.c_int64, [C.c_int64]),
     "botgat_edge_drop_draw": (C.c_int, [C.c_int64, C.c_int64, C.c_uint64, c_vp, c_vp, C.c_int, c_vp]),
     "botgat_edge_mlp_supported": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),

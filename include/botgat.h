@@ -287,6 +287,35 @@ int botgat_rows_gather(const float* table, int64_t ld, int64_t width, const int6
 int botgat_rows_scatter_add(float* table, int64_t ld, int64_t width, const int64_t* rows, int64_t n_rows,
                             const float* in /* (n_rows,width), rows unique */, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Neighbour sampling and block construction on the device.  Replaces
+ * dgl.dataloading.MultiLayerNeighborSampler + NodeDataLoader and their CPU worker processes
+ * (src/ogbn-proteins/gat.py:177-201, src/ogbn-products/gat.py:202-233), per layer:
+ *   frontier = sample_neighbors(g, seeds, fanout): botgat_sample_count, then botgat_sample_neighbors
+ *   block    = to_block(frontier, seeds):          botgat_block_compact, then botgat_graph_create
+ * Uniform without replacement over the in-edges of each seed; every in-edge when in-degree <= fanout or
+ * fanout <= 0; fanout <= 256.  Deterministic in (graph, seeds, fanout, seed).
+ *
+ * botgat_sample_count: offsets[i] (device, n_seeds+1) = start of seed i's picks, *n_out (HOST) = total;
+ *   workspace = botgat_sample_workspace_bytes(n_seeds) bytes; synchronises `stream`.
+ * botgat_sample_neighbors: for seed i and its j-th pick, at offsets[i]+j: out_src = source node id in g,
+ *   out_dst = i (the block's destination id), out_eid = edge id in g.
+ * botgat_block_compact: src_nodes = seeds followed by the sampled sources that are not seeds in ascending id
+ *   (capacity n_seeds + n_edges), src_local[e] = position of src_global[e] in src_nodes, *n_src (HOST) = length
+ *   of src_nodes; seeds must be unique; workspace = botgat_block_workspace_bytes(n_parent) bytes, 256-byte
+ *   aligned; synchronises `stream`.
+ * ---------------------------------------------------------------------- */
+int64_t botgat_sample_workspace_bytes(int64_t n_seeds);
+int botgat_sample_count(const botgat_graph* g, int64_t n_seeds, const int64_t* seeds, int32_t fanout,
+                        int64_t* offsets, int64_t* n_out /* HOST */, void* workspace, void* stream);
+int botgat_sample_neighbors(const botgat_graph* g, int64_t n_seeds, const int64_t* seeds, int32_t fanout,
+                            uint64_t seed, const int64_t* offsets, int64_t* out_src, int64_t* out_dst,
+                            int64_t* out_eid, void* stream);
+int64_t botgat_block_workspace_bytes(int64_t n_parent);
+int botgat_block_compact(int64_t n_parent, int64_t n_seeds, const int64_t* seeds, int64_t n_edges,
+                         const int64_t* src_global, int64_t* src_local, int64_t* src_nodes, int64_t* n_src /* HOST */,
+                         void* workspace, int device, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

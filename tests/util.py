@@ -168,3 +168,67 @@ def philox_edge_drop_keep(seed, n_edges, n_drop):
     keep = np.ones(n_edges, dtype=np.uint8)
     keep[np.argsort(keys, kind="stable")[:n_drop]] = 0
     return torch.from_numpy(keep)
+
+
+def _philox4x32(seed, c0, c1, c2, c3):
+    """numpy Philox4x32-10 over arrays of counter words (uint32); returns the four output words."""
+    import numpy as np
+
+    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), 0x9E3779B9, 0xBB67AE85
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint32) for c in (c0, c1, c2, c3))
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    for _ in range(10):
+        p0 = M0 * c0.astype(np.uint64)
+        p1 = M1 * c2.astype(np.uint64)
+        hi0, lo0 = (p0 >> np.uint64(32)).astype(np.uint32), p0.astype(np.uint32)
+        hi1, lo1 = (p1 >> np.uint64(32)).astype(np.uint32), p1.astype(np.uint32)
+        c0, c1, c2, c3 = hi1 ^ c1 ^ np.uint32(k0), lo1, hi0 ^ c3 ^ np.uint32(k1), lo0
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def sample_neighbors_ref(indptr, indices, eids, seeds, fanout, seed):
+    """numpy restatement of `botgat_sample_neighbors` (bot_b200/csrc/sampling.cu): per seed v with in-degree d > fanout
+    the candidate stream c_n = mulhi64(philox64(seed; n>>1, 0x40000000, v, 0x5BD1E995)[n&1], d), n = 0, 1, ...,
+    accepted when new until m = fanout picks (or, when fanout > d // 2, m = d - fanout EXCLUDED positions, the rest
+    emitted in row order).  Returns (src, dst_pos, eid, offsets)."""
+    import numpy as np
+
+    src, dst, eid, offsets = [], [], [], [0]
+    for i, v in enumerate(np.asarray(seeds)):
+        beg, d = int(indptr[v]), int(indptr[v + 1] - indptr[v])
+        if fanout <= 0 or d <= fanout:
+            pos = list(range(d))
+        else:
+            complement = fanout > d // 2
+            m = d - fanout if complement else fanout
+            picks, n0 = [], 0
+            while len(picks) < m:
+                n = np.arange(n0, n0 + 32, dtype=np.uint64)
+                w = _philox4x32(seed, (n >> np.uint64(1)).astype(np.uint32), np.full(32, 0x40000000, np.uint32),
+                                np.full(32, v, np.uint32), np.full(32, 0x5BD1E995, np.uint32))
+                for j in range(32):
+                    hi, lo = (w[2][j], w[3][j]) if (n0 + j) & 1 else (w[0][j], w[1][j])
+                    c = (((int(hi) << 32) | int(lo)) * d) >> 64
+                    if c not in picks and len(picks) < m:
+                        picks.append(c)
+                n0 += 32
+            pos = [j for j in range(d) if j not in set(picks)] if complement else picks
+        src += [int(indices[beg + j]) for j in pos]
+        eid += [int(eids[beg + j]) for j in pos]
+        dst += [i] * len(pos)
+        offsets.append(len(src))
+    return (np.asarray(src, dtype=np.int64), np.asarray(dst, dtype=np.int64), np.asarray(eid, dtype=np.int64),
+            np.asarray(offsets, dtype=np.int64))
+
+
+def to_block_ref(n_parent, seeds, src):
+    """numpy restatement of `botgat_block_compact`: src nodes = seeds, then the other sampled sources ascending."""
+    import numpy as np
+
+    seeds = np.asarray(seeds, dtype=np.int64)
+    extra = np.setdiff1d(np.unique(src), seeds)
+    nodes = np.concatenate([seeds, extra])
+    where = np.full(n_parent, -1, dtype=np.int64)
+    where[nodes] = np.arange(nodes.size)
+    return nodes, where[np.asarray(src, dtype=np.int64)]
