@@ -119,3 +119,60 @@ def test_pad_heads():
     from bot_b200.functional import pad_heads
 
     assert [pad_heads(h) for h in (1, 2, 3, 4, 5, 6, 8, 9, 12)] == [1, 2, 4, 4, 8, 8, 8, 12, 12]
+
+
+def test_lazy_frame_gathers_parent_rows():
+    from bot_b200.sampling import NID, _LazyFrame
+
+    parent = {"feat": torch.arange(20.0).view(10, 2), "deg": torch.arange(10)}
+    ids = torch.tensor([7, 2, 2, 9])
+    f = _LazyFrame(parent, ids)
+    assert torch.equal(f[NID], ids) and "feat" in f and "nope" not in f
+    assert torch.equal(f["feat"], parent["feat"][ids]) and torch.equal(f["deg"], ids)
+    f["feat"] = f["feat"] + 1          # the reference's add_labels overwrites srcdata["feat"] (gat.py:88-100)
+    assert torch.equal(f["feat"], parent["feat"][ids] + 1)
+    assert set(f.keys()) == {NID, "feat", "deg"}
+    with pytest.raises(KeyError):
+        f["nope"]
+
+
+def test_sampling_restatement_properties():
+    """The numpy restatement the GPU sampler is checked against: exact counts, no repeats, real in-edges,
+    and a uniform draw (direct and complement paths)."""
+    import numpy as np
+
+    from oracle import graph_ref
+    from util import sample_neighbors_ref, to_block_ref
+
+    src, dst = graph_ref.synthetic_coo(120, 3000, 1, power_law=0.9)
+    ref = graph_ref.build_formats(src, dst, 120, 120)
+    seeds = np.arange(0, 120, 3)
+    for fanout in (3, 20, -1):
+        s, d, e, off = sample_neighbors_ref(ref["in_indptr"], ref["in_indices"], ref["in_eid"], seeds, fanout, 99)
+        deg = ref["in_deg"][seeds]
+        assert np.array_equal(np.diff(off), deg if fanout <= 0 else np.minimum(deg, fanout))
+        assert np.unique(e).size == e.size
+        assert np.array_equal(src[e], s) and np.array_equal(dst[e], seeds[d])
+        nodes, local = to_block_ref(120, seeds, s)
+        assert np.array_equal(nodes[: seeds.size], seeds) and np.unique(nodes).size == nodes.size
+        assert np.array_equal(nodes[local], s)
+    indptr, idx = np.array([0, 30]), np.arange(30)
+    for k in (6, 24):
+        freq = np.zeros(30)
+        for sd in range(600):
+            _, _, e, _ = sample_neighbors_ref(indptr, idx, idx, np.array([0]), k, sd)
+            assert e.size == k
+            freq[e] += 1
+        p = k / 30
+        z = (freq / 600 - p) / (p * (1 - p) / 600) ** 0.5
+        assert np.abs(z).max() < 4.5
+
+
+def test_edge_drop_restatement_counts():
+    from util import philox_edge_drop_keep
+
+    for E, n_drop in ((1, 0), (7, 3), (1000, 370), (1001, 1000)):
+        keep = philox_edge_drop_keep(5, E, n_drop)
+        assert int(keep.sum()) == E - n_drop
+    a, b = philox_edge_drop_keep(1, 5000, 500), philox_edge_drop_keep(2, 5000, 500)
+    assert not torch.equal(a, b)
