@@ -78,7 +78,17 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark_begin(self, timeout=3.0):
+        # nvidia-smi needs a few hundred ms before its first line: do not start the timed region without it
+        t = time.time()
+        while self.proc is not None and not self.lines and time.time() - t < timeout:
+            time.sleep(0.01)
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -91,7 +101,13 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        # the sampler runs from before the warm-up; only samples that arrived inside the timed region count
+        t0, t1 = getattr(self, "t0", 0.0), getattr(self, "t1", float("inf"))
+        inside = [ln for (t, ln) in self.lines if t0 <= t <= t1]
+        window = "timed region"
+        if not inside:
+            inside, window = [ln for (_, ln) in self.lines], "whole run (no sample fell inside the timed region)"
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 6:
                 continue
@@ -104,7 +120,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ----------------------------------------------------------------------------
@@ -242,22 +258,24 @@ def run_ours(args):
         for t in (ft_own, el_own, er, ee):
             t.grad = None
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step_resident()
     barrier()
     launches0 = lib.botgat_launch_count()
     kt = functional.KernelTimer()
     functional.timer = kt
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_begin()
     barrier()
     e0.record()
     for _ in range(args.steps):
         step_resident()
     e1.record()
     barrier()
+    sampler.mark_end()
     functional.timer = None
     clocks = sampler.stop() if rank == 0 else None
     launches = lib.botgat_launch_count() - launches0

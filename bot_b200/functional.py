@@ -208,7 +208,7 @@ def _forward_core(graph, ft2d, H, D, el, er, ee, ld_ee, keep, attn_mul, ld_am, s
 
 
 def _backward_core(graph, cfg, pre, hooks, ft2d, el, er, ee, keep, attn_mul, src_scale, dst_scale, out, row_max, row_sum,
-                   gout, grad_ft2d, need_er, need_ee):
+                   gout, grad_ft2d, need_er, need_ee, hook_grad_ft=None):
     """The three backward phases.  ``grad_ft2d``: 2-D tensor whose first H*D columns receive grad_ft (any aligned row
     stride).  Returns (grad_el (N_s,H), grad_er | None, grad_ee | None)."""
     lib = _lib.load()
@@ -264,7 +264,7 @@ def _backward_core(graph, cfg, pre, hooks, ft2d, el, er, ee, keep, attn_mul, src
     elif timer is None:
         a.phases = 3
         _lib.check(lib.botgat_gat_backward(h, C.byref(a), _stream()), "botgat_gat_backward")
-        post_src(grad_ft2d, grad_el)  # e.g. start the halo reduce-scatter while the edge phase runs
+        post_src(grad_ft2d if hook_grad_ft is None else hook_grad_ft, grad_el)  # e.g. start the halo reduce-scatter while the edge phase runs
         a.phases = 4
         _lib.check(lib.botgat_gat_backward(h, C.byref(a), _stream()), "botgat_gat_backward")
     else:
@@ -274,7 +274,7 @@ def _backward_core(graph, cfg, pre, hooks, ft2d, el, er, ee, keep, attn_mul, src
                 rc = lib.botgat_gat_backward(h, C.byref(a), _stream())
             _lib.check(rc, "botgat_gat_backward")
             if bit == 2 and post_src is not None:
-                post_src(grad_ft2d, grad_el)
+                post_src(grad_ft2d if hook_grad_ft is None else hook_grad_ft, grad_el)
     return grad_el, grad_er, (grad_ee if need_ee else None)
 
 
@@ -329,7 +329,7 @@ class GATFusedFn(torch.autograd.Function):
         with torch.cuda.device(ft.device):
             grad_el, grad_er, grad_ee = _backward_core(
                 ctx.graph, ctx.cfg, ctx.pre, ctx.hooks, ft.view(-1, H * D), el, er, ee, keep, attn_mul, src_scale, dst_scale,
-                out, row_max, row_sum, gout, grad_ft.view(-1, H * D), need_er, need_ee)
+                out, row_max, row_sum, gout, grad_ft.view(-1, H * D), need_er, need_ee, hook_grad_ft=grad_ft)
         return (None, grad_ft, grad_el, grad_er, grad_ee, None, None, None, None, None, None, None, None)
 
 
