@@ -62,6 +62,7 @@ SIGNATURES = {
     "botgat_launch_count": (C.c_int64, []),
     "botgat_graph_create": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, c_vp, c_vp, C.c_int, c_vp, C.POINTER(c_vp)]),
     "botgat_graph_destroy": (None, [c_vp]),
+    "botgat_graph_destroy_async": (None, [c_vp, c_vp]),
     "botgat_graph_get": (C.c_int, [c_vp, C.c_int, C.POINTER(c_vp), c_i64p]),
     "botgat_graph_get_info": (C.c_int, [c_vp, C.POINTER(GraphInfo)]),
     "botgat_coo_to_bidirected": (C.c_int, [C.c_int64, C.c_int64, c_vp, c_vp, c_vp, c_vp, c_i64p, C.c_int, c_vp]),

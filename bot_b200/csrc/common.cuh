@@ -220,7 +220,7 @@ Tiling choose_tiling(int H, int D, int64_t ld_g, const void* pg, int64_t ld_o, c
 // host (segments.cu): build / free the segment table of one CSR; a no-op when no row exceeds the segment length
 int build_segments(int n_rows, const int32_t* indptr, const int32_t* deg, int64_t max_deg, botgat_graph::SegTable* t,
                    cudaStream_t st);
-void free_segments(botgat_graph::SegTable* t);
+void free_segments(botgat_graph::SegTable* t, bool async, cudaStream_t st);
 
 // steps (of 32/G neighbours each) whose row loads a lane keeps in flight together.
 // Measured on B200 (profiles/r01_*): at D=80 (3 slots) two steps at 3 blocks/SM beat four steps at 2 blocks/SM.

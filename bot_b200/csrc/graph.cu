@@ -186,15 +186,37 @@ extern "C" int botgat_abi_version(void) { return BOTGAT_ABI_VERSION; }
 extern "C" const char* botgat_last_error(void) { return g_err; }
 extern "C" int64_t botgat_launch_count(void) { return (int64_t)g_launches.load(); }
 
-extern "C" void botgat_graph_destroy(botgat_graph* g) {
+// The structure arrays come from the device's stream-ordered pool (cudaMallocAsync): mini-batch blocks are created and
+// destroyed every step, and cudaMalloc / cudaFree would synchronise the device each time.
+static void configure_pool(int device) {
+  static std::atomic<unsigned> done{0};
+  const unsigned bit = 1u << (device & 31);
+  if (done.fetch_or(bit) & bit) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) != cudaSuccess) return;
+  uint64_t thr = 0;
+  // keep freed blocks cached (up to 2 GiB) unless the application already chose a threshold
+  if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr) == cudaSuccess && thr == 0) {
+    thr = 2ull << 30;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+}
+
+static void destroy_impl(botgat_graph* g, bool async, cudaStream_t st) {
   if (!g) return;
   DeviceGuard guard(g->device);
-  cudaFree(g->in_indptr); cudaFree(g->in_indices); cudaFree(g->in_eid);
-  cudaFree(g->out_indptr); cudaFree(g->out_indices); cudaFree(g->out_eid);
-  cudaFree(g->in_deg); cudaFree(g->out_deg);
-  free_segments(&g->seg_in); free_segments(&g->seg_out);
+  void* ptrs[] = {g->in_indptr, g->in_indices, g->in_eid, g->out_indptr, g->out_indices, g->out_eid, g->in_deg, g->out_deg};
+  for (void* q : ptrs) {
+    if (!q) continue;
+    // cudaFree of pool memory synchronises, then releases; it is also the fallback if the stream is unusable
+    if (!async || cudaFreeAsync(q, st) != cudaSuccess) { cudaGetLastError(); cudaFree(q); }
+  }
+  free_segments(&g->seg_in, async, st); free_segments(&g->seg_out, async, st);
   delete g;
 }
+
+extern "C" void botgat_graph_destroy(botgat_graph* g) { destroy_impl(g, false, nullptr); }
+extern "C" void botgat_graph_destroy_async(botgat_graph* g, void* stream) { destroy_impl(g, true, (cudaStream_t)stream); }
 
 extern "C" int botgat_graph_create(int64_t n_src, int64_t n_dst, int64_t n_edges, const int64_t* src,
                                    const int64_t* dst, int device, void* stream, botgat_graph** out) {
@@ -216,13 +238,14 @@ extern "C" int botgat_graph_create(int64_t n_src, int64_t n_dst, int64_t n_edges
     ~Cleanup() { if (armed) { botgat_graph_destroy(g); } }
   } cleanup{g};
 
+  configure_pool(device);
   const size_t eb = sizeof(int32_t) * (size_t)std::max<int64_t>(n_edges, 1);
-  BG_CHECK(cudaMalloc(&g->in_indptr, sizeof(int32_t) * (n_dst + 1)));
-  BG_CHECK(cudaMalloc(&g->out_indptr, sizeof(int32_t) * (n_src + 1)));
-  BG_CHECK(cudaMalloc(&g->in_indices, eb)); BG_CHECK(cudaMalloc(&g->in_eid, eb));
-  BG_CHECK(cudaMalloc(&g->out_indices, eb)); BG_CHECK(cudaMalloc(&g->out_eid, eb));
-  BG_CHECK(cudaMalloc(&g->in_deg, sizeof(int32_t) * (n_dst + 1)));
-  BG_CHECK(cudaMalloc(&g->out_deg, sizeof(int32_t) * (n_src + 1)));
+  BG_CHECK(cudaMallocAsync(&g->in_indptr, sizeof(int32_t) * (n_dst + 1), st));
+  BG_CHECK(cudaMallocAsync(&g->out_indptr, sizeof(int32_t) * (n_src + 1), st));
+  BG_CHECK(cudaMallocAsync(&g->in_indices, eb, st)); BG_CHECK(cudaMallocAsync(&g->in_eid, eb, st));
+  BG_CHECK(cudaMallocAsync(&g->out_indices, eb, st)); BG_CHECK(cudaMallocAsync(&g->out_eid, eb, st));
+  BG_CHECK(cudaMallocAsync(&g->in_deg, sizeof(int32_t) * (n_dst + 1), st));
+  BG_CHECK(cudaMallocAsync(&g->out_deg, sizeof(int32_t) * (n_src + 1), st));
 
   int32_t *src32 = nullptr, *dst32 = nullptr, *iota = nullptr, *ktmp = nullptr;
   int* flags = nullptr;  // [bad, max_in, zero_in, max_out, zero_out]

@@ -55,9 +55,12 @@ __global__ void k_seg_fill(int n_rows, const int32_t* __restrict__ indptr, int L
   }
 }
 
-void free_segments(botgat_graph::SegTable* t) {
-  cudaFree(t->row); cudaFree(t->beg); cudaFree(t->end); cudaFree(t->slot);
-  cudaFree(t->split_rows); cudaFree(t->split_first);
+void free_segments(botgat_graph::SegTable* t, bool async, cudaStream_t st) {
+  void* ptrs[] = {t->row, t->beg, t->end, t->slot, t->split_rows, t->split_first};
+  for (void* q : ptrs) {
+    if (!q) continue;
+    if (!async || cudaFreeAsync(q, st) != cudaSuccess) { cudaGetLastError(); cudaFree(q); }
+  }
   *t = botgat_graph::SegTable();
 }
 
@@ -86,10 +89,10 @@ int build_segments(int n_rows, const int32_t* indptr, const int32_t* deg, int64_
   BG_CHECK(cudaMemcpyAsync(&tot[2], split_off + n_rows, 4, cudaMemcpyDeviceToHost, st));
   BG_CHECK(cudaStreamSynchronize(st));
   t->n_items = tot[0]; t->n_slots = tot[1]; t->n_split = tot[2];
-  BG_CHECK(cudaMalloc(&t->row, 4 * (size_t)t->n_items)); BG_CHECK(cudaMalloc(&t->beg, 4 * (size_t)t->n_items));
-  BG_CHECK(cudaMalloc(&t->end, 4 * (size_t)t->n_items)); BG_CHECK(cudaMalloc(&t->slot, 4 * (size_t)t->n_items));
-  BG_CHECK(cudaMalloc(&t->split_rows, 4 * (size_t)(t->n_split + 1)));
-  BG_CHECK(cudaMalloc(&t->split_first, 4 * (size_t)(t->n_split + 1)));
+  BG_CHECK(cudaMallocAsync(&t->row, 4 * (size_t)t->n_items, st)); BG_CHECK(cudaMallocAsync(&t->beg, 4 * (size_t)t->n_items, st));
+  BG_CHECK(cudaMallocAsync(&t->end, 4 * (size_t)t->n_items, st)); BG_CHECK(cudaMallocAsync(&t->slot, 4 * (size_t)t->n_items, st));
+  BG_CHECK(cudaMallocAsync(&t->split_rows, 4 * (size_t)(t->n_split + 1), st));
+  BG_CHECK(cudaMallocAsync(&t->split_first, 4 * (size_t)(t->n_split + 1), st));
   k_seg_fill<<<(n_rows + 1 + 255) / 256, 256, 0, st>>>(n_rows, indptr, L, seg_off, slot_off, split_off, t->row, t->beg,
                                                        t->end, t->slot, t->split_rows, t->split_first);
   BG_LAUNCHED(1);

@@ -86,9 +86,14 @@ class Graph:
         h, self._handle = getattr(self, "_handle", None), None
         if h is not None and _lib._lib is not None:
             try:
-                _lib._lib.botgat_graph_destroy(h)
+                # back to the stream-ordered pool behind the work enqueued so far (no device synchronisation:
+                # mini-batch blocks come and go every step)
+                _lib._lib.botgat_graph_destroy_async(h, C.c_void_p(torch.cuda.current_stream(self._src.device).cuda_stream))
             except Exception:
-                pass
+                try:
+                    _lib._lib.botgat_graph_destroy(h)
+                except Exception:
+                    pass
 
     def create_formats_(self):
         """``graph.create_formats_()`` (run.py:146): materialise CSR + CSC now."""

@@ -57,6 +57,9 @@ int botgat_graph_create(int64_t n_src, int64_t n_dst, int64_t n_edges,
                         const int64_t* src, const int64_t* dst,
                         int device, void* stream, botgat_graph** out);
 void botgat_graph_destroy(botgat_graph* g);
+/* Same, without synchronising the device: the memory returns to the stream-ordered pool after the work already
+ * enqueued on `stream` (every consumer of the graph must have been enqueued there or have finished). */
+void botgat_graph_destroy_async(botgat_graph* g, void* stream);
 
 enum {
   BOTGAT_IN_INDPTR = 0,   /* int32 (n_dst+1) */
