@@ -137,15 +137,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB_BWD) gat_bwd_src_
     const int pos = base + lane;
     o.rec = make_float4(0.f, 0.f, 0.f, 0.f);
     o.eb = -INFINITY;  // lanes past the row end behave like dropped edges: alpha = 0
-    o.amul = 1.f;
+    o.amul = 1.f; o.ame = 1.f; o.amp = 1.f;
+    o.ee = 0.f;
+    o.kp = 1;
     if (pos < end) {
       o.rec = __ldg(drec_h + v);
       o.eb = eb_h ? __ldg(eb_h + pos) : 0.f;
-      if (ee_h) o.eb += __ldg(ee_h + (int64_t)k * H);
-      if (keep && !__ldg(keep + k)) o.eb = -INFINITY;
+      if (ee_h) o.ee = __ldg(ee_h + (int64_t)k * H);
+      if (keep) o.kp = __ldg(keep + k);
       if (am_h) o.amul = __ldg(am_h + pos);
-      else if (amul_h) o.amul = __ldg(amul_h + (int64_t)k * H);
-      else if (philox) o.amul = philox_dropout_mul(p.seed, (uint32_t)k, (uint32_t)h, p.attn_p, p.inv_keep);
+      if (amul_h) o.ame = __ldg(amul_h + (int64_t)k * H);
+      if (philox) o.amp = philox_dropout_mul(p.seed, (uint32_t)k, (uint32_t)h, p.attn_p, p.inv_keep);
     }
   };
   // one step: the group's neighbour row is in x; acc += w*x, and the dot <x, ft[u]> goes to the owner lane
@@ -174,11 +176,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB_BWD) gat_bwd_src_
     load_operands(base + 32, vtx1, k1, o1);
 
     // lane = neighbour: recompute the attention weight of this edge
-    const float z = el_u + o0.rec.x + o0.eb;
+    const float z = el_u + o0.rec.x + o0.logit_term();
     const float s = leaky_relu(z, slope);
     const float alpha = (s == -INFINITY) ? 0.f : __expf(s - o0.rec.y) * o0.rec.z;
     const float dz = z > 0.f ? 1.f : slope;
-    const float w_lane = alpha * o0.amul;
+    const float am0 = o0.multiplier();
+    const float w_lane = alpha * am0;
     float d_lane = 0.f;
 
     int e = 0;
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB_BWD) gat_bwd_src_
       consume(x, my < cnt ? ww : 0.f, e, d_lane);
     }
     // d_lane = <src_scale*ft[u], g'[v]>; softmax + leaky_relu adjoint (App. A.3)
-    const float gz = alpha * (d_lane * o0.amul - o0.rec.w) * dz;
+    const float gz = alpha * (d_lane * am0 - o0.rec.w) * dz;
     if (gz_h && lane < cnt) gz_h[base + lane] = gz;
     if (gze_h && lane < cnt) gze_h[(int64_t)k0 * H] = gz;
     gel_lane += gz;

@@ -97,20 +97,24 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB) gat_fwd_kernel(c
     }
   };
   // raw loaded values only: any arithmetic on them here would stall on the load just issued and undo the pipeline
-  struct Ops { float el, eb, cs, am; unsigned keep; };
+  // Raw operands of one chunk, combined one iteration later.  Every field has ONE producer: a default written
+  // before the loads and at most one predicated load.  (With an if / else-if chain ptxas puts the default into the
+  // else branch BEHIND the load; that MOV then waits on the scoreboard slot the freshly issued loads share —
+  // 12 % of the kernel's stall samples in profiles/r01_g.)
+  struct Ops { float el, eb, ee, cs, am, ame, amp; unsigned keep; };
   auto load_operands = [&](int base, int u, int k, Ops& o) {
     const int pos = base + lane;
     o.el = -INFINITY;  // lane past the row end: logit -inf, weight 0
-    o.eb = 0.f; o.cs = 1.f; o.am = 1.f; o.keep = 1u;
+    o.eb = 0.f; o.ee = 0.f; o.cs = 1.f; o.am = 1.f; o.ame = 1.f; o.amp = 1.f; o.keep = 1u;
     if (pos < end) {
       o.el = __ldg(el_h + (int64_t)u * H);
       if (eb_h) o.eb = __ldg(eb_h + pos);
-      else if (ee_h) o.eb = __ldg(ee_h + (int64_t)k * H);
+      if (ee_h) o.ee = __ldg(ee_h + (int64_t)k * H);
       if (keep) o.keep = __ldg(keep + k);
       if (cs) o.cs = __ldg(cs + u);
       if (am_h) o.am = __ldg(am_h + pos);
-      else if (amul_h) o.am = __ldg(amul_h + (int64_t)k * H);
-      else if (philox) o.am = philox_dropout_mul(p.seed, (uint32_t)k, (uint32_t)h, p.attn_p, p.inv_keep);
+      if (amul_h) o.ame = __ldg(amul_h + (int64_t)k * H);
+      if (philox) o.amp = philox_dropout_mul(p.seed, (uint32_t)k, (uint32_t)h, p.attn_p, p.inv_keep);
     }
   };
   int u0, u1, u2 = 0, k0, k1, k2 = 0;
@@ -126,8 +130,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB) gat_fwd_kernel(c
     load_operands(base + 32, u1, k1, o1);
 
     // ---- online softmax on chunk c ----
-    const float z0 = o0.keep ? o0.el + er_v + o0.eb : -INFINITY;
-    const float mul0 = o0.cs * o0.am;
+    const float z0 = o0.keep ? o0.el + er_v + (o0.eb + o0.ee) : -INFINITY;
+    const float mul0 = o0.cs * (o0.am * o0.ame * o0.amp);
     const float s = leaky_relu(z0, slope);  // -inf stays -inf (dropped edge / lane past the row end)
     const float m_new = fmaxf(m, warp_max(s));
     if (m_new > m) {

@@ -55,7 +55,14 @@ struct BwdParams {
 
 struct SrcOps {
   float4 rec;  // {er[v], row_max[v], 1/row_sum[v], t[v]}
-  float eb, amul;
+  // raw loads, combined one pipeline stage later by logit_term(): consuming a load where it is issued would
+  // stall the warp there (even a predicated-off FADD waits for its source register)
+  // every field has one producer (a default written before the loads + at most one predicated load): an
+  // if / else-if chain would leave a default MOV behind the loads that waits on their scoreboard slot
+  float eb, ee, amul, ame, amp;
+  int kp;
+  __device__ __forceinline__ float logit_term() const { return kp ? eb + ee : -INFINITY; }
+  __device__ __forceinline__ float multiplier() const { return amul * ame * amp; }
 };
 
 // Low-degree graphs (average row shorter than one 32-neighbour chunk and a half) use the group-per-row kernels
