@@ -551,3 +551,60 @@ def test_partitioned_layer_on_gpu(cuda):
             assert x.grad.shape == y.grad.shape and rel_err(x.grad, y.grad) <= 1e-4
     finally:
         dist.destroy_process_group()
+
+
+def test_full_size_properties(cuda):
+    """BASELINE.json's north-star size (proteins shape: N = 132,534, E = 39,561,252, H = 6, D = 80, edge logits,
+    edge_drop 0.1) is beyond the oracle; size-independent properties instead:
+      1. ft = 1  ->  every row with a kept in-edge sums its attention to 1
+      2. the layer is linear in ft for fixed logits
+      3. adjoint identity <gout, out(ft)> == <grad_ft, ft>  (backward gather against forward gather)
+      4. dropped edges receive exactly zero grad_ee; reruns are bit-identical"""
+    import bot_b200
+    from bot_b200.functional import edge_drop_keep, gat_fused
+
+    N, E, H, D = 132534, 39561252, 6, 80
+    g = torch.Generator(device=cuda).manual_seed(0)
+    src = torch.randint(0, N, (E,), device=cuda, generator=g)
+    dst = torch.randint(0, N, (E,), device=cuda, generator=g)
+    graph = bot_b200.Graph(src, dst, N)
+    el = torch.randn(N, H, device=cuda, generator=g).requires_grad_(True)
+    er = torch.randn(N, H, device=cuda, generator=g).requires_grad_(True)
+    ee = torch.randn(E, 8, device=cuda, generator=g).requires_grad_(True)
+    keep = edge_drop_keep(E, int(E * 0.1), 7, cuda)
+    assert int(keep.sum()) == E - int(E * 0.1)
+
+    def layer(ft):
+        return gat_fused(graph, ft, el, er, ee, keep)
+
+    # 1. rows sum to one
+    kept_in = torch.zeros(N, device=cuda).index_add_(0, dst, keep.float())
+    ones = layer(torch.ones(N, H, D, device=cuda)).detach()
+    has = kept_in > 0
+    assert float((ones[has] - 1.0).abs().max()) <= 2e-5
+    assert float(ones[~has].abs().max() if (~has).any() else 0.0) == 0.0
+    del ones
+    # 2. linearity
+    f1 = torch.randn(N, H, D, device=cuda, generator=g)
+    f2 = torch.randn(N, H, D, device=cuda, generator=g)
+    o1, o2 = layer(f1).detach(), layer(f2).detach()
+    o12 = layer(0.5 * f1 - 2.0 * f2).detach()
+    assert rel_err(o12, 0.5 * o1 - 2.0 * o2) <= FWD_TOL
+    del o2, o12, f2
+    # 3. adjoint identity, 4. dropped edges, determinism
+    ft = f1.requires_grad_(True)
+    gout = torch.randn(N, H, D, device=cuda, generator=g)
+    out = layer(ft)
+    out.backward(gout)
+    lhs = float((gout.double() * out.detach().double()).sum())
+    rhs = float((ft.grad.double() * ft.detach().double()).sum())
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), 1.0)
+    assert float(ee.grad[keep == 0].abs().max()) == 0.0 and float(ee.grad[:, H:].abs().max()) == 0.0
+    assert torch.isfinite(ee.grad).all() and torch.isfinite(el.grad).all() and torch.isfinite(er.grad).all()
+    first = (out.detach().clone(), ft.grad.clone(), el.grad.clone(), er.grad.clone(), ee.grad.clone())
+    for t in (ft, el, er, ee):
+        t.grad = None
+    out2 = layer(ft)
+    out2.backward(gout)
+    again = (out2.detach(), ft.grad, el.grad, er.grad, ee.grad)
+    assert all(torch.equal(a, b) for a, b in zip(first, again))
