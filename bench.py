@@ -416,8 +416,59 @@ def run_ours(args):
         del conv, h_host, fe_host
         torch.cuda.empty_cache()
     else:
-        e2e = {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-               "note": "end-to-end host-buffer leg is measured at N=1 only; at N>1 this repeats the device-resident value"}
+        # the same layer call as at N=1, partitioned: every rank feeds ITS shard — the node features of its owned rows and
+        # the edge features of its local edges — from pinned host memory through bot_b200.HostFeed, runs the node-side
+        # projections on its rows, the partitioned sparse section (halo all-gather / reduce-scatter inside), all-reduces
+        # the weight gradients and reads its loss back
+        from bot_b200.functional import edge_logits
+
+        torch.manual_seed(0)
+        conv = GATConv(HEADS * HID, EDGE_EMB, HID, n_heads=HEADS, edge_drop=EDGE_DROP).to(dev)   # same weights everywhere
+        conv.train()
+        host_shard = [torch.randn(n_own, HEADS * HID).pin_memory(), torch.randn(E_local, EDGE_EMB).pin_memory()]
+        h2d_rank = sum(t.numel() * 4 for t in host_shard)
+        params = [p for p in conv.parameters()]
+
+        def run_fed_ranks(k):
+            feed = bot_b200.HostFeed(dev, depth=2)
+            feed.submit(*host_shard)
+            for i in range(k):
+                if i + 1 < k:
+                    feed.submit(*host_shard)
+                x, fe = (d.wait() for d in feed.take(requires_grad=(0, 1)))
+                ft = conv.src_fc(x).view(-1, HEADS, HID)
+                resid = conv.dst_fc(x).view(-1, HEADS, HID)
+                el, er = conv.attn_src_fc(x), conv.attn_dst_fc(x)
+                ee = edge_logits(fe, conv.attn_edge_fc.weight)
+                keep = functional.edge_drop_keep(E_local, int(E_local * EDGE_DROP), next(seeds), dev)
+                y = layer.gat(ft, el, er, ee, keep, None, None, None, SLOPE, 0.0, 0) + resid
+                loss = y.square().mean()
+                loss.backward()
+                flat = torch.cat([p.grad.flatten() for p in params])
+                dist.all_reduce(flat)                      # data-parallel weight gradients
+                conv.zero_grad(set_to_none=True)
+                float(loss.item())  # device -> host read of the step's result
+
+        run_fed_ranks(max(1, min(args.warmup, 3)))
+        k_e2e = max(1, args.steps)
+        barrier()
+        e0.record()
+        run_fed_ranks(k_e2e)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1), float(h2d_rank)], device=dev, dtype=torch.float64)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms_e2e = float(tmax[0].item()) / k_e2e
+        e2e = {"value": n_edges / (ms_e2e * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": int(t[1].item()),
+               "d2h_bytes_per_step": 4 * world, "ms_per_step": round(ms_e2e, 3), "steps": k_e2e,
+               "call": "the N=1 layer, partitioned: on every rank nn.Linear projections of its owned rows + "
+                       "bot_b200.partition.PartitionedGraph.gat + residual + backward + all-reduce of the weight gradients; each "
+                       "rank copies its shard (feat_src of its rows, feat_edge of its local edges) from pinned host memory every "
+                       "step through bot_b200.HostFeed (step i+1's copy enqueued before step i's layer) and reads its loss back; "
+                       "max over ranks; h2d bytes summed over ranks"}
+        del host_shard, conv
 
     # secondary number: the same layer on a heavy-tailed graph (dst ~ rank^-0.8; the hottest row has ~2 % of all edges)
     skew = None
