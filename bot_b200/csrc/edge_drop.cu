@@ -126,7 +126,48 @@ __global__ void k_drop_apply(const DropState* __restrict__ st, const uint32_t* _
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < need; i += gridDim.x * blockDim.x) keep[sorted_eid[i]] = 0;
 }
 
+// Small graphs (a partition's local edge set): the undecided candidates fit one block — bitonic sort in shared memory
+// and apply in the same kernel instead of a device-wide radix sort of 64-bit keys (8 passes over a padded buffer).
+constexpr int kSmallCap = 4096;
+__global__ void __launch_bounds__(1024)
+k_drop_sort_apply_small(const DropState* __restrict__ st, const uint64_t* __restrict__ cand_key,
+                        const uint32_t* __restrict__ cand_eid, uint8_t* __restrict__ keep) {
+  __shared__ uint64_t sk[kSmallCap];
+  __shared__ uint32_t sv[kSmallCap];
+  const uint32_t n = min(st->n_cand, (uint32_t)kSmallCap), need = min(st->need, n);
+  int m = 2;  // sort the next power of two >= n only
+  while (m < (int)n) m <<= 1;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    sk[i] = i < (int)n ? cand_key[i] : ~0ull;
+    sv[i] = i < (int)n ? cand_eid[i] : 0u;
+  }
+  __syncthreads();
+  for (int k = 2; k <= m; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const bool up = (i & k) == 0;
+          // ties (equal 64-bit keys: practically never) are broken by edge id so that the result is deterministic
+          const bool gt = sk[i] > sk[l] || (sk[i] == sk[l] && sv[i] > sv[l]);
+          if (gt == up) {
+            const uint64_t tk = sk[i]; sk[i] = sk[l]; sk[l] = tk;
+            const uint32_t tv = sv[i]; sv[i] = sv[l]; sv[l] = tv;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (uint32_t i = threadIdx.x; i < need; i += blockDim.x) keep[sv[i]] = 0;
+}
+
+// the one-block path is taken when twice the expected population of a digit (mean E/4096, standard deviation
+// sqrt(mean): 2x is > 40 sigma away) still fits it, i.e. up to 8.4 M edges
+static inline bool drop_small(int64_t n_edges) { return (n_edges >> (kDropBits - 1)) <= kSmallCap; }
+
 static inline uint32_t drop_cap(int64_t n_edges) {  // 8x the expected population of one digit, at least 64k
+  if (drop_small(n_edges)) return kSmallCap;
   return (uint32_t)std::max<int64_t>(65536, n_edges >> (kDropBits - 3));
 }
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -179,16 +220,22 @@ extern "C" int botgat_edge_drop_draw(int64_t n_edges, int64_t n_drop, uint64_t s
   uint64_t* key_out = (uint64_t*)(ws + L.key_out);
   uint32_t* eid_in = (uint32_t*)(ws + L.eid_in);
   uint32_t* eid_out = (uint32_t*)(ws + L.eid_out);
+  const bool small = drop_small(n_edges);
   BG_CHECK(cudaMemsetAsync(ws, 0, L.key_in, st));                                    // histogram + state
-  BG_CHECK(cudaMemsetAsync(key_in, 0xFF, sizeof(uint64_t) * L.cap, st));             // unused slots sort last
+  if (!small) BG_CHECK(cudaMemsetAsync(key_in, 0xFF, sizeof(uint64_t) * L.cap, st));  // unused slots sort last
   const int64_t n_pairs = (n_edges + 1) >> 1;
-  const int64_t work = (n_pairs + 255) / 256;
+  // at least 16 pairs per thread: every block merges its 4096-bin histogram into the global one
+  const int64_t work = (n_pairs + 256 * 16 - 1) / (256 * 16);
   k_drop_hist<<<resident_grid(k_drop_hist, 256, work), 256, 0, st>>>(n_edges, seed, hist);
   k_drop_pick<<<1, 1024, 0, st>>>(hist, n_drop, state);
   k_drop_mark<<<resident_grid(k_drop_mark, 256, work), 256, 0, st>>>(n_edges, seed, state, keep, key_in, eid_in, L.cap);
-  size_t cub_bytes = L.cub_bytes;
-  BG_CHECK(cub::DeviceRadixSort::SortPairs(ws + L.cub, cub_bytes, key_in, key_out, eid_in, eid_out, (int)L.cap, 0, 64, st));
-  k_drop_apply<<<64, 256, 0, st>>>(state, eid_out, keep);
+  if (small) {
+    k_drop_sort_apply_small<<<1, 1024, 0, st>>>(state, key_in, eid_in, keep);
+  } else {
+    size_t cub_bytes = L.cub_bytes;
+    BG_CHECK(cub::DeviceRadixSort::SortPairs(ws + L.cub, cub_bytes, key_in, key_out, eid_in, eid_out, (int)L.cap, 0, 64, st));
+    k_drop_apply<<<64, 256, 0, st>>>(state, eid_out, keep);
+  }
   BG_LAUNCHED(4);
   BG_CHECK(cudaGetLastError());
   return 0;

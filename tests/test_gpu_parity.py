@@ -327,7 +327,8 @@ def test_edge_embedding_fused_equals_materialised(cuda):
 
 
 @pytest.mark.parametrize("E,n_drop,seed", [(1, 0, 1), (1, 1, 2), (2, 1, 3), (1001, 370, 4), (100000, 10000, 5),
-                                           (3000001, 300000, 6), (50000, 49999, 7), (50000, 1, (1 << 61) + 12345)])
+                                           (3000001, 300000, 6), (50000, 49999, 7), (50000, 1, (1 << 61) + 12345),
+                                           (9000001, 900000, 8)])
 def test_edge_drop_draw_exact(cuda, E, n_drop, seed):
     """botgat_edge_drop_draw: exactly n_drop zeros, bit-identical to 'drop the n_drop smallest Philox keys'."""
     from bot_b200.functional import edge_drop_keep
