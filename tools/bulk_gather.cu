@@ -37,6 +37,44 @@ k_gather_ldg(const float* __restrict__ table, int ld, int n_vec, const int* __re
   if (acc.x + acc.y + acc.z + acc.w == 123456.f) *sink = acc.x;
 }
 
+// 256-bit loads (LDG.E.ENL2.256): 4 lanes per 128-byte line, 3 slots cover the 320-byte row, 8 rows per step, 2 steps in flight
+__global__ void __launch_bounds__(kWarps * 32, 4)
+k_gather_ldg256(const float* __restrict__ table, int ld, int n_vec8, const int* __restrict__ idx, int64_t n_idx, float* sink) {
+  const int lane = threadIdx.x & 31, grp = lane >> 2, l4 = lane & 3;
+  const int64_t warp = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * kWarps;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int64_t base = warp * 32; base < n_idx; base += n_warps * 32) {
+    const int mine = base + lane < n_idx ? __ldg(idx + base + lane) : 0;
+#pragma unroll
+    for (int e = 0; e < 32; e += 16) {
+      float x[2][3][8];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int r = __shfl_sync(0xffffffffu, mine, e + s * 8 + grp);
+        const float* p = table + (int64_t)r * ld;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float* q = p + 8 * min(l4 + 4 * i, n_vec8 - 1);
+          asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=f"(x[s][i][0]), "=f"(x[s][i][1]), "=f"(x[s][i][2]), "=f"(x[s][i][3]), "=f"(x[s][i][4]),
+                         "=f"(x[s][i][5]), "=f"(x[s][i][6]), "=f"(x[s][i][7])
+                       : "l"(q));
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[c] += x[s][i][c];
+    }
+  }
+  float t = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) t += acc[c];
+  if (t == 123456.f) *sink = t;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ROWS rows per stage, STAGES stages per warp
@@ -123,6 +161,15 @@ extern "C" __attribute__((visibility("default"))) double gather_ms(const float* 
     k_gather_ldg<<<blocks, kWarps * 32>>>(table, ld, row_floats / 4, idx, n_idx, sink);
     cudaEventRecord(e0);
     k_gather_ldg<<<blocks, kWarps * 32>>>(table, ld, row_floats / 4, idx, n_idx, sink);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1);
+  } else if (variant == 4) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k_gather_ldg256<<<blocks, kWarps * 32>>>(table, ld, row_floats / 8, idx, n_idx, sink);
+    cudaEventRecord(e0);
+    k_gather_ldg256<<<blocks, kWarps * 32>>>(table, ld, row_floats / 8, idx, n_idx, sink);
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     cudaEventElapsedTime(&ms, e0, e1);
