@@ -29,13 +29,26 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # The contract is ONE JSON line on stdout, but libraries print there too (NCCL's version banner: this image sets
-# NCCL_DEBUG=VERSION).  File descriptor 1 is pointed at stderr for the whole run; the JSON line goes to the real stdout.
-_REAL_STDOUT = os.dup(1)
-os.dup2(2, 1)
+# NCCL_DEBUG=VERSION).  main() points file descriptor 1 at stderr for the whole run; the JSON line goes to the real stdout.
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Called by main() only (importing this module for its constants must not touch the caller's stdout)."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
 
 
 def emit(line):
-    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+    text = json.dumps(line) + "\n"
+    if _REAL_STDOUT is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, text.encode())
 
 
 import torch  # noqa: E402
@@ -528,6 +541,7 @@ def run_ours(args):
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

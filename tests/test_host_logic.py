@@ -176,3 +176,17 @@ def test_edge_drop_restatement_counts():
         assert int(keep.sum()) == E - n_drop
     a, b = philox_edge_drop_keep(1, 5000, 500), philox_edge_drop_keep(2, 5000, 500)
     assert not torch.equal(a, b)
+
+
+def test_bench_algorithmic_bytes_match_survey():
+    """1,983 B/edge forward and 3,996 B/edge backward at the proteins shape (the figure
+    `roofline.achieved` is computed from), 78.4 + 158.1 GB per layer."""
+    import bench
+
+    E, N, H, D = 39561252, 132534, 6, 80
+    bf, bb = bench.algorithmic_bytes(E, N, N, H, D)
+    assert round(bf / E) == 1983 and round(bb / E) == 3996
+    assert abs(bf / 1e9 - 78.4) < 0.1 and abs(bb / 1e9 - 158.1) < 0.1
+    # products shape (no edge features): 2,018 + 4,148 B/edge
+    bf, bb = bench.algorithmic_bytes(61859140, 2449029, 2449029, 4, 120, er=True, ee=False)
+    assert abs(bf / 61859140 - 2018) < 1.5 and abs(bb / 61859140 - 4148) < 2.5
