@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BOTGAT_LIB") or os.path.join(_HERE, "libbotgat.so")  # BOTGAT_LIB: developer A/B builds
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_i64p = C.POINTER(C.c_int64)
 c_vp = C.c_void_p
@@ -38,6 +38,7 @@ class FwdArgs(C.Structure):
         ("am", c_vp), ("ee", c_vp), ("keep", c_vp), ("attn_mul", c_vp), ("src_scale", c_vp), ("dst_scale", c_vp),
         ("slope", C.c_float), ("attn_p", C.c_float), ("seed", C.c_uint64),
         ("out", c_vp), ("row_max", c_vp), ("row_sum", c_vp), ("scratch", c_vp),
+        ("h_begin", C.c_int32), ("h_count", C.c_int32),
     ]
 
 
@@ -52,6 +53,7 @@ class BwdArgs(C.Structure):
         ("out", c_vp), ("row_max", c_vp), ("row_sum", c_vp), ("gout", c_vp),
         ("drec", c_vp), ("gprime", c_vp), ("scratch", c_vp), ("gz", c_vp),
         ("grad_ft", c_vp), ("grad_el", c_vp), ("grad_ee", c_vp), ("ld_gee", C.c_int64), ("grad_er", c_vp),
+        ("h_begin", C.c_int32), ("h_count", C.c_int32),
     ]
 
 

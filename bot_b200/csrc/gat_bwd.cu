@@ -76,8 +76,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB_BWD) gat_bwd_src_
   constexpr int GSTRIDE = G * VW;
   constexpr bool kPacked = NS > 1 && NS <= G && (NS & (NS - 1)) == 0;  // packed dot-product reduction usable
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.x / p.blocks_per_slab;
-  const int item = (blockIdx.x - h * p.blocks_per_slab) * kWarpsPerBlock + warp;
+  const int hl = blockIdx.x / p.blocks_per_slab;  // head within this launch's range
+  const int h = hl + p.h_begin;
+  const int item = (blockIdx.x - hl * p.blocks_per_slab) * kWarpsPerBlock + warp;
   if (item >= p.n_items) return;
   const int row = p.seg_row ? p.seg_row[item] : item;
   const int slot = p.seg_row ? p.seg_slot[item] : -1;
@@ -362,7 +363,11 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
     p.seg_row = split ? seg.row : nullptr; p.seg_beg = seg.beg; p.seg_end = seg.end; p.seg_slot = seg.slot;
     p.n_items = split ? seg.n_items : p.n_rows; p.scratch = a->scratch;
     p.blocks_per_slab = (p.n_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    const int64_t nblocks = (int64_t)p.blocks_per_slab * a->H;
+    p.h_begin = a->h_begin;
+    p.h_count = a->h_count > 0 ? a->h_count : a->H - a->h_begin;
+    BG_REQUIRE(p.h_begin >= 0 && p.h_count > 0 && p.h_begin + p.h_count <= a->H, "backward: bad head range [%d, +%d) of %d", a->h_begin, a->h_count, a->H);
+    BG_REQUIRE(!split || p.h_count == a->H, "backward: a graph with split rows needs the full head range");
+    const int64_t nblocks = (int64_t)p.blocks_per_slab * p.h_count;
     BG_REQUIRE(nblocks < (1ll << 31), "backward: grid too large");
     int rc = lowdeg ? launch_src_lowdeg(p, t, st) : launch_src(p, t, dim3((unsigned)nblocks), st);
     if (rc) return rc;

@@ -43,8 +43,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB) gat_fwd_kernel(c
   // work item = a whole row, or one segment of a heavy row (segments.cu)
   const int row = p.seg_row ? p.seg_row[item] : item;
   const int slot = p.seg_row ? p.seg_slot[item] : -1;
-  const int h = slab / p.col_parts;
-  const int cp = slab - h * p.col_parts;
+  const int hl = slab / p.col_parts;  // head within this launch's range
+  const int h = hl + p.h_begin;
+  const int cp = slab - hl * p.col_parts;
   const int c0 = cp * p.part_cols;
   const int nv = (min(p.D - c0, p.part_cols) + VW - 1) / VW;  // vectors in this slab row
   const int grp = lane >> GSH;
@@ -268,7 +269,11 @@ extern "C" int botgat_gat_forward(const botgat_graph* g, const botgat_fwd_args* 
   p.seg_row = split ? seg.row : nullptr; p.seg_beg = seg.beg; p.seg_end = seg.end; p.seg_slot = seg.slot;
   p.n_items = split ? seg.n_items : p.n_rows; p.scratch = a->scratch;
   p.blocks_per_slab = (p.n_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  const int64_t nblocks = (int64_t)p.blocks_per_slab * a->H * t.col_parts;
+  p.h_begin = a->h_begin;
+  p.h_count = a->h_count > 0 ? a->h_count : a->H - a->h_begin;
+  BG_REQUIRE(p.h_begin >= 0 && p.h_count > 0 && p.h_begin + p.h_count <= a->H, "forward: bad head range [%d, +%d) of %d", a->h_begin, a->h_count, a->H);
+  BG_REQUIRE(!split || p.h_count == a->H, "forward: a graph with split rows needs the full head range");
+  const int64_t nblocks = (int64_t)p.blocks_per_slab * p.h_count * t.col_parts;
   BG_REQUIRE(nblocks < (1ll << 31), "forward: grid too large");
   int rc;
   if (lowdeg)

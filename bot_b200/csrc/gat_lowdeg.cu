@@ -56,12 +56,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB) gat_fwd_lowdeg_k
   const int gw = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int slab = gw / warps_per_slab;
   const int wrow = gw - slab * warps_per_slab;
-  if (slab >= p.H * p.col_parts) return;
+  if (slab >= p.h_count * p.col_parts) return;
   const int j = lane & (G - 1), gbase = lane & ~(G - 1);
   const int row = wrow * RPW + (lane >> GSH);
   const bool valid = row < p.n_rows;
-  const int h = slab / p.col_parts;
-  const int cp = slab - h * p.col_parts;
+  const int hl = slab / p.col_parts;  // head within this launch's range
+  const int h = hl + p.h_begin;
+  const int cp = slab - hl * p.col_parts;
   const int c0 = cp * p.part_cols;
   const int nv = (min(p.D - c0, p.part_cols) + VW - 1) / VW;
   const int v0 = j - (((h * p.D + c0) / VW) & p.omask);
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB) gat_fwd_lowdeg_k
 int launch_fwd_lowdeg(const FwdParams& p, const Tiling& t, cudaStream_t st) {
   const int rpw = 32 >> t.gshift;
   const int warps_per_slab = (p.n_rows + rpw - 1) / rpw;
-  const int64_t warps = (int64_t)warps_per_slab * p.H * p.col_parts;
+  const int64_t warps = (int64_t)warps_per_slab * p.h_count * p.col_parts;
   const int64_t nblocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
   if (nblocks >= (1ll << 31)) { set_error("forward: grid too large"); return -1; }
   dim3 grid((unsigned)nblocks), block(kWarpsPerBlock * 32);
@@ -220,9 +221,10 @@ gat_bwd_src_lowdeg_kernel(const BwdParams p, int warps_per_slab) {
   constexpr bool kPacked = NS > 1 && NS <= G && (NS & (NS - 1)) == 0;
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  const int h = gw / warps_per_slab;
-  const int wrow = gw - h * warps_per_slab;
-  if (h >= p.H) return;
+  const int hl = gw / warps_per_slab;  // head within this launch's range
+  const int wrow = gw - hl * warps_per_slab;
+  if (hl >= p.h_count) return;
+  const int h = hl + p.h_begin;
   const int j = lane & (G - 1), gbase = lane & ~(G - 1);
   const int row = wrow * RPW + (lane >> GSH);
   const bool valid = row < p.n_rows;
@@ -384,7 +386,7 @@ gat_bwd_src_lowdeg_kernel(const BwdParams p, int warps_per_slab) {
 int launch_src_lowdeg(const BwdParams& p, const Tiling& t, cudaStream_t st) {
   const int rpw = 32 >> t.gshift;
   const int warps_per_slab = (p.n_rows + rpw - 1) / rpw;
-  const int64_t warps = (int64_t)warps_per_slab * p.H;
+  const int64_t warps = (int64_t)warps_per_slab * p.h_count;
   const int64_t nblocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
   if (nblocks >= (1ll << 31)) { set_error("backward: grid too large"); return -1; }
   dim3 grid((unsigned)nblocks), block(kWarpsPerBlock * 32);

@@ -21,6 +21,7 @@ struct FwdParams {
   float *out, *row_max, *row_sum;
   int col_parts, part_cols, omask;
   int blocks_per_slab;
+  int h_begin, h_count;  // head range of this launch
   // row splitting (segments.cu): work items are segments when seg_row != nullptr
   const int32_t *seg_row, *seg_beg, *seg_end, *seg_slot;
   int n_items;
@@ -48,6 +49,7 @@ struct BwdParams {
   float *grad_ft, *grad_el, *gz;
   int omask;
   int blocks_per_slab;
+  int h_begin, h_count;  // head range of this launch
   const int32_t *seg_row, *seg_beg, *seg_end, *seg_slot;
   int n_items;
   float* scratch;

@@ -201,9 +201,14 @@ def _forward_core(graph, ft2d, H, D, el, er, ee, ld_ee, keep, attn_mul, ld_am, s
         a.scratch = scratch.data_ptr()
     if hooks is not None and hooks.pre_kernel is not None:
         hooks.pre_kernel()  # e.g. wait for an asynchronous halo all-gather that fills ft / el
-    with _span("gat_fwd"):
-        rc = lib.botgat_gat_forward(h, C.byref(a), _stream())
-    _lib.check(rc, "botgat_gat_forward")
+    chunks = hooks.head_chunks if hooks is not None and hooks.head_chunks else [(0, H)]
+    for i, (hb, hc) in enumerate(chunks):   # one launch per head range: a caller can feed ft head by head
+        if len(chunks) > 1 and hooks.pre_head is not None:
+            hooks.pre_head(i)
+        a.h_begin, a.h_count = hb, hc
+        with _span("gat_fwd"):
+            rc = lib.botgat_gat_forward(h, C.byref(a), _stream())
+        _lib.check(rc, "botgat_gat_forward")
     return out, row_max, row_sum, pre, float(a.attn_p)
 
 
@@ -259,7 +264,23 @@ def _backward_core(graph, cfg, pre, hooks, ft2d, el, er, ee, keep, attn_mul, src
     a.grad_ft, a.grad_el, a.grad_ee, a.grad_er = grad_ft2d.data_ptr(), grad_el.data_ptr(), p(grad_ee), p(grad_er)
     a.ld_gee = grad_ee.stride(0) if grad_ee is not None else 0
     post_src = hooks.post_src if hooks is not None else None
-    if timer is None and post_src is None:
+    chunks = hooks.head_chunks if hooks is not None and hooks.head_chunks else None
+    if chunks is not None and len(chunks) > 1:
+        # src phase head range by head range; the caller's hook ships each range's grad_ft while the next one runs
+        a.phases = 1
+        _lib.check(lib.botgat_gat_backward(h, C.byref(a), _stream()), "botgat_gat_backward")
+        for i, (hb, hc) in enumerate(chunks):
+            a.phases, a.h_begin, a.h_count = 2, hb, hc
+            with _span("gat_bwd_src"):
+                rc = lib.botgat_gat_backward(h, C.byref(a), _stream())
+            _lib.check(rc, "botgat_gat_backward")
+            if hooks.post_src_head is not None:
+                hooks.post_src_head(i, grad_ft2d if hook_grad_ft is None else hook_grad_ft, grad_el)
+        a.phases, a.h_begin, a.h_count = 4, 0, 0
+        with _span("gat_bwd_edge"):
+            rc = lib.botgat_gat_backward(h, C.byref(a), _stream())
+        _lib.check(rc, "botgat_gat_backward")
+    elif timer is None and post_src is None:
         _lib.check(lib.botgat_gat_backward(h, C.byref(a), _stream()), "botgat_gat_backward")
     elif timer is None:
         a.phases = 3
@@ -571,8 +592,11 @@ class Hooks:
     ``pre_kernel()`` runs after edge staging, right before the forward gather kernel is launched;
     ``post_src(grad_ft, grad_el)`` runs in backward after the src pass, before the edge phase."""
 
-    def __init__(self, pre_kernel=None, post_src=None):
+    def __init__(self, pre_kernel=None, post_src=None, head_chunks=None, pre_head=None, post_src_head=None):
         self.pre_kernel, self.post_src = pre_kernel, post_src
+        # optional head pipelining: ``head_chunks`` = [(h_begin, h_count), ...]; ``pre_head(i)`` runs before the forward
+        # launch of chunk i, ``post_src_head(i, grad_ft, grad_el)`` after the backward src launch of chunk i
+        self.head_chunks, self.pre_head, self.post_src_head = head_chunks, pre_head, post_src_head
 
 
 def gat_fused(graph, ft, el, er=None, ee=None, keep=None, attn_mul=None, src_scale=None, dst_scale=None,

@@ -22,6 +22,8 @@ result" and the partition maps are bit-exact against ``oracle/graph_ref.py``.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -86,9 +88,42 @@ class _DenseHaloAsync(torch.autograd.Function):
         return out, None, None, None
 
 
+class _DenseHaloHeads(torch.autograd.Function):
+    """`_DenseHaloAsync` for a (rows, H, D) table shipped one head range at a time: the forward starts one
+    all-gather per range (``state.fwd_chunks``; the layer's ``pre_head`` hook waits for range i and copies it into
+    place right before the kernel launch of range i, so range i+1 travels while range i is computed); the backward
+    collects the per-range reduce-scatters the ``post_src_head`` hook started (``state.bwd_chunks``)."""
+
+    @staticmethod
+    def forward(ctx, shard, group, state, chunks):
+        world = dist.get_world_size(group)
+        ctx.group, ctx.state, ctx.chunks, ctx.shard_shape = group, state, chunks, tuple(shard.shape)
+        state.out = shard.new_empty((world * shard.shape[0],) + tuple(shard.shape[1:]))
+        state.fwd_chunks, state.bwd_chunks = [], []
+        for hb, hc in chunks:
+            piece = shard[:, hb:hb + hc].contiguous()
+            buf = shard.new_empty((world * shard.shape[0], hc) + tuple(shard.shape[2:]))
+            work = dist.all_gather_into_tensor(buf, piece, group=group, async_op=True)
+            state.fwd_chunks.append((work, buf))
+        return state.out
+
+    @staticmethod
+    def backward(ctx, grad):
+        st, world = ctx.state, dist.get_world_size(ctx.group)
+        res = grad.new_empty(ctx.shard_shape)
+        if len(st.bwd_chunks) == len(ctx.chunks):
+            for (hb, hc), (work, piece) in zip(ctx.chunks, st.bwd_chunks):
+                work.wait()
+                res[:, hb:hb + hc] = piece
+        else:  # the hooks did not run (plain autograd use): one reduce-scatter of the whole gradient
+            dist.reduce_scatter_tensor(res, grad.contiguous(), op=dist.ReduceOp.SUM, group=ctx.group)
+        return res, None, None, None
+
+
 class _HaloState:
     def __init__(self):
         self.fwd, self.bwd = {}, {}
+        self.out, self.fwd_chunks, self.bwd_chunks = None, [], []
 
 
 class _SparseHalo(torch.autograd.Function):
@@ -131,6 +166,8 @@ class PartitionedGraph:
 
     def __init__(self, src, dst, n_nodes, world=None, rank=None, group=None, plan="auto", build_graph=True):
         self.group = group
+        # per-head pipelining of the halo exchange in `gat` (see _gat_head_pipelined); opt-in until measured at N = 8
+        self.pipeline_heads = os.environ.get("BOTGAT_PIPE_HEADS", "0") == "1"
         self.world = dist.get_world_size(group) if world is None else world
         self.rank = dist.get_rank(group) if rank is None else rank
         self.n_nodes = n_nodes
@@ -219,6 +256,8 @@ class PartitionedGraph:
             ft_all, el_all = self.halo_gather(ft_own, el_own)
             return gat_fused(self.local, ft_all, el_all, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed)
         st = _HaloState()
+        if self.pipeline_heads and ft_own.dim() == 3 and ft_own.shape[1] > 1:
+            return self._gat_head_pipelined(st, ft_own, el_own, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed)
         ft_all = _DenseHaloAsync.apply(self._pad(ft_own), self.group, st, "ft")
         el_all = _DenseHaloAsync.apply(self._pad(el_own), self.group, st, "el")
 
@@ -235,6 +274,39 @@ class PartitionedGraph:
         out = gat_fused(self.local, ft_all, el_all, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed,
                         hooks=Hooks(pre_kernel, post_src))
         return out
+
+    def _gat_head_pipelined(self, st, ft_own, el_own, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed):
+        """`gat` with the feature exchange pipelined per head against per-head kernel launches (the kernels work
+        head-major): all-gather of head h+1 || forward kernel of head h; backward src kernel of head h+1 ||
+        reduce-scatter of head h's grad_ft.  Opt-in (``pipeline_heads`` / BOTGAT_PIPE_HEADS=1)."""
+        from .functional import Hooks, gat_fused
+
+        H = ft_own.shape[1]
+        chunks = [(h, 1) for h in range(H)]
+        ft_all = _DenseHaloHeads.apply(self._pad(ft_own), self.group, st, chunks)
+        el_all = _DenseHaloAsync.apply(self._pad(el_own), self.group, st, "el")
+
+        def pre_head(i):
+            if i == 0:
+                st.fwd.pop("el").wait()
+            work, buf = st.fwd_chunks[i]
+            work.wait()
+            hb, hc = chunks[i]
+            st.out[:, hb:hb + hc].copy_(buf)
+
+        def post_src_head(i, grad_ft, grad_el):
+            hb, hc = chunks[i]
+            g = grad_ft[:, hb:hb + hc].contiguous()
+            piece = g.new_empty((g.shape[0] // self.world,) + tuple(g.shape[1:]))
+            work = dist.reduce_scatter_tensor(piece, g, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            st.bwd_chunks.append((work, piece))
+            if i == len(chunks) - 1:
+                out = grad_el.new_empty((grad_el.shape[0] // self.world,) + tuple(grad_el.shape[1:]))
+                w = dist.reduce_scatter_tensor(out, grad_el, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                st.bwd["el"] = (w, out)
+
+        return gat_fused(self.local, ft_all, el_all, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed,
+                         hooks=Hooks(head_chunks=chunks, pre_head=pre_head, post_src_head=post_src_head))
 
     def owned_slice(self, full_table):
         """Rows of a replicated (N, ...) table this rank owns."""

@@ -31,7 +31,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define BOTGAT_ABI_VERSION 1
+#define BOTGAT_ABI_VERSION 2
 
 typedef struct botgat_graph botgat_graph;
 
@@ -218,6 +218,10 @@ typedef struct {
   float* row_max;         /* (n_dst, H)  saved for backward */
   float* row_sum;         /* (n_dst, H)  saved for backward */
   float* scratch;         /* forward scratch (see botgat_graph_info), or NULL when n_slots_in == 0 */
+  /* Head range of this launch: heads [h_begin, h_begin + h_count); h_count == 0 = all remaining heads.  All array
+   * arguments keep their full-H meaning.  Lets a caller overlap per-head transfers with per-head launches (the
+   * kernels work head-major anyway).  Graphs with split rows (n_slots_in > 0) need the full range. */
+  int32_t h_begin, h_count;
 } botgat_fwd_args;
 int botgat_gat_forward(const botgat_graph* g, const botgat_fwd_args* a /* HOST */, void* stream);
 
@@ -267,6 +271,8 @@ typedef struct {
   float* grad_ee;         /* (n_edges, ld_gee) edge-id order, or NULL; required when grad_er is requested (its input) */
   int64_t ld_gee;         /* row stride of grad_ee in floats; 0 = H */
   float* grad_er;         /* (n_dst, H) or NULL */
+  /* head range of the src phase (phases & 2), as in botgat_fwd_args; the node and edge phases always cover all heads */
+  int32_t h_begin, h_count;
 } botgat_bwd_args;
 int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args* a /* HOST */, void* stream);
 

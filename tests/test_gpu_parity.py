@@ -609,3 +609,32 @@ def test_full_size_properties(cuda):
     out2.backward(gout)
     again = (out2.detach(), ft.grad, el.grad, er.grad, ee.grad)
     assert all(torch.equal(a, b) for a, b in zip(first, again))
+
+
+@pytest.mark.parametrize("name", ["proteins_like_edge_drop", "arxiv_like_H3_D250_symm", "cora_like_H8_D8"])
+def test_head_range_launches(cuda, name):
+    """Forward and backward src phase launched one head range at a time (botgat_*_args.h_begin / h_count, the hook
+    protocol of the head-pipelined halo exchange) give bit-identical results to the single launch."""
+    import bot_b200
+    from bot_b200.functional import Hooks, gat_fused
+
+    n_src, n_dst, e, H, D, kw = CASES[name]
+    c = make_case(n_src, n_dst, e, H, D, seed=3, **kw)
+    g = bot_b200.Graph(c["src"].to(cuda), c["dst"].to(cuda), n_src, n_dst)
+    names = ["ft", "el"] + (["er"] if c.get("er") is not None else []) + (["ee"] if c.get("ee") is not None else [])
+    keep = c["keep"].to(cuda) if c.get("keep") is not None else None
+    cs = c["src_scale"].to(cuda) if c.get("src_scale") is not None else None
+    ds = c["dst_scale"].to(cuda) if c.get("dst_scale") is not None else None
+    seen = []
+    chunks = [(0, 1), (1, H - 1)] if H > 2 else [(h, 1) for h in range(H)]
+    hooks = Hooks(head_chunks=chunks, pre_head=lambda i: seen.append(("f", i)),
+                  post_src_head=lambda i, gft, gel: seen.append(("b", i, tuple(gft.shape))))
+    res = []
+    for hk in (None, hooks):
+        t = {k: c[k].to(cuda).clone().requires_grad_(True) for k in names}
+        am = c["attn_mul"].to(cuda) if c.get("attn_mul") is not None else None
+        out = gat_fused(g, t["ft"], t["el"], t.get("er"), t.get("ee"), keep, am, cs, ds, 0.2, 0.0, 0, hooks=hk)
+        out.backward(c["gout"].to(cuda))
+        res.append([out.detach()] + [t[k].grad for k in names])
+    assert all(torch.equal(a, b) for a, b in zip(*res))
+    assert seen == [("f", i) for i in range(len(chunks))] + [("b", i, (n_src, H, D)) for i in range(len(chunks))]

@@ -114,7 +114,11 @@ def _fake_gat_fused(graph, ft, el, er=None, ee=None, keep=None, attn_mul=None, s
     class Fn(torch.autograd.Function):
         @staticmethod
         def forward(ctx, ft, el, er, ee):
-            hooks.pre_kernel()
+            if hooks.head_chunks:
+                for i in range(len(hooks.head_chunks)):   # the kernels would be launched range by range
+                    hooks.pre_head(i)
+            else:
+                hooks.pre_kernel()
             with torch.enable_grad():
                 ins = [t.detach().requires_grad_(True) for t in (ft, el, er, ee)]
                 out = gat_ref.gat_sparse(lsrc, ldst, n_dst, *ins, keep, attn_mul, slope, src_scale, dst_scale)
@@ -124,13 +128,17 @@ def _fake_gat_fused(graph, ft, el, er=None, ee=None, keep=None, attn_mul=None, s
         @staticmethod
         def backward(ctx, g):
             gft, gel, ger, gee = torch.autograd.grad(ctx.out, ctx.ins, g)
-            hooks.post_src(gft.contiguous(), gel.contiguous())
+            if hooks.head_chunks:
+                for i in range(len(hooks.head_chunks)):
+                    hooks.post_src_head(i, gft.contiguous(), gel.contiguous())
+            else:
+                hooks.post_src(gft.contiguous(), gel.contiguous())
             return gft, gel, ger, gee
 
     return Fn.apply(ft, el, er, ee)
 
 
-def _worker_overlap(rank, world, port, seed, ret):
+def _worker_overlap(rank, world, port, seed, ret, pipeline_heads=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -141,6 +149,7 @@ def _worker_overlap(rank, world, port, seed, ret):
         n, src, dst = _graph(seed)
         pg = PartitionedGraph(src, dst, n, plan="dense", build_graph=False)
         pg.local = (pg.lsrc, pg.ldst, pg.n_own)
+        pg.pipeline_heads = pipeline_heads
         F_.gat_fused = _fake_gat_fused
         H, D = 2, 4
         g = torch.Generator().manual_seed(seed + 100)
@@ -171,13 +180,14 @@ def _worker_overlap(rank, world, port, seed, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_overlapped_layer_equals_single(world):
-    """PartitionedGraph.gat (collectives started asynchronously around the kernels) == single-process result."""
+@pytest.mark.parametrize("world,pipeline_heads", [(2, False), (3, False), (2, True), (3, True)])
+def test_overlapped_layer_equals_single(world, pipeline_heads):
+    """PartitionedGraph.gat (collectives started asynchronously around the kernels; optionally one head range at a
+    time) == single-process result."""
     port = _free_port()
     with mp.Manager() as m:
         ret = m.dict()
-        mp.spawn(_worker_overlap, args=(world, port, 11, ret), nprocs=world, join=True)
+        mp.spawn(_worker_overlap, args=(world, port, 11, ret, pipeline_heads), nprocs=world, join=True)
         assert all(ret.get(r) == "ok" for r in range(world)), dict(ret)
 
 
