@@ -55,6 +55,29 @@ def test_struct_sizes_match_header():
     assert [int(x) for x in out] == [ctypes.sizeof(_lib.FwdArgs), ctypes.sizeof(_lib.BwdArgs), ctypes.sizeof(_lib.GraphInfo)]
 
 
+def test_struct_field_offsets_match_header():
+    """Every field of the ctypes mirrors sits at the offset the C compiler gives it (names, order and types)."""
+    import subprocess
+    import tempfile
+
+    from bot_b200 import _lib
+
+    structs = (("botgat_fwd_args", _lib.FwdArgs), ("botgat_bwd_args", _lib.BwdArgs), ("botgat_graph_info", _lib.GraphInfo))
+    lines = ['#include "botgat.h"', "#include <stddef.h>", "#include <stdio.h>", "int main(){"]
+    for cname, ct in structs:
+        for fname, _ in ct._fields_:
+            lines.append(f'printf("%zu\\n", offsetof({cname}, {fname}));')
+    lines.append("return 0;}")
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "p.c")
+        open(c, "w").write("\n".join(lines))
+        exe = os.path.join(d, "p")
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        got = [int(x) for x in subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()]
+    want = [getattr(ct, fname).offset for _, ct in structs for fname, _ in ct._fields_]
+    assert got == want
+
+
 def test_no_cpu_fallback():
     """Compute entry points refuse CPU tensors instead of silently falling back."""
     import pytest
