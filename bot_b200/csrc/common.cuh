@@ -91,7 +91,10 @@ constexpr unsigned kFull = 0xffffffffu;
 // ---------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float leaky_relu(float z, float slope) { return z > 0.f ? z : z * slope; }
+// -inf (a dropped edge, a lane past the row end) must stay -inf for every slope >= 0: -inf * 0 would be NaN
+__device__ __forceinline__ float leaky_relu(float z, float slope) {
+  return z > 0.f ? z : (z == -INFINITY ? -INFINITY : z * slope);
+}
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll

@@ -320,9 +320,22 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
   const int64_t HD = (int64_t)a->H * a->D;
   BG_REQUIRE(a->ld_ft >= HD && a->ld_out >= HD && a->ld_gft >= HD, "backward: leading dimension < H*D");
   BG_REQUIRE(a->eb_out ? (a->Hb == 1 || a->Hb == a->H) : true, "backward: Hb must be 1 or H");
-  if (g->n_dst == 0 || g->n_src == 0) return 0;
   DeviceGuard guard(g->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (g->n_dst == 0 || g->n_src == 0) {
+    // no destination rows (an empty row range of the 1-D partition still has n_src > 0 halo sources): every gradient
+    // is exactly zero — write the zeros, the caller's buffers are uninitialised and may be reduce-scattered to peers
+    const int ph = a->phases ? a->phases : 7;
+    if ((ph & 2) && g->n_src > 0) {
+      BG_CHECK(cudaMemset2DAsync(a->grad_ft, sizeof(float) * a->ld_gft, 0, sizeof(float) * HD, (size_t)g->n_src, st));
+      BG_CHECK(cudaMemsetAsync(a->grad_el, 0, sizeof(float) * (size_t)g->n_src * a->H, st));
+    }
+    if ((ph & 4) && a->grad_er && g->n_dst > 0)
+      BG_CHECK(cudaMemsetAsync(a->grad_er, 0, sizeof(float) * (size_t)g->n_dst * a->H, st));
+    if ((ph & 4) && a->grad_ee && g->n_edges > 0)
+      BG_CHECK(cudaMemsetAsync(a->grad_ee, 0, sizeof(float) * (size_t)g->n_edges * (a->ld_gee > 0 ? a->ld_gee : a->H), st));
+    return 0;
+  }
   dim3 block(kWarpsPerBlock * 32);
   const int phases = a->phases ? a->phases : 7;
   const int64_t ld_gee = a->ld_gee > 0 ? a->ld_gee : a->H;

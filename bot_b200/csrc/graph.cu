@@ -100,8 +100,11 @@ __global__ void k_narrow_and_check(int64_t n, const int64_t* __restrict__ a, int
                                    int32_t* __restrict__ iota, int* __restrict__ bad) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t v = a[i];
-    if (v < 0 || v >= bound) *bad = 1;
-    out[i] = (int32_t)v;
+    const bool oob = v < 0 || v >= bound;
+    if (oob) *bad = 1;
+    // an out-of-range id is reported after the build (graph_create reads `bad` back); until then it must not index
+    // anything: the histogram, the sort and the gathers below all use these narrowed ids
+    out[i] = oob ? 0 : (int32_t)v;
     if (iota) iota[i] = (int32_t)i;
   }
 }

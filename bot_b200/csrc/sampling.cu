@@ -38,18 +38,24 @@ __device__ __forceinline__ uint32_t candidate(uint64_t seed, uint32_t v, uint32_
   return (uint32_t)__umul64hi(x, (uint64_t)d);
 }
 
-__global__ void k_sample_count(const int32_t* __restrict__ indptr, int64_t n_seeds, const int64_t* __restrict__ seeds,
-                               int fanout, int64_t* __restrict__ counts) {
+__global__ void k_sample_count(const int32_t* __restrict__ indptr, int64_t n_rows, int64_t n_seeds,
+                               const int64_t* __restrict__ seeds, int fanout, int64_t* __restrict__ counts,
+                               int* __restrict__ bad) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n_seeds) return;
   const int64_t v = seeds[i];
+  if (v < 0 || v >= n_rows) {  // reported by botgat_sample_count after its synchronisation; never used as an index
+    *bad = 1;
+    counts[i] = 0;
+    return;
+  }
   const int d = indptr[v + 1] - indptr[v];
   counts[i] = (fanout <= 0 || d <= fanout) ? d : fanout;
 }
 
 __global__ void __launch_bounds__(kSampleWarps * 32)
 k_sample(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, const int32_t* __restrict__ eids,
-         int64_t n_seeds, const int64_t* __restrict__ seeds, int fanout, uint64_t seed, const int64_t* __restrict__ offsets,
+         int64_t n_rows, int64_t n_seeds, const int64_t* __restrict__ seeds, int fanout, uint64_t seed, const int64_t* __restrict__ offsets,
          int64_t* __restrict__ out_src, int64_t* __restrict__ out_dst, int64_t* __restrict__ out_eid) {
   __shared__ uint32_t s_picks[kSampleWarps][kMaxFanout];
   __shared__ uint32_t s_bits[kSampleWarps][2 * kMaxFanout / 32];
@@ -58,6 +64,7 @@ k_sample(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices
   uint32_t* bits = s_bits[warp];
   for (int64_t i = (int64_t)blockIdx.x * kSampleWarps + warp; i < n_seeds; i += (int64_t)gridDim.x * kSampleWarps) {
     const int64_t v = seeds[i];
+    if (v < 0 || v >= n_rows) continue;  // botgat_sample_count already rejected such a seed list (count 0 here)
     const int beg = indptr[v], d = indptr[v + 1] - beg;
     const int64_t base = offsets[i];
     if (fanout <= 0 || d <= fanout) {
@@ -119,15 +126,22 @@ k_sample(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices
 }
 
 // ---- block construction ------------------------------------------------------------------------------------------
-__global__ void k_block_mark_seeds(int64_t n_seeds, const int64_t* __restrict__ seeds, int32_t* __restrict__ seed_pos) {
+// node ids outside [0, n_parent) set *bad (reported by botgat_block_compact after its synchronisation) and are never
+// used as an index
+__global__ void k_block_mark_seeds(int64_t n_parent, int64_t n_seeds, const int64_t* __restrict__ seeds,
+                                   int32_t* __restrict__ seed_pos, int* __restrict__ bad) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < n_seeds) seed_pos[seeds[i]] = (int32_t)i;
+  if (i >= n_seeds) return;
+  const int64_t v = seeds[i];
+  if (v < 0 || v >= n_parent) { *bad = 1; return; }
+  seed_pos[v] = (int32_t)i;
 }
-__global__ void k_block_mark_hits(int64_t n_edges, const int64_t* __restrict__ src, const int32_t* __restrict__ seed_pos,
-                                  int32_t* __restrict__ hit) {
+__global__ void k_block_mark_hits(int64_t n_parent, int64_t n_edges, const int64_t* __restrict__ src,
+                                  const int32_t* __restrict__ seed_pos, int32_t* __restrict__ hit, int* __restrict__ bad) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e < n_edges) {
     const int64_t g = src[e];
+    if (g < 0 || g >= n_parent) { *bad = 1; return; }
     if (seed_pos[g] < 0) hit[g] = 1;
   }
 }
@@ -137,18 +151,20 @@ __global__ void k_block_nodes(int64_t n_parent, int64_t n_seeds, const int64_t* 
   if (g < n_seeds) src_nodes[g] = seeds[g];
   if (g < n_parent && hit[g]) src_nodes[n_seeds + rank[g]] = g;
 }
-__global__ void k_block_relabel(int64_t n_edges, int64_t n_seeds, const int64_t* __restrict__ src, const int32_t* __restrict__ seed_pos,
-                                const int32_t* __restrict__ rank, int64_t* __restrict__ src_local) {
+__global__ void k_block_relabel(int64_t n_parent, int64_t n_edges, int64_t n_seeds, const int64_t* __restrict__ src,
+                                const int32_t* __restrict__ seed_pos, const int32_t* __restrict__ rank,
+                                int64_t* __restrict__ src_local) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e < n_edges) {
     const int64_t g = src[e];
+    if (g < 0 || g >= n_parent) { src_local[e] = 0; return; }
     const int32_t sp = seed_pos[g];
     src_local[e] = sp >= 0 ? (int64_t)sp : n_seeds + rank[g];
   }
 }
 
 static inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
-struct BlockLayout { size_t seed_pos, hit, rank, cub, total, cub_bytes; };
+struct BlockLayout { size_t seed_pos, hit, rank, cub, bad, total, cub_bytes; };
 static BlockLayout block_layout(int64_t n_parent) {
   BlockLayout L;
   size_t o = 0;
@@ -158,6 +174,7 @@ static BlockLayout block_layout(int64_t n_parent) {
   L.cub_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, L.cub_bytes, (const int32_t*)nullptr, (int32_t*)nullptr, (int)(n_parent + 1));
   L.cub = o; o += up256(L.cub_bytes);
+  L.bad = o; o += 256;
   L.total = o;
   return L;
 }
@@ -169,7 +186,7 @@ using namespace botgat;
 extern "C" int64_t botgat_sample_workspace_bytes(int64_t n_seeds) {
   size_t bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int64_t*)nullptr, (int64_t*)nullptr, (int)(n_seeds + 1));
-  return (int64_t)(up256(bytes) + up256(sizeof(int64_t) * (size_t)(n_seeds + 1)));
+  return (int64_t)(up256(bytes) + up256(sizeof(int64_t) * (size_t)(n_seeds + 1)) + 256);  // scan temp | counts | bad flag
 }
 
 extern "C" int botgat_sample_count(const botgat_graph* g, int64_t n_seeds, const int64_t* seeds, int32_t fanout,
@@ -184,12 +201,18 @@ extern "C" int botgat_sample_count(const botgat_graph* g, int64_t n_seeds, const
   size_t cub_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (const int64_t*)nullptr, (int64_t*)nullptr, (int)(n_seeds + 1));
   int64_t* counts = (int64_t*)((char*)workspace + up256(cub_bytes));
+  int* bad = (int*)((char*)workspace + up256(cub_bytes) + up256(sizeof(int64_t) * (size_t)(n_seeds + 1)));
   BG_CHECK(cudaMemsetAsync(counts + n_seeds, 0, sizeof(int64_t), st));
-  k_sample_count<<<(unsigned)((n_seeds + 255) / 256), 256, 0, st>>>(g->in_indptr, n_seeds, seeds, fanout, counts);
+  BG_CHECK(cudaMemsetAsync(bad, 0, sizeof(int), st));
+  k_sample_count<<<(unsigned)((n_seeds + 255) / 256), 256, 0, st>>>(g->in_indptr, g->n_dst, n_seeds, seeds, fanout, counts, bad);
   BG_CHECK(cub::DeviceScan::ExclusiveSum(workspace, cub_bytes, counts, offsets, (int)(n_seeds + 1), st));
   BG_LAUNCHED(2);
+  int hbad = 0;
   BG_CHECK(cudaMemcpyAsync(n_out, offsets + n_seeds, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  BG_CHECK(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
   BG_CHECK(cudaStreamSynchronize(st));
+  if (hbad) *n_out = 0;
+  BG_REQUIRE(!hbad, "sample_count: seed node id out of range [0, %lld)", (long long)g->n_dst);
   return 0;
 }
 
@@ -204,7 +227,7 @@ extern "C" int botgat_sample_neighbors(const botgat_graph* g, int64_t n_seeds, c
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t work = (n_seeds + kSampleWarps - 1) / kSampleWarps;
   k_sample<<<resident_grid(k_sample, kSampleWarps * 32, work), kSampleWarps * 32, 0, st>>>(
-      g->in_indptr, g->in_indices, g->in_eid, n_seeds, seeds, fanout, seed, offsets, out_src, out_dst, out_eid);
+      g->in_indptr, g->in_indices, g->in_eid, g->n_dst, n_seeds, seeds, fanout, seed, offsets, out_src, out_dst, out_eid);
   BG_LAUNCHED(1);
   BG_CHECK(cudaGetLastError());
   return 0;
@@ -227,19 +250,24 @@ extern "C" int botgat_block_compact(int64_t n_parent, int64_t n_seeds, const int
   int32_t* seed_pos = (int32_t*)(ws + L.seed_pos);
   int32_t* hit = (int32_t*)(ws + L.hit);
   int32_t* rank = (int32_t*)(ws + L.rank);
+  int* bad = (int*)(ws + L.bad);
   BG_CHECK(cudaMemsetAsync(seed_pos, 0xFF, sizeof(int32_t) * (size_t)n_parent, st));
   BG_CHECK(cudaMemsetAsync(hit, 0, sizeof(int32_t) * (size_t)(n_parent + 1), st));
-  if (n_seeds) k_block_mark_seeds<<<(unsigned)((n_seeds + 255) / 256), 256, 0, st>>>(n_seeds, seeds, seed_pos);
-  if (n_edges) k_block_mark_hits<<<(unsigned)((n_edges + 255) / 256), 256, 0, st>>>(n_edges, src_global, seed_pos, hit);
+  BG_CHECK(cudaMemsetAsync(bad, 0, sizeof(int), st));
+  if (n_seeds) k_block_mark_seeds<<<(unsigned)((n_seeds + 255) / 256), 256, 0, st>>>(n_parent, n_seeds, seeds, seed_pos, bad);
+  if (n_edges) k_block_mark_hits<<<(unsigned)((n_edges + 255) / 256), 256, 0, st>>>(n_parent, n_edges, src_global, seed_pos, hit, bad);
   size_t cub_bytes = L.cub_bytes;
   BG_CHECK(cub::DeviceScan::ExclusiveSum(ws + L.cub, cub_bytes, hit, rank, (int)(n_parent + 1), st));
   const int64_t span = n_parent > n_seeds ? n_parent : n_seeds;
   k_block_nodes<<<(unsigned)((span + 255) / 256), 256, 0, st>>>(n_parent, n_seeds, seeds, hit, rank, src_nodes);
-  if (n_edges) k_block_relabel<<<(unsigned)((n_edges + 255) / 256), 256, 0, st>>>(n_edges, n_seeds, src_global, seed_pos, rank, src_local);
+  if (n_edges) k_block_relabel<<<(unsigned)((n_edges + 255) / 256), 256, 0, st>>>(n_parent, n_edges, n_seeds, src_global, seed_pos, rank, src_local);
   BG_LAUNCHED(5);
   int32_t n_new = 0;
+  int hbad = 0;
   BG_CHECK(cudaMemcpyAsync(&n_new, rank + n_parent, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  BG_CHECK(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
   BG_CHECK(cudaStreamSynchronize(st));
+  BG_REQUIRE(!hbad, "block_compact: node id out of range [0, %lld)", (long long)n_parent);
   *n_src = n_seeds + n_new;
   return 0;
 }

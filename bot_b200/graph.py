@@ -64,9 +64,16 @@ class Graph:
         self._handle = None
         self._info = None
         self._cache = {}
+        self._streams = {}   # cuda_stream handle -> torch stream: every stream the structure was used on
 
     # ---- lifetime of the device structure ---------------------------------
     def _ensure(self):
+        """The device structure handle.  Every kernel launch that reads the structure goes through here, so this
+        is also where the launching stream is remembered: ``__del__`` frees behind ALL of them."""
+        if self._src.is_cuda:
+            st = torch.cuda.current_stream(self._src.device)
+            if st.cuda_stream not in self._streams:
+                self._streams[st.cuda_stream] = st
         if self._handle is not None:
             return self._handle
         _require_cuda(self._src, "graph structure")
@@ -87,8 +94,13 @@ class Graph:
         if h is not None and _lib._lib is not None:
             try:
                 # back to the stream-ordered pool behind the work enqueued so far (no device synchronisation:
-                # mini-batch blocks come and go every step)
-                _lib._lib.botgat_graph_destroy_async(h, C.c_void_p(torch.cuda.current_stream(self._src.device).cuda_stream))
+                # mini-batch blocks come and go every step).  The free is enqueued on the current stream; kernels
+                # that read the structure on OTHER streams (a side stream, a user stream) are ordered before it first.
+                cur = torch.cuda.current_stream(self._src.device)
+                for handle, st in self._streams.items():
+                    if handle != cur.cuda_stream:
+                        cur.wait_stream(st)
+                _lib._lib.botgat_graph_destroy_async(h, C.c_void_p(cur.cuda_stream))
             except Exception:
                 try:
                     _lib._lib.botgat_graph_destroy(h)

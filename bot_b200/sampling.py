@@ -138,11 +138,9 @@ class NodeDataLoader:
         self.nids = torch.as_tensor(nids, dtype=torch.int64, device=g.device)
         self.batch_size, self.shuffle, self.drop_last, self.batch_sampler = batch_size, shuffle, drop_last, batch_sampler
 
-    def _batches(self):
-        if self.batch_sampler is not None:
-            for idx in self.batch_sampler:
-                yield self.nids[torch.as_tensor(idx, dtype=torch.int64, device=self.nids.device)]
-            return
+        self._bs_iter = None   # ONE persistent iterator over batch_sampler (the reference's BatchSampler never ends)
+
+    def _plain_batches(self):
         n = self.nids.numel()
         order = torch.randperm(n, device=self.nids.device) if self.shuffle else torch.arange(n, device=self.nids.device)
         for lo in range(0, n, self.batch_size):
@@ -152,11 +150,49 @@ class NodeDataLoader:
 
     def __len__(self):
         if self.batch_sampler is not None:
-            return len(self.batch_sampler)
+            bs = self.batch_sampler
+            if hasattr(bs, "__len__"):
+                return len(bs)
+            if hasattr(bs, "n") and hasattr(bs, "batch_size"):   # the reference's BatchSampler (utils.py:22-32): batches per epoch
+                return (bs.n + bs.batch_size - 1) // bs.batch_size
+            raise TypeError("NodeDataLoader: batch_sampler has no length")
         n = self.nids.numel()
         return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
 
     def __iter__(self):
-        for seeds in self._batches():
-            blocks = self.sampler.sample_blocks(self.g, seeds)
-            yield blocks[0].srcdata[NID], seeds, blocks
+        return _NodeDataLoaderIter(self)
+
+
+class _NodeDataLoaderIter:
+    """Iterator of :class:`NodeDataLoader`.  With a ``batch_sampler`` it draws from the loader's ONE persistent
+    iterator: the reference's ``BatchSampler`` (utils.py:22-32) is infinite and yields ``None`` as the end-of-epoch
+    sentinel, and ``DataLoaderWrapper`` (utils.py:8-19) keeps calling ``next`` on the same iterator epoch after
+    epoch — so ``None`` ends the epoch (StopIteration) and the NEXT call starts the following one."""
+
+    def __init__(self, loader):
+        self.loader = loader
+        if loader.batch_sampler is not None:
+            if loader._bs_iter is None:
+                loader._bs_iter = iter(loader.batch_sampler)
+            self._plain = None
+        else:
+            self._plain = loader._plain_batches()
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        ld = self.loader
+        if self._plain is not None:
+            seeds = next(self._plain)
+        else:
+            try:
+                idx = next(ld._bs_iter)
+            except StopIteration:
+                ld._bs_iter = None      # a finite sampler: start over at the next epoch
+                raise
+            if idx is None:             # end-of-epoch sentinel
+                raise StopIteration
+            seeds = ld.nids[torch.as_tensor(idx, dtype=torch.int64).to(ld.nids.device)]
+        blocks = ld.sampler.sample_blocks(ld.g, seeds)
+        return blocks[0].srcdata[NID], seeds, blocks

@@ -52,6 +52,12 @@ int64_t botgat_launch_count(void);
  *   out-CSR (rows = src):                   indptr, indices (= dst), eid
  * with a stable sort (inside a row, increasing edge id), plus degree tables.
  * Synchronises `stream` once before returning (it reads back two scalars).
+ * Node ids outside [0, n_src) / [0, n_dst) are detected BEFORE anything is indexed by them and
+ * reported as an error (return < 0, no graph).
+ * Memory: the structure arrays come from the device's default stream-ordered pool
+ * (cudaMallocAsync).  If the application left that pool's release threshold at its default (0),
+ * the first call on a device raises it to 2 GiB so that per-batch blocks recycle their memory;
+ * an application-chosen threshold is respected.
  * ---------------------------------------------------------------------- */
 int botgat_graph_create(int64_t n_src, int64_t n_dst, int64_t n_edges,
                         const int64_t* src, const int64_t* dst,

@@ -638,3 +638,59 @@ def test_head_range_launches(cuda, name):
         res.append([out.detach()] + [t[k].grad for k in names])
     assert all(torch.equal(a, b) for a, b in zip(*res))
     assert seen == [("f", i) for i in range(len(chunks))] + [("b", i, (n_src, H, D)) for i in range(len(chunks))]
+
+
+def test_out_of_range_node_id_is_a_clean_error(cuda):
+    """An id outside [0, n) must come back as an error BEFORE it is used as an index (no out-of-bounds histogram
+    write, no sticky device fault): the device keeps working afterwards."""
+    import bot_b200
+    from bot_b200 import sampling
+
+    src = torch.tensor([0, 1, 2, 50_000_000, 3], device=cuda)
+    dst = torch.tensor([1, 2, 3, 0, -7], device=cuda)
+    with pytest.raises(RuntimeError, match="out of range"):
+        bot_b200.Graph(src, dst, 10).create_formats_()
+    torch.cuda.synchronize()                                        # would raise on a sticky illegal-address fault
+    c = make_case(50, 50, 400, 2, 8, seed=3)
+    check_case(c, cuda)
+    g = bot_b200.Graph(c["src"].to(cuda), c["dst"].to(cuda), 50)
+    with pytest.raises(RuntimeError, match="out of range"):
+        sampling.sample_neighbors(g, torch.tensor([1, 2, 10**9], device=cuda), 4, 0)
+    with pytest.raises(RuntimeError, match="out of range"):
+        sampling.to_block(g, torch.tensor([1, 99], device=cuda), torch.tensor([1, 2], device=cuda),
+                          torch.tensor([0, 1], device=cuda), torch.tensor([0, 1], device=cuda))
+    torch.cuda.synchronize()
+    check_case(c, cuda)
+
+
+def test_block_without_destination_rows_has_zero_gradients(cuda):
+    """A rank whose row range is empty still owns halo sources: its gradients must be written (zeros), they are
+    reduce-scattered into the other ranks' gradients (bot_b200/partition.py)."""
+    import bot_b200
+    from bot_b200.functional import gat_fused
+
+    g = bot_b200.create_block((torch.empty(0, dtype=torch.int64), torch.empty(0, dtype=torch.int64)), 40, 0, device=cuda)
+    ft = torch.randn(40, 2, 8, device=cuda, requires_grad=True)
+    el = torch.randn(40, 2, device=cuda, requires_grad=True)
+    er = torch.randn(0, 2, device=cuda, requires_grad=True)
+    out = gat_fused(g, ft, el, er)
+    assert out.shape == (0, 2, 8)
+    # poison the caching allocator so that an unwritten gradient buffer would not read as zeros
+    junk = torch.full((40, 2, 8), float("nan"), device=cuda)
+    del junk
+    out.backward(torch.empty(0, 2, 8, device=cuda))
+    assert float(ft.grad.abs().max()) == 0.0 and float(el.grad.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("lowdeg", ["0", "1000000"])
+def test_zero_negative_slope(cuda, monkeypatch, lowdeg):
+    """negative_slope = 0 (a valid GATConv argument): the -inf logit of a dropped edge / a lane past the row end must
+    not become NaN through -inf * 0."""
+    monkeypatch.setenv("BOTGAT_LOWDEG", lowdeg)
+    c = make_case(300, 300, 5000, 3, 24, ee=True, keep_p=0.3, seed=21)
+    ref_out, ref_g = oracle_run(c, slope=0.0)
+    out, g, _ = engine_run(c, cuda, slope=0.0)
+    assert torch.isfinite(out).all()
+    assert rel_err(out, ref_out) <= FWD_TOL
+    for k in ("ft", "el", "er", "ee"):
+        assert rel_err(g[k], ref_g[k]) <= 1e-4, k

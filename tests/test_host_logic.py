@@ -190,3 +190,66 @@ def test_bench_algorithmic_bytes_match_survey():
     # products shape (no edge features): 2,018 + 4,148 B/edge
     bf, bb = bench.algorithmic_bytes(61859140, 2449029, 2449029, 4, 120, er=True, ee=False)
     assert abs(bf / 61859140 - 2018) < 1.5 and abs(bb / 61859140 - 4148) < 2.5
+
+
+class _RefBatchSampler:
+    """Restatement of the reference's BatchSampler (src/ogbn-proteins/utils.py:22-32): infinite, ``None`` ends an epoch."""
+
+    def __init__(self, n, batch_size):
+        self.n, self.batch_size = n, batch_size
+
+    def __iter__(self):
+        while True:
+            for b in torch.randperm(self.n).split(self.batch_size):
+                yield b
+            yield None
+
+
+class _RefDataLoaderWrapper:
+    """Restatement of DataLoaderWrapper (utils.py:8-19): ONE iter() reused every epoch, any exception ends the epoch."""
+
+    def __init__(self, dataloader):
+        self.iter = iter(dataloader)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        try:
+            return next(self.iter)
+        except Exception:
+            raise StopIteration() from None
+
+
+def test_node_dataloader_with_the_reference_batch_sampler_over_epochs():
+    """`NodeDataLoader(..., batch_sampler=BatchSampler(n, bs))` wrapped in `DataLoaderWrapper`
+    (src/ogbn-proteins/gat.py:179-189) must yield every node once per epoch, for several epochs, with and
+    without the wrapper; `len()` = batches per epoch."""
+    from bot_b200 import sampling
+
+    class FakeBlock:
+        def __init__(self, seeds):
+            self.srcdata = {sampling.NID: seeds}
+
+    class FakeSampler:
+        def sample_blocks(self, g, seeds):
+            return [FakeBlock(seeds)]
+
+    class FakeGraph:
+        device = torch.device("cpu")
+
+    nids = torch.arange(100, 137)
+    loader = sampling.NodeDataLoader(FakeGraph(), nids, FakeSampler(), batch_sampler=_RefBatchSampler(37, 10), num_workers=10)
+    assert len(loader) == 4
+    wrapped = _RefDataLoaderWrapper(loader)
+    for _ in range(3):
+        got = [out for _, out, _ in wrapped]
+        assert len(got) == 4 and torch.equal(torch.cat(got).sort().values, nids)
+    loader = sampling.NodeDataLoader(FakeGraph(), nids, FakeSampler(), batch_sampler=_RefBatchSampler(37, 10))
+    for _ in range(3):   # plain `for ... in loader` also sees one epoch per loop
+        got = [out for _, out, _ in loader]
+        assert len(got) == 4 and torch.equal(torch.cat(got).sort().values, nids)
+    # finite batch samplers restart every epoch
+    loader = sampling.NodeDataLoader(FakeGraph(), nids, FakeSampler(), batch_sampler=[[0, 1], [2]])
+    for _ in range(2):
+        assert [o.tolist() for _, o, _ in loader] == [[100, 101], [102]]

@@ -113,14 +113,16 @@ def check_case(c, device, **kw):
     return errs
 
 
-def philox_attn_mul(seed, n_edges, n_heads, p):
+def philox_attn_mul(seed, n_edges, n_heads, p, eids=None):
     """numpy restatement of `philox_dropout_mul` (bot_b200/csrc/common.cuh): Philox4x32-10 keyed on the 64-bit
-    seed, counter (edge id, head >> 2, 0x9E3779B9, 0xBB67AE85), component head & 3; keep iff u >= p."""
+    seed, counter (edge id, head >> 2, 0x9E3779B9, 0xBB67AE85), component head & 3; keep iff u >= p.
+    ``eids``: evaluate only these edge ids (rows of the result follow it) instead of 0..n_edges-1."""
     import numpy as np
 
     M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
+    eid = np.arange(n_edges, dtype=np.uint32) if eids is None else np.asarray(eids).astype(np.uint32)
+    n_edges = eid.shape[0]
     out = np.zeros((n_edges, n_heads), dtype=np.float32)
-    eid = np.arange(n_edges, dtype=np.uint32)
     for h in range(n_heads):
         c0 = eid.copy()
         c1 = np.full(n_edges, h >> 2, dtype=np.uint32)
