@@ -310,6 +310,24 @@ using namespace botgat;
 extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args* a, void* stream) {
   BG_REQUIRE(g && a, "backward: null graph/args");
   BG_REQUIRE(a->H > 0 && a->D > 0, "backward: bad H=%d D=%d", a->H, a->D);
+  DeviceGuard guard(g->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g->n_dst == 0 || g->n_src == 0) {
+    // no destination rows (an empty row range of the 1-D partition still has n_src > 0 halo sources): every gradient
+    // is exactly zero — write the zeros, the caller's buffers are uninitialised and may be reduce-scattered to peers.
+    // (Checked before the null-pointer tests below: empty tensors legitimately have null data pointers.)
+    const int ph = a->phases ? a->phases : 7;
+    if ((ph & 2) && g->n_src > 0) {
+      BG_REQUIRE(a->grad_ft && a->grad_el && a->ld_gft >= (int64_t)a->H * a->D, "backward: null grad_ft/grad_el");
+      BG_CHECK(cudaMemset2DAsync(a->grad_ft, sizeof(float) * a->ld_gft, 0, sizeof(float) * a->H * a->D, (size_t)g->n_src, st));
+      BG_CHECK(cudaMemsetAsync(a->grad_el, 0, sizeof(float) * (size_t)g->n_src * a->H, st));
+    }
+    if ((ph & 4) && a->grad_er && g->n_dst > 0)
+      BG_CHECK(cudaMemsetAsync(a->grad_er, 0, sizeof(float) * (size_t)g->n_dst * a->H, st));
+    if ((ph & 4) && a->grad_ee && g->n_edges > 0)
+      BG_CHECK(cudaMemsetAsync(a->grad_ee, 0, sizeof(float) * (size_t)g->n_edges * (a->ld_gee > 0 ? a->ld_gee : a->H), st));
+    return 0;
+  }
   BG_REQUIRE(a->ft && a->el && a->out && a->row_max && a->row_sum && a->gout, "backward: null input");
   BG_REQUIRE(a->drec && a->grad_ft && a->grad_el, "backward: null drec/grad_ft/grad_el");
   BG_REQUIRE(!a->dst_scale || a->gprime, "backward: gprime workspace required with dst_scale");
@@ -320,22 +338,6 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
   const int64_t HD = (int64_t)a->H * a->D;
   BG_REQUIRE(a->ld_ft >= HD && a->ld_out >= HD && a->ld_gft >= HD, "backward: leading dimension < H*D");
   BG_REQUIRE(a->eb_out ? (a->Hb == 1 || a->Hb == a->H) : true, "backward: Hb must be 1 or H");
-  DeviceGuard guard(g->device);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (g->n_dst == 0 || g->n_src == 0) {
-    // no destination rows (an empty row range of the 1-D partition still has n_src > 0 halo sources): every gradient
-    // is exactly zero — write the zeros, the caller's buffers are uninitialised and may be reduce-scattered to peers
-    const int ph = a->phases ? a->phases : 7;
-    if ((ph & 2) && g->n_src > 0) {
-      BG_CHECK(cudaMemset2DAsync(a->grad_ft, sizeof(float) * a->ld_gft, 0, sizeof(float) * HD, (size_t)g->n_src, st));
-      BG_CHECK(cudaMemsetAsync(a->grad_el, 0, sizeof(float) * (size_t)g->n_src * a->H, st));
-    }
-    if ((ph & 4) && a->grad_er && g->n_dst > 0)
-      BG_CHECK(cudaMemsetAsync(a->grad_er, 0, sizeof(float) * (size_t)g->n_dst * a->H, st));
-    if ((ph & 4) && a->grad_ee && g->n_edges > 0)
-      BG_CHECK(cudaMemsetAsync(a->grad_ee, 0, sizeof(float) * (size_t)g->n_edges * (a->ld_gee > 0 ? a->ld_gee : a->H), st));
-    return 0;
-  }
   dim3 block(kWarpsPerBlock * 32);
   const int phases = a->phases ? a->phases : 7;
   const int64_t ld_gee = a->ld_gee > 0 ? a->ld_gee : a->H;

@@ -240,6 +240,7 @@ using namespace botgat;
 extern "C" int botgat_gat_forward(const botgat_graph* g, const botgat_fwd_args* a, void* stream) {
   BG_REQUIRE(g && a, "forward: null graph/args");
   BG_REQUIRE(a->H > 0 && a->D > 0, "forward: bad H=%d D=%d", a->H, a->D);
+  if (g->n_dst == 0) return 0;  // nothing to write; empty outputs legitimately have null data pointers
   BG_REQUIRE(a->ft && a->el && a->out && a->row_max && a->row_sum, "forward: null ft/el/out/row_max/row_sum");
   BG_REQUIRE(a->ld_ft >= (int64_t)a->H * a->D && a->ld_out >= (int64_t)a->H * a->D, "forward: leading dimension < H*D");
   BG_REQUIRE(a->ld_ft < (1ll << 30), "forward: ld_ft too large");
@@ -247,7 +248,6 @@ extern "C" int botgat_gat_forward(const botgat_graph* g, const botgat_fwd_args* 
   BG_REQUIRE(!(a->eb && (a->ee || a->keep)), "forward: pass edge logits either staged (eb) or by edge id (ee/keep)");
   BG_REQUIRE(!(a->am && a->attn_mul), "forward: pass the dropout multiplier either staged (am) or by edge id (attn_mul)");
   BG_REQUIRE(a->attn_p >= 0.f && a->attn_p < 1.f, "forward: attn_p must be in [0,1)");
-  if (g->n_dst == 0) return 0;
   DeviceGuard guard(g->device);
   cudaStream_t st = (cudaStream_t)stream;
 
