@@ -53,16 +53,40 @@ def emit(line):
 
 import torch  # noqa: E402
 
-# ogbn-proteins layer shape
-N_NODES, N_EDGES, HEADS, HID, EDGE_EMB = 132534, 39561252, 6, 80, 16
-EDGE_DROP, SLOPE = 0.1, 0.2
-METRIC = "GAT layer fwd+bwd edges/sec (ogbn-proteins shape)"
-CPU_SAMPLE_EDGES = N_EDGES // 4   # bounded CPU sample: ~4.6 s per fwd+bwd on the GPU box's 16 host cores
+SLOPE = 0.2
+# BASELINE.json configs.  `proteins` is the north-star / headline shape; the others are
+# measured with the same code path at their own flags (`--shape`), N=1 and partitioned.
+SHAPES = {
+    "proteins": dict(n=132534, e=39561252, H=6, D=80, er=True, ee=True, edge_drop=0.1, attn_p=0.0, symm=False, in_feats=480,
+                     desc="attn_dst + edge-feature logits (8-dim raw edge feats -> 16-dim edge emb), edge_drop=0.1 (training)",
+                     ref="src/ogbn-proteins/gat.py:320-327, models.py:209-221"),
+    "products": dict(n=2449029, e=61859140, H=4, D=120, er=True, ee=False, edge_drop=0.1, attn_p=0.0, symm=False, in_feats=480,
+                     desc="attn_dst, no edge features, edge_drop=0.1 (training)",
+                     ref="src/ogbn-products/gat.py:379-386, models.py:211-223"),
+    "reddit": dict(n=232965, e=114615892, H=4, D=64, er=False, ee=False, edge_drop=0.0, attn_p=0.1, symm=True, in_feats=256,
+                   desc="source-only logits, symmetric norm, attn_drop=0.1 drawn in-kernel (training)",
+                   ref="src/no-sampling/run.py:978, models.py:683-694"),
+    "arxiv": dict(n=169343, e=2484941, H=3, D=250, er=False, ee=False, edge_drop=0.0, attn_p=0.1, symm=True, in_feats=750,
+                  desc="source-only logits, symmetric norm, attn_drop=0.1 drawn in-kernel (training); too small to shard: "
+                       "replicas only", ref="src/no-sampling/run.py:1017"),
+}
+EDGE_FEATS, EDGE_EMB = 8, 16
+# kept for importers (tests): the headline shape
+N_NODES, N_EDGES, HEADS, HID = SHAPES["proteins"]["n"], SHAPES["proteins"]["e"], SHAPES["proteins"]["H"], SHAPES["proteins"]["D"]
+EDGE_DROP = SHAPES["proteins"]["edge_drop"]
 
 
-def workload_name(n_nodes=N_NODES, n_edges=N_EDGES):
-    return (f"ogbn-proteins-shape GATConv layer: N={n_nodes} E={n_edges} H={HEADS} D={HID} fp32, attn_dst + "
-            f"edge-feature logits ({EDGE_EMB}-dim edge emb), edge_drop={EDGE_DROP} (training), uniform random edges")
+def metric_name(shape):
+    return f"GAT layer fwd+bwd edges/sec (ogbn-{shape} shape)" if shape != "reddit" else "GAT layer fwd+bwd edges/sec (Reddit shape)"
+
+
+METRIC = metric_name("proteins")
+
+
+def workload_name(shape, n_nodes, n_edges):
+    c = SHAPES[shape]
+    return (f"{shape}-shape GATConv layer: N={n_nodes} E={n_edges} H={c['H']} D={c['D']} fp32, {c['desc']}, "
+            f"uniform random edges ({c['ref']})")
 
 
 def algorithmic_bytes(E, N_s, N_d, H, D, er=True, ee=True):
@@ -73,6 +97,17 @@ def algorithmic_bytes(E, N_s, N_d, H, D, er=True, ee=True):
     fwd = E * (4 + h + R + x) + N_d * (8 + h * e_r + R + 2 * h)
     bwd = E * ((4 + h + R + x + h) + (8 + 2 * h + R)) + N_d * (8 + 2 * R + 2 * h + 2 * h * e_r) + N_s * (8 + R + h)
     return fwd, bwd
+
+
+def performed_bytes(E, N_s, N_d, H, D, er=True, ee=True):
+    """Bytes of the passes this engine actually performs: the forward gather, ONE backward
+    gather (the reference's dst-major re-gather for grad_a is eliminated: the dots ride on the src pass) and the
+    per-edge record streams.  = forward + the src-pass bracket of SURVEY 8(d) + the node pass."""
+    bf, bb = algorithmic_bytes(E, N_s, N_d, H, D, er, ee)
+    R, h = 4 * H * D, 4 * H
+    x = (h + 4) if ee else 0
+    b_dst = E * (4 + h + R + x + h) + N_d * (8 + R + 2 * h + 2 * h)
+    return bf, bb - b_dst
 
 
 # ----------------------------------------------------------------------------
@@ -162,47 +197,120 @@ def synth_edges(n_nodes, n_edges, device, seed=0, power_law=0.0):
 # ----------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference math on a bounded sample
 # ----------------------------------------------------------------------------
-def cpu_port_run(steps, warmup, n_edges=CPU_SAMPLE_EDGES):
-    """fwd+bwd of the same layer math on the host (oracle port, non-materialising form).
-    Returns dict(value, unit, cores, kind, sample, ms_per_step)."""
+def cpu_port_run(shape, steps, warmup, n_edges=None, budget_s=200.0):
+    """fwd+bwd of the same layer math, same flags, on the host (oracle port, non-materialising form,
+    oracle/gat_ref.py gat_sparse_big_*).  A step processes a uniform edge subsample of the workload over ALL nodes,
+    sized so that the whole run stays within ``budget_s``.  Returns dict(value, unit, cores, kind, sample, ms_per_step)."""
     from oracle import gat_ref
 
+    c = SHAPES[shape]
+    n, H, D = c["n"], c["H"], c["D"]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    src, dst = synth_edges(N_NODES, n_edges, "cpu", seed=0)
-    bg = gat_ref.BigGraph(src, dst, N_NODES, N_NODES)
+    if n_edges is None:
+        # ~0.45 us per edge and step at H*D = 480 on 16 cores (measured: 4.3 s for 9.9 M edges); scale to the budget
+        per_edge = 0.45e-6 * (H * D) / 480.0 * (16.0 / max(cores, 1))
+        n_edges = int(min(c["e"], max(1_000_000, budget_s / max(steps + warmup, 1) / per_edge)))
+    src, dst = synth_edges(n, n_edges, "cpu", seed=0)
+    bg = gat_ref.BigGraph(src, dst, n, n)
     g = torch.Generator().manual_seed(1)
-    ft = torch.randn(N_NODES, HEADS, HID, generator=g)
-    el = torch.randn(N_NODES, HEADS, generator=g)
-    er = torch.randn(N_NODES, HEADS, generator=g)
-    ee = torch.randn(n_edges, HEADS, generator=g)
-    gout = torch.randn(N_NODES, HEADS, HID, generator=g)
+    ft = torch.randn(n, H, D, generator=g)
+    el = torch.randn(n, H, generator=g)
+    er = torch.randn(n, H, generator=g) if c["er"] else None
+    ee = torch.randn(n_edges, H, generator=g) if c["ee"] else None
+    gout = torch.randn(n, H, D, generator=g)
+    cs = ds = None
+    if c["symm"]:
+        cs = torch.bincount(src, minlength=n).float().clamp(min=1).pow(-0.5)
+        ds = torch.bincount(dst, minlength=n).float().clamp(min=1).pow(0.5)
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            out, a, z = gat_ref.gat_sparse_big_forward(bg, ft, el, er, ee, SLOPE)
-            gat_ref.gat_sparse_big_backward(bg, ft, a, z, out, gout, SLOPE)
+            keep = mul = None
+            if c["edge_drop"] > 0:     # models.py:529-532: exactly int(E*p) random edges dropped
+                keep = torch.ones(n_edges, dtype=torch.bool)
+                keep[torch.randperm(n_edges, generator=g)[: int(n_edges * c["edge_drop"])]] = False
+            if c["attn_p"] > 0:        # models.py:537/544: nn.Dropout on the attention
+                mul = (torch.rand(n_edges, H, generator=g) >= c["attn_p"]).float() / (1.0 - c["attn_p"])
+            out, saved = gat_ref.gat_sparse_big_forward(bg, ft, el, er, ee, SLOPE, keep, mul, cs, ds)
+            gat_ref.gat_sparse_big_backward(bg, saved, gout, SLOPE, c["er"], c["ee"], keep, cs, ds)
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     t = sum(times) / len(times)
+    frac = n_edges / c["e"]
     return {"value": n_edges / t, "unit": "edges/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"same layer math on a {n_edges}-edge uniform subsample ({N_EDGES // n_edges}x fewer edges) over all {N_NODES} "
-                      f"nodes, fwd+bwd, {len(times)} timed steps, oracle/gat_ref.py gat_sparse_big_* "
-                      f"(segment_reduce + per-head sparse CSR matmul), torch {torch.__version__} CPU",
-            "ms_per_step": t * 1e3}
+            "sample": f"same layer math and flags (edge-drop draw / dropout mask included) on a {n_edges}-edge uniform subsample "
+                      f"({frac:.2f} of the workload's edges) over all {n} nodes, fwd+bwd, {len(times)} timed steps, "
+                      f"oracle/gat_ref.py gat_sparse_big_* (segment_reduce + per-head sparse CSR matmul), torch {torch.__version__} CPU, "
+                      f"{torch.get_num_threads()} threads",
+            "ms_per_step": t * 1e3, "edges_per_step": n_edges}
+
+
+def cora_cpu_reference(steps=20, warmup=3):
+    """BASELINE config 1 / SURVEY 8d: the full 2-layer Cora-shape GAT (2,708 nodes, 10,556 raw edges -> self loops,
+    1,433 feats, 8 heads x 8, 7 classes, edge_drop 0.5; src/no-sampling/run.py:895) forward + backward on the host,
+    restated on the oracle (oracle/modules_ref.py gatconv_v1) — the reference's own CPU-runnable case."""
+    from oracle import graph_ref, modules_ref
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    n, e, f_in, n_cls, H, D = 2708, 10556, 1433, 7, 8, 8
+    src, dst = graph_ref.synthetic_coo(n, e, 0)
+    src, dst = graph_ref.add_self_loop(*graph_ref.remove_self_loop(src, dst), n)
+    src, dst = torch.from_numpy(src), torch.from_numpy(dst)
+    E = src.numel()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(n, f_in, generator=g)
+    sd0 = {"fc.weight": torch.randn(H * D, f_in, generator=g) * 0.05, "attn_l": torch.randn(1, H, D, generator=g) * 0.1,
+           "res_fc.weight": torch.randn(H * D, f_in, generator=g) * 0.05}
+    sd1 = {"fc.weight": torch.randn(n_cls, H * D, generator=g) * 0.1, "attn_l": torch.randn(1, 1, n_cls, generator=g) * 0.1,
+           "res_fc.weight": torch.randn(n_cls, H * D, generator=g) * 0.1}
+    params = [t.requires_grad_(True) for sd in (sd0, sd1) for t in sd.values()]
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        keeps = []
+        for _ in range(2):
+            keep = torch.ones(E, dtype=torch.bool)
+            keep[torch.randperm(E, generator=g)[: int(E * 0.5)]] = False
+            keeps.append(keep)
+        h = modules_ref.gatconv_v1(sd0, src, dst, n, n, x, num_heads=H, out_feats=D, keep=keeps[0]).flatten(1)
+        h = torch.relu(h)
+        out = modules_ref.gatconv_v1(sd1, src, dst, n, n, h, num_heads=1, out_feats=n_cls, keep=keeps[1]).mean(1)
+        out.square().mean().backward()
+        for p_ in params:
+            p_.grad = None
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    return {"workload": f"2-layer GAT, Cora shape (N={n}, E={E} with self loops, {f_in} feats, {H}x{D} -> 1x{n_cls}, edge_drop 0.5), "
+                        "whole model fwd+bwd on the host (oracle/modules_ref.py over oracle/gat_ref.py), run.py:895",
+            "ms_per_step": round(t * 1e3, 3), "edges_per_s": 2 * E / t, "cores": torch.get_num_threads(), "kind": "port"}
+
+
+def common_config(shape, n_nodes, n_edges, world):
+    """`config` of the JSON line — identical for both arms (the driver compares them)."""
+    par = "single GPU" if world == 1 else (f"1-D dst-row partition x{world}, halo all-gather + gradient reduce-scatter (NCCL)"
+                                           if shape != "arxiv" else f"{world} independent replicas (too small to shard)")
+    return {"workload": workload_name(shape, n_nodes, n_edges), "shape": shape,
+            "l2": "inputs_exceed_l2 (no flush between iterations: the per-step working set is >= 20x the 126 MB L2)",
+            "parallelism": par,
+            "timed": "edge-drop mask draw (exactly int(E*p) edges) + per-edge operand staging + fused fwd + bwd (node / src / "
+                     "edge passes); per-edge operands are resident in the graph's canonical edge order (what the layer's own "
+                     "edge-logit kernels emit from canonically stored edata); no instrumentation inside the timed region"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_port_run(args.steps, max(args.warmup, 1))
+    r = cpu_port_run(args.shape, args.steps, max(args.warmup, 1))
+    c = SHAPES[args.shape]
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "edges/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(args.shape), "value": r["value"], "unit": "edges/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(), "sampled_edges_per_step": CPU_SAMPLE_EDGES},
+        "config": common_config(args.shape, c["n"], c["e"], int(os.environ.get("WORLD_SIZE", "1"))),
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -219,8 +327,10 @@ def run_ours(args):
     import bot_b200
     from bot_b200 import _lib, functional
     from bot_b200.functional import gat_fused
-    from bot_b200.ogbn_proteins import GATConv
 
+    shape = args.shape
+    c = SHAPES[shape]
+    H, D = c["H"], c["D"]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -231,50 +341,70 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    replicas = world > 1 and shape == "arxiv"     # too small to shard: N independent replicas, no collective
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    n_nodes, n_edges = args.nodes, args.edges
-    src, dst = synth_edges(n_nodes, n_edges, dev, seed=0)
+    n_nodes, n_edges = args.nodes or c["n"], args.edges or c["e"]
+    src, dst = synth_edges(n_nodes, n_edges, dev, seed=0 if not replicas else rank)
     gen = torch.Generator(device=dev).manual_seed(1)
 
-    if world == 1:
+    layer = None
+    if world == 1 or replicas:
         graph = bot_b200.Graph(src, dst, n_nodes)
         graph.create_formats_()
-        layer = None
     else:
         from bot_b200 import partition
 
         layer = partition.PartitionedGraph(src, dst, n_nodes)
         graph = layer.local
         graph.create_formats_()
+    full_src, full_dst = (src, dst) if (world == 1 and not args.no_parity) else (None, None)
+    cs_l = ds_l = cs_own = None
+    if c["symm"]:   # clamp(out_deg,1)^-0.5 on the gathered rows, clamp(in_deg,1)^+0.5 on the outputs (models.py:500-505, 550-555)
+        if layer is None:
+            cs_l, ds_l = graph.deg_scale("out", -0.5), graph.deg_scale("in", 0.5)
+        else:
+            cs_full = torch.bincount(src, minlength=n_nodes).float().clamp(min=1).pow(-0.5)
+            ds_full = torch.bincount(dst, minlength=n_nodes).float().clamp(min=1).pow(0.5)
+            cs_own = layer.owned_slice(cs_full).contiguous()
+            with torch.no_grad():
+                cs_l = layer.halo_gather(cs_own).contiguous()
+            ds_l = layer.owned_slice(ds_full).contiguous()
+            del cs_full, ds_full
     del src, dst
     E_local = graph.number_of_edges()
     n_src_l, n_dst_l = graph.number_of_src_nodes(), graph.number_of_dst_nodes()
+    info = graph._info
 
     # ---------------- device-resident leg (value) ----------------
-    n_own = n_dst_l if world > 1 else n_nodes
-    ft_own = torch.randn(n_own, HEADS, HID, device=dev, generator=gen).requires_grad_(True)
-    el_own = torch.randn(n_own, HEADS, device=dev, generator=gen).requires_grad_(True)
-    er = torch.randn(n_dst_l, HEADS, device=dev, generator=gen).requires_grad_(True)
-    # edge logits as the drop-in GATConv emits them: (E, pad_heads(H)) = (E, 8), one 32-byte record per edge
-    ee = torch.randn(E_local, functional.pad_heads(HEADS), device=dev, generator=gen).requires_grad_(True)
-    gout = torch.randn(n_dst_l, HEADS, HID, device=dev, generator=gen)
+    n_own = n_dst_l if layer is not None else n_nodes
+    ft_own = torch.randn(n_own, H, D, device=dev, generator=gen).requires_grad_(True)
+    el_own = torch.randn(n_own, H, device=dev, generator=gen).requires_grad_(True)
+    er = torch.randn(n_dst_l, H, device=dev, generator=gen).requires_grad_(True) if c["er"] else None
+    # edge logits as the layer's own producers emit them: one 32-byte record per edge (E, pad_heads(H)), in the graph's
+    # CANONICAL edge order (static edata is stored canonically, bot_b200.graph.EdgeFrame)
+    ee = torch.randn(E_local, functional.pad_heads(H), device=dev, generator=gen).requires_grad_(True) if c["ee"] else None
+    gout = torch.randn(n_dst_l, H, D, device=dev, generator=gen)
+    leaves = [t for t in (ft_own, el_own, er, ee) if t is not None]
 
     seeds = iter(range(1, 1 << 30))
 
-    def step_resident():
-        # the reference's draw: exactly int(E * p) uniformly random edges dropped (models.py:136-139)
-        keep = functional.edge_drop_keep(E_local, int(E_local * EDGE_DROP), next(seeds), dev)
-        if world == 1:
-            out = gat_fused(graph, ft_own, el_own, er, ee, keep, None, None, None, SLOPE, 0.0, 0)
+    def step_resident(keep_grads=False, seed=None):
+        sd = next(seeds) if seed is None else seed
+        # the reference's draw: exactly int(E * p) uniformly random edges dropped (models.py:136-139 / 528-532)
+        keep = functional.edge_drop_keep(E_local, int(E_local * c["edge_drop"]), sd, dev) if c["edge_drop"] > 0 else None
+        if layer is None:
+            out = gat_fused(graph, ft_own, el_own, er, ee, keep, None, cs_l, ds_l, SLOPE, c["attn_p"], sd, edge_order="canonical")
         else:
-            out = layer.gat(ft_own, el_own, er, ee, keep, None, None, None, SLOPE, 0.0, 0)
+            out = layer.gat(ft_own, el_own, er, ee, keep, None, cs_l, ds_l, SLOPE, c["attn_p"], sd, edge_order="canonical")
         out.backward(gout)
-        for t in (ft_own, el_own, er, ee):
+        if keep_grads:
+            return out.detach(), keep
+        for t in leaves:
             t.grad = None
 
     sampler = ClockSampler(local_rank)
@@ -284,8 +414,6 @@ def run_ours(args):
         step_resident()
     barrier()
     launches0 = lib.botgat_launch_count()
-    kt = functional.KernelTimer()
-    functional.timer = kt
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.mark_begin()
     barrier()
@@ -295,7 +423,6 @@ def run_ours(args):
     e1.record()
     barrier()
     sampler.mark_end()
-    functional.timer = None
     clocks = sampler.stop() if rank == 0 else None
     launches = lib.botgat_launch_count() - launches0
     ms_total = e0.elapsed_time(e1)
@@ -304,202 +431,114 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    value = n_edges / (ms_step * 1e-3)
+    total_edges = n_edges * (world if replicas else 1)
+    value = total_edges / (ms_step * 1e-3)
+
+    # per-kernel durations: a SECOND, instrumented pass of the same steps (CUDA events around every ABI call, the backward
+    # issued as three calls) — outside the headline's timed region
+    kt = functional.KernelTimer()
+    functional.timer = kt
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    torch.cuda.synchronize()
+    functional.timer = None
+    ms_instr = e0.elapsed_time(e1)
     ktot = kt.totals()
 
-    # roofline of the dominant kernel (largest share of the timed region)
+    # ---------------- roofline of the dominant kernel ----------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+        hbm_peak, hbm_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     else:
-        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md); MEASURED_PEAKS.json absent"
-    bf, bb = algorithmic_bytes(E_local, n_src_l, n_dst_l, HEADS, HID)
-    # backward bytes split by pass (first bracket = dst pass over the in-CSR, second = src pass)
-    R, h = 4 * HEADS * HID, 4 * HEADS
-    b_dst = E_local * (4 + h + R + (h + 4) + h) + n_dst_l * (8 + R + 2 * h + 2 * h)
-    b_src = bb - b_dst
-    # the dst-major re-gather of the reference's backward (b_dst) is eliminated algorithmically: the src pass
-    # produces the per-edge dot products from the rows it gathers anyway.  Per-kernel rooflines count only
-    # the bytes of the kernel's own gather; `whole_step` keeps SURVEY's full fwd+bwd figure.
+        hbm_peak, hbm_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md); MEASURED_PEAKS.json absent"
+    l2_peak = None
+    l2path = os.path.join(ROOT, "profiles", "l2_peak.json")
+    if os.path.exists(l2path):
+        l2_peak = float(json.load(open(l2path))["l2_read_gbs"])
+    bf, b_src = performed_bytes(E_local, n_src_l, n_dst_l, H, D, c["er"], c["ee"])
     alg = {"gat_fwd": bf, "gat_bwd_src": b_src}
+    # the gathers are served by the L2 when one head's (N x D) slab of the gathered table fits it:
+    # then the L2 -> SM bandwidth is the bound that applies; otherwise (products) the rows come from DRAM
+    slab_mb = max(n_src_l, n_dst_l) * D * 4 / 2**20
+    l2_bound = l2_peak is not None and slab_mb <= 64.0
     kernels = {}
     for name, (n, tot) in ktot.items():
         avg = tot / n
-        k = {"launches": n, "avg_ms": round(avg, 4), "share_of_step": round(tot / ms_total, 4)}
+        k = {"launches": n, "avg_ms": round(avg, 4), "share_of_instrumented_step": round(tot / ms_instr, 4)}
         if name in alg:
             k["algorithmic_bytes"] = alg[name]
             k["achieved_GBs"] = round(alg[name] / (avg * 1e-3) / 1e9, 1)
-            k["frac_of_peak"] = round(k["achieved_GBs"] / peak, 4)
+            k["frac_of_hbm_peak"] = round(k["achieved_GBs"] / hbm_peak, 4)
+            if l2_peak:
+                k["frac_of_l2_peak"] = round(k["achieved_GBs"] / l2_peak, 4)
         kernels[name] = k
     dom = max((n for n in kernels if n in alg), key=lambda n: kernels[n]["avg_ms"] * kernels[n]["launches"])
-    traffic = None
+    # DRAM bytes per launch from ncu, only if a capture of THIS shape and GPU count is committed (tools/profile_round.sh)
+    traffic, dram_step = None, None
     tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(dom)
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_GBs"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["frac_of_peak"], "traffic": traffic, "peak_source": peak_src,
+        tj = json.load(open(tpath)).get(shape, {}).get(str(world), {})
+        traffic = tj.get(dom)
+        if tj.get("_step_total"):
+            dram_step = {"bytes_per_step": tj["_step_total"], "GBs": round(tj["_step_total"] / (ms_step * 1e-3) / 1e9, 1),
+                         "frac_of_hbm_peak": round(tj["_step_total"] / (ms_step * 1e-3) / 1e9 / hbm_peak, 4),
+                         "source": tj.get("_source")}
+    peak = l2_peak if l2_bound else hbm_peak
+    step_bytes = bf + b_src
+    roofline = {"bound": "l2" if l2_bound else "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_GBs"], "peak": peak,
+                "unit": "GB/s", "frac": round(kernels[dom]["achieved_GBs"] / peak, 4), "traffic": traffic,
+                "peak_source": "profiles/l2_peak.json (L2 -> SM read bandwidth measured on this pool with tools/l2peak.cu)"
+                if l2_bound else hbm_src,
                 "algorithmic_bytes_per_launch": alg[dom],
-                "whole_step": {"algorithmic_bytes": bf + bb,
-                               "achieved_GBs": round((bf + bb) / (ms_step * 1e-3) / 1e9, 1),
-                               "frac": round((bf + bb) / (ms_step * 1e-3) / 1e9 / peak, 4)}}
+                "hbm": {"peak": hbm_peak, "frac": kernels[dom]["frac_of_hbm_peak"], "peak_source": hbm_src},
+                "whole_step": {"performed_bytes": step_bytes, "achieved_GBs": round(step_bytes / (ms_step * 1e-3) / 1e9, 1),
+                               "frac_of_bound_peak": round(step_bytes / (ms_step * 1e-3) / 1e9 / peak, 4),
+                               "frac_of_hbm_peak": round(step_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak, 4),
+                               "dram": dram_step,
+                               "note": "bytes of the passes actually performed (forward gather + ONE backward gather + node pass); "
+                                       "SURVEY 8d's figure additionally counts the reference's dst-major re-gather, which this "
+                                       "engine eliminates"},
+                "note": ("achieved = SURVEY 8d gather-model bytes of the kernel's own pass / its CUDA-event time.  bound = l2: every "
+                         f"(N x D) head slab of the gathered table ({slab_mb:.0f} MB) is L2-resident by construction, so the "
+                         "model's bytes are L2 -> SM traffic and the HBM fraction (`hbm`) exceeds 1; `traffic` = DRAM bytes ncu "
+                         "measured for this launch, or null when no capture of this shape / GPU count is committed")
+                if l2_bound else "achieved = SURVEY 8d gather-model bytes of the kernel's own pass / its CUDA-event time; the "
+                                 f"gathered head slab ({slab_mb:.0f} MB) exceeds the L2, rows come from DRAM"}
 
-    # second roofline: the feature slabs are L2-resident by construction, so the gathers are
-    # bounded by L2 -> SM bandwidth, measured on this pool with tools/l2peak.cu (profiles/l2_peak.json)
-    l2path = os.path.join(ROOT, "profiles", "l2_peak.json")
-    if os.path.exists(l2path):
-        l2peak = float(json.load(open(l2path))["l2_read_gbs"])
-        roofline["l2"] = {"bound": "l2", "peak": l2peak, "unit": "GB/s", "peak_source": "profiles/l2_peak.json (measured)",
-                          "kernels": {n: {"achieved": kernels[n]["achieved_GBs"],
-                                          "frac": round(kernels[n]["achieved_GBs"] / l2peak, 4)} for n in alg if n in kernels}}
-    roofline["note"] = ("achieved = SURVEY 8d gather-model bytes / CUDA-event time; it exceeds the HBM peak because each "
-                        "(N x D) head slab stays L2-resident: `traffic` is the DRAM bytes ncu measured for the same launch")
+    # ---------------- value parity of THIS run against the row-subsample oracle (checker only) ----------------
+    parity = None
+    if world == 1 and rank == 0 and not args.no_parity:
+        parity = parity_check(graph, full_src, full_dst, n_nodes, c, ft_own, el_own, er, ee, gout, cs_l, ds_l, step_resident, dev)
+        for t in leaves:
+            t.grad = None
+    del full_src, full_dst
 
-    del ft_own, el_own, er, ee, gout
+    del ft_own, el_own, er, ee, gout, leaves
     torch.cuda.empty_cache()
 
-    # ---------------- end-to-end leg through GATConv.forward with host buffers ----------------
-    e2e = None
-    if world == 1:
-        torch.manual_seed(0)
-        conv = GATConv(HEADS * HID, EDGE_EMB, HID, n_heads=HEADS, edge_drop=EDGE_DROP).to(dev)
-        conv.train()
-        h_host = torch.randn(n_nodes, HEADS * HID).pin_memory()
-        fe_host = torch.randn(n_edges, EDGE_EMB).pin_memory()
-        h2d = h_host.numel() * 4 + fe_host.numel() * 4
-
-        copy_stream = torch.cuda.Stream()
-
-        def finish(y):
-            loss = y.square().mean()
-            loss.backward()
-            conv.zero_grad(set_to_none=True)
-            return float(loss.item())  # device -> host read of the step's result
-
-        def step_serial():
-            # copy and layer of the same step back to back (how the reference's loop is written): node features first
-            # (the projections need them at once), edge features on a copy stream so that their 2.5 GB transfer
-            # overlaps the node-side GEMMs and the edge-drop draw (bot_b200.Deferred)
-            h = h_host.to(dev, non_blocking=True).requires_grad_(True)
-            with torch.cuda.stream(copy_stream):
-                fe = fe_host.to(dev, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-            return finish(conv(graph, h, bot_b200.Deferred(fe, ev, requires_grad=True)))
-
-        def run_serial(k):
-            for _ in range(k):
-                step_serial()
-
-        def run_fed(k):
-            # bot_b200.HostFeed: the copies of step i+1 are enqueued before step i's layer and run beside it
-            # (two device buffer sets); every step still copies its own 2.8 GB and reads its loss back
-            feed = bot_b200.HostFeed(dev, depth=2)
-            feed.submit(h_host, fe_host)
-            for i in range(k):
-                if i + 1 < k:
-                    feed.submit(h_host, fe_host)
-                h, fe = feed.take(requires_grad=(0, 1))
-                finish(conv(graph, h, fe))
-
-        def timed(run, k):
-            torch.cuda.synchronize()
-            e0.record()
-            run(k)
-            e1.record()
-            torch.cuda.synchronize()
-            return e0.elapsed_time(e1) / k
-
-        w_e2e = max(1, min(args.warmup, 3))
-        run_serial(w_e2e)
-        k_serial = max(1, min(args.steps, 5))
-        ms_serial = timed(run_serial, k_serial)
-        torch.cuda.empty_cache()
-        run_fed(w_e2e)
-        k_e2e = max(1, args.steps)
-        ms_e2e = timed(run_fed, k_e2e)
-        e2e = {"value": n_edges / (ms_e2e * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-               "ms_per_step": round(ms_e2e, 3), "steps": k_e2e,
-               "call": "bot_b200.ogbn_proteins.GATConv.forward(graph, feat_src, feat_edge) + backward; feat_src (N,480) and "
-                       "feat_edge (E,16) copied from pinned host memory every step through bot_b200.HostFeed (double-buffered: "
-                       "step i+1's copy is enqueued before step i's layer; the first copy and the last layer of the timed "
-                       "region are not overlapped), loss read back every step; graph structure resident (the reference moves "
-                       "the graph once, run.py:539); includes the five nn.Linear projections",
-               "unpipelined": {"ms_per_step": round(ms_serial, 3), "value": n_edges / (ms_serial * 1e-3), "steps": k_serial,
-                               "note": "same call with each step's copy issued inside the step (no prefetch)"}}
-        del conv, h_host, fe_host
-        torch.cuda.empty_cache()
-    else:
-        # the same layer call as at N=1, partitioned: every rank feeds ITS shard — the node features of its owned rows and
-        # the edge features of its local edges — from pinned host memory through bot_b200.HostFeed, runs the node-side
-        # projections on its rows, the partitioned sparse section (halo all-gather / reduce-scatter inside), all-reduces
-        # the weight gradients and reads its loss back
-        from bot_b200.functional import edge_logits
-
-        torch.manual_seed(0)
-        conv = GATConv(HEADS * HID, EDGE_EMB, HID, n_heads=HEADS, edge_drop=EDGE_DROP).to(dev)   # same weights everywhere
-        conv.train()
-        host_shard = [torch.randn(n_own, HEADS * HID).pin_memory(), torch.randn(E_local, EDGE_EMB).pin_memory()]
-        h2d_rank = sum(t.numel() * 4 for t in host_shard)
-        params = [p for p in conv.parameters()]
-
-        def run_fed_ranks(k):
-            feed = bot_b200.HostFeed(dev, depth=2)
-            feed.submit(*host_shard)
-            for i in range(k):
-                if i + 1 < k:
-                    feed.submit(*host_shard)
-                x, fe = (d.wait() for d in feed.take(requires_grad=(0, 1)))
-                ft = conv.src_fc(x).view(-1, HEADS, HID)
-                resid = conv.dst_fc(x).view(-1, HEADS, HID)
-                el, er = conv.attn_src_fc(x), conv.attn_dst_fc(x)
-                ee = edge_logits(fe, conv.attn_edge_fc.weight)
-                keep = functional.edge_drop_keep(E_local, int(E_local * EDGE_DROP), next(seeds), dev)
-                y = layer.gat(ft, el, er, ee, keep, None, None, None, SLOPE, 0.0, 0) + resid
-                loss = y.square().mean()
-                loss.backward()
-                flat = torch.cat([p.grad.flatten() for p in params])
-                dist.all_reduce(flat)                      # data-parallel weight gradients
-                conv.zero_grad(set_to_none=True)
-                float(loss.item())  # device -> host read of the step's result
-
-        run_fed_ranks(max(1, min(args.warmup, 3)))
-        k_e2e = max(1, args.steps)
-        barrier()
-        e0.record()
-        run_fed_ranks(k_e2e)
-        e1.record()
-        barrier()
-        t = torch.tensor([e0.elapsed_time(e1), float(h2d_rank)], device=dev, dtype=torch.float64)
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        ms_e2e = float(tmax[0].item()) / k_e2e
-        e2e = {"value": n_edges / (ms_e2e * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": int(t[1].item()),
-               "d2h_bytes_per_step": 4 * world, "ms_per_step": round(ms_e2e, 3), "steps": k_e2e,
-               "call": "the N=1 layer, partitioned: on every rank nn.Linear projections of its owned rows + "
-                       "bot_b200.partition.PartitionedGraph.gat + residual + backward + all-reduce of the weight gradients; each "
-                       "rank copies its shard (feat_src of its rows, feat_edge of its local edges) from pinned host memory every "
-                       "step through bot_b200.HostFeed (step i+1's copy enqueued before step i's layer) and reads its loss back; "
-                       "max over ranks; h2d bytes summed over ranks"}
-        del host_shard, conv
+    e2e = run_e2e(args, shape, c, graph, layer, world, rank, dev, n_nodes, n_edges, n_own, E_local, cs_l, ds_l, cs_own, barrier,
+                  seeds, replicas)
 
     # secondary number: the same layer on a heavy-tailed graph (dst ~ rank^-0.8; the hottest row has ~2 % of all edges)
     skew = None
-    if world == 1 and not args.no_skew:
+    if world == 1 and not args.no_skew and shape == "proteins":
         s2, d2 = synth_edges(n_nodes, n_edges, dev, seed=0, power_law=0.8)
         g2 = bot_b200.Graph(s2, d2, n_nodes)
         g2.create_formats_()
         del s2, d2
         gen2 = torch.Generator(device=dev).manual_seed(2)
-        t_ft = torch.randn(n_nodes, HEADS, HID, device=dev, generator=gen2).requires_grad_(True)
-        t_el = torch.randn(n_nodes, HEADS, device=dev, generator=gen2).requires_grad_(True)
-        t_er = torch.randn(n_nodes, HEADS, device=dev, generator=gen2).requires_grad_(True)
-        t_ee = torch.randn(n_edges, functional.pad_heads(HEADS), device=dev, generator=gen2).requires_grad_(True)
-        t_go = torch.randn(n_nodes, HEADS, HID, device=dev, generator=gen2)
+        t_ft = torch.randn(n_nodes, H, D, device=dev, generator=gen2).requires_grad_(True)
+        t_el = torch.randn(n_nodes, H, device=dev, generator=gen2).requires_grad_(True)
+        t_er = torch.randn(n_nodes, H, device=dev, generator=gen2).requires_grad_(True)
+        t_ee = torch.randn(n_edges, functional.pad_heads(H), device=dev, generator=gen2).requires_grad_(True)
+        t_go = torch.randn(n_nodes, H, D, device=dev, generator=gen2)
 
         def step_skew():
-            keep = functional.edge_drop_keep(n_edges, int(n_edges * EDGE_DROP), next(seeds), dev)
-            gat_fused(g2, t_ft, t_el, t_er, t_ee, keep, None, None, None, SLOPE, 0.0, 0).backward(t_go)
+            keep = functional.edge_drop_keep(n_edges, int(n_edges * c["edge_drop"]), next(seeds), dev)
+            gat_fused(g2, t_ft, t_el, t_er, t_ee, keep, None, None, None, SLOPE, 0.0, 0, edge_order="canonical").backward(t_go)
             for t in (t_ft, t_el, t_er, t_ee):
                 t.grad = None
 
@@ -517,27 +556,193 @@ def run_ours(args):
         del g2, t_ft, t_el, t_er, t_ee, t_go
         torch.cuda.empty_cache()
 
-    cpu_baseline = None
+    cpu_baseline = cora = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_port_run(steps=2, warmup=1)
+        r = cpu_port_run(shape, steps=2, warmup=1, budget_s=25.0)
         cpu_baseline = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cora = cora_cpu_reference()
 
     if rank == 0:
+        cfg = common_config(shape, n_nodes, n_edges, world)
         line = {
-            "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(n_nodes, n_edges), "l2": "inputs_exceed_l2 (no flush between iterations: "
-                       "the per-step working set, >= 2.5 GB, is 20x the 126 MB L2)",
-                       "parallelism": "single GPU" if world == 1 else f"1-D dst-row partition x{world}, halo all-gather + "
-                       "gradient reduce-scatter (NCCL)",
-                       "timed": "edge-drop mask draw (exactly int(E*p) edges, botgat_edge_drop_draw) + edge staging + fused fwd + bwd (node/src/dst passes) + edge unstage"},
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "e2e": e2e, "skew_variant": skew,
+            "metric": metric_name(shape), "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak" if replicas else "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "roofline": roofline, "kernels": kernels, "instrumented_ms_per_step": round(ms_instr / args.steps, 4),
+            "graph": {"canonical_edge_order": bool(info.in_eid_identity), "transpose_tiles": [int(info.tiles_src), int(info.tiles_dst)],
+                      "split_row_slots": [int(info.n_slots_in), int(info.n_slots_out)]},
+            "parity": parity, "cpu_baseline": cpu_baseline, "config1_cora_cpu_reference": cora, "e2e": e2e, "skew_variant": skew,
             "gpu_launches": int(launches), "clocks": clocks,
         }
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def parity_check(graph, src, dst, n_nodes, c, ft, el, er, ee, gout, cs, ds, step, dev, n_v=400, n_u=6):
+    """One more (untimed) step of the resident leg, compared on a random sample of rows with the fp64 row-subsample
+    oracle (oracle/gat_rows.py — the CHECKER; nothing on the measured path touches it)."""
+    from oracle import gat_rows
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import philox_attn_mul, rel_err
+
+    H = c["H"]
+    sd = 424242
+    out, keep = step(keep_grads=True, seed=sd)
+    torch.cuda.synchronize()
+    perm = graph.edge_perm()
+    if perm is not None:        # the resident operands are in canonical order: show the oracle the COO in that order
+        src, dst = src[perm], dst[perm]
+    rs = torch.Generator().manual_seed(7)
+    V = torch.randperm(n_nodes, generator=rs)[:n_v].to(dev)
+    U = torch.randperm(n_nodes, generator=rs)[:n_u].to(dev)
+    W = torch.unique(torch.cat([V, gat_rows.adjacent_dst(src, dst, n_nodes, U)]))
+    sub = gat_rows.build_sub(src, dst, n_nodes, n_nodes, W, ft=ft, el=el, er=er, ee=ee, keep=keep, src_scale=cs, dst_scale=ds, gout=gout)
+    if c["attn_p"] > 0:
+        sub["attn_mul"] = philox_attn_mul(sd, 0, H, c["attn_p"], eids=sub["eid"].numpy()).double()
+    ref = gat_rows.eval_explicit(sub, SLOPE)
+    Wd, Ud, comp = sub["W"].to(dev), sub["U"].to(dev), sub["complete"]
+    errs = {"out": rel_err(out[Wd], ref["out"]),
+            "grad_ft": rel_err(ft.grad[Ud][comp.to(dev)], ref["grad_ft"][comp]),
+            "grad_el": rel_err(el.grad[Ud][comp.to(dev)], ref["grad_el"][comp])}
+    if er is not None:
+        errs["grad_er"] = rel_err(er.grad[Wd], ref["grad_er"])
+    if ee is not None:
+        errs["grad_ee"] = rel_err(ee.grad[sub["eid"].to(dev)][:, :H], ref["grad_ee"])
+    return {"parity_max_rel": max(errs.values()), "forward_max_rel": errs["out"],
+            "grad_max_rel": max(v for k, v in errs.items() if k != "out"), "per_tensor": errs,
+            "tolerance": {"forward": 1e-5, "grad": 1e-4}, "ok": errs["out"] <= 1e-5 and all(v <= 1e-4 for v in errs.values()),
+            "rows_checked": {"dst": int(W.numel()), "src": int(comp.sum()), "edges": int(sub["e_src"].numel())},
+            "checker": "oracle/gat_rows.py eval_explicit (fp64) on all in-edges of the sampled rows; metric max|x-ref|/max|ref|"}
+
+
+def run_e2e(args, shape, c, graph, layer, world, rank, dev, n_nodes, n_edges, n_own, E_local, cs_l, ds_l, cs_own, barrier, seeds,
+            replicas):
+    """The same metric through the reference-facing module call with HOST buffers: every step copies its inputs from
+    pinned host memory (bot_b200.HostFeed, double-buffered) and reads its loss back."""
+    import torch.distributed as dist
+
+    import bot_b200
+    from bot_b200 import functional
+
+    H, D, F_in = c["H"], c["D"], c["in_feats"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.manual_seed(0)
+    v2 = shape in ("proteins", "products")
+    if v2:
+        from bot_b200.ogbn_proteins import GATConv
+
+        conv = GATConv(F_in, EDGE_EMB if c["ee"] else 0, D, n_heads=H, edge_drop=c["edge_drop"]).to(dev)
+        enc = torch.nn.Linear(EDGE_FEATS, EDGE_EMB).to(dev) if c["ee"] else None      # the model's per-layer edge_encoder[i]
+    else:
+        from bot_b200.no_sampling import GATConv
+
+        conv = GATConv(F_in, D, num_heads=H, attn_drop=c["attn_p"], use_symmetric_norm=True).to(dev)
+        conv.attn_dropout_mode = "fused"
+        enc = None
+    conv.train()
+    params = list(conv.parameters()) + (list(enc.parameters()) if enc is not None else [])
+    host = [torch.randn(n_own, F_in).pin_memory()]
+    if c["ee"]:
+        # RAW 8-dim edge features of this rank's edges, stored in the graph's canonical edge order (static data: permuted
+        # once when it was assigned, bot_b200.graph.EdgeFrame); the layer's fused encoder turns them into logits on the GPU
+        host.append(torch.rand(E_local, EDGE_FEATS).pin_memory())
+    h2d = sum(t.numel() * 4 for t in host)
+
+    def layer_call(x, fe):
+        if layer is None:
+            if v2:
+                fe_arg = None if fe is None else bot_b200.EdgeEmbedding(fe.wait(), enc, canonical=True)
+                return conv(graph, x, fe_arg)
+            return conv(graph, x.wait() if isinstance(x, bot_b200.Deferred) else x)
+        # partitioned: the module's body spelled out around PartitionedGraph.gat (projections of the OWNED rows only)
+        x = x.wait() if isinstance(x, bot_b200.Deferred) else x
+        sd = next(seeds)
+        keep = functional.edge_drop_keep(E_local, int(E_local * c["edge_drop"]), sd, dev) if c["edge_drop"] > 0 else None
+        if v2:
+            ft = conv.src_fc(x).view(-1, H, D)
+            resid = conv.dst_fc(x).view(-1, H, D)
+            el, er = conv.attn_src_fc(x), conv.attn_dst_fc(x)
+            ee = bot_b200.EdgeEmbedding(fe.wait(), enc, canonical=True).logits(conv.attn_edge_fc.weight) if fe is not None else None
+            return layer.gat(ft, el, er, ee, keep, None, None, None, SLOPE, 0.0, 0, edge_order="canonical") + resid
+        ft = conv.fc(x).view(-1, H, D)
+        el = torch.einsum("nhd,hd->nh", ft, conv.attn_l[0]) * cs_own.unsqueeze(-1)      # el from the scaled ft, models.py:517
+        return layer.gat(ft, el, None, None, keep, None, cs_l, ds_l, SLOPE, c["attn_p"], sd, edge_order="canonical") \
+            + conv.res_fc(x).view(-1, H, D)
+
+    def finish(y):
+        loss = y.square().mean()
+        loss.backward()
+        if world > 1 and not replicas:
+            flat = torch.cat([p.grad.flatten() for p in params if p.grad is not None])
+            dist.all_reduce(flat)                      # data-parallel weight gradients
+        for p in params:
+            p.grad = None
+        return float(loss.item())  # device -> host read of the step's result
+
+    def run_fed(k):
+        # bot_b200.HostFeed: the copies of step i+1 are enqueued before step i's layer and run beside it
+        feed = bot_b200.HostFeed(dev, depth=2)
+        feed.submit(*host)
+        for i in range(k):
+            if i + 1 < k:
+                feed.submit(*host)
+            got = feed.take(requires_grad=(0,))
+            finish(layer_call(got[0], got[1] if len(got) > 1 else None))
+
+    def run_serial(k):
+        # copy and layer of the same step back to back (how the reference's loop is written)
+        for _ in range(k):
+            feed = bot_b200.HostFeed(dev, depth=1)
+            feed.submit(*host)
+            got = feed.take(requires_grad=(0,))
+            finish(layer_call(got[0], got[1] if len(got) > 1 else None))
+
+    def timed(run, k):
+        barrier()
+        e0.record()
+        run(k)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / k
+
+    w_e2e = max(1, min(args.warmup, 3))
+    unp = None
+    if world == 1:
+        run_serial(w_e2e)
+        k_serial = max(1, min(args.steps, 5))
+        ms_serial = timed(run_serial, k_serial)
+        unp = {"ms_per_step": round(ms_serial, 3), "value": n_edges / (ms_serial * 1e-3), "steps": k_serial,
+               "note": "same call with each step's copy issued inside the step (no prefetch)"}
+        torch.cuda.empty_cache()
+    run_fed(w_e2e)
+    k_e2e = max(1, args.steps)
+    ms_e2e = timed(run_fed, k_e2e)
+    h2d_total = h2d
+    if world > 1:
+        t = torch.tensor([float(h2d)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        h2d_total = int(t.item())
+    total_edges = n_edges * (world if replicas else 1)
+    call = ("bot_b200.ogbn_proteins.GATConv.forward(graph, feat_src, EdgeEmbedding(raw efeat, edge_encoder))" if shape == "proteins" else
+            "bot_b200.ogbn_products.GATConv.forward(graph, feat_src)" if shape == "products" else
+            "bot_b200.no_sampling.GATConv.forward(graph, feat)")
+    return {"value": total_edges / (ms_e2e * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": 4 * world,
+            "ms_per_step": round(ms_e2e, 3), "steps": k_e2e,
+            "call": call + " + backward" + ("" if world == 1 else ", partitioned: every rank projects its OWNED rows, runs "
+                    "PartitionedGraph.gat (halo all-gather / gradient reduce-scatter inside), all-reduces the weight gradients") +
+                    f"; per step every rank copies feat_src ({n_own} x {F_in})" + (f" and the RAW edge features ({E_local} x {EDGE_FEATS}, "
+                    "canonical edge order)" if c["ee"] else "") + " from pinned host memory through bot_b200.HostFeed (double-buffered: step "
+                    "i+1's copy is enqueued before step i's layer) and reads its loss back; graph structure resident (the reference "
+                    "moves the graph once, run.py:539); dense nn.Linear projections included; max over ranks",
+            "unpipelined": unp}
 
 
 def main():
@@ -547,10 +752,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--nodes", type=int, default=N_NODES)
-    ap.add_argument("--edges", type=int, default=N_EDGES)
+    ap.add_argument("--shape", default="proteins", choices=list(SHAPES),
+                    help="BASELINE.json config to run (default: the headline ogbn-proteins shape)")
+    ap.add_argument("--nodes", type=int, default=0, help="override the shape's node count (developer runs)")
+    ap.add_argument("--edges", type=int, default=0, help="override the shape's edge count (developer runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-skew", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

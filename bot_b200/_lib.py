@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BOTGAT_LIB") or os.path.join(_HERE, "libbotgat.so")  # BOTGAT_LIB: developer A/B builds
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_i64p = C.POINTER(C.c_int64)
 c_vp = C.c_void_p
@@ -26,6 +26,7 @@ class GraphInfo(C.Structure):
         ("max_in_deg", C.c_int64), ("max_out_deg", C.c_int64),
         ("has_zero_in_degree", C.c_int32), ("device", C.c_int32),
         ("n_slots_in", C.c_int64), ("n_slots_out", C.c_int64),
+        ("in_eid_identity", C.c_int32), ("tiles_src", C.c_int32), ("tiles_dst", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 

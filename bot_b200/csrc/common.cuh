@@ -68,6 +68,13 @@ struct botgat_graph {
   int32_t *in_indptr = nullptr, *in_indices = nullptr, *in_eid = nullptr;
   int32_t *out_indptr = nullptr, *out_indices = nullptr, *out_eid = nullptr;
   int32_t *in_deg = nullptr, *out_deg = nullptr;
+  // Canonical edge numbering: in_eid[p] == p for every p (the COO came sorted by destination), so edge-ordered
+  // operands ARE in in-CSR order and, with the COO sorted by (dst, src), both CSRs have sorted neighbour lists.
+  int in_eid_identity = 0;
+  // Cache-blocked traversal of the out-CSR for the in <-> out transposes of per-edge records (edge_ops.cu): the
+  // out-CSR positions grouped by (source block, destination block), tiles_s x tiles_d blocks; nullptr = plain order.
+  int32_t* out_tile_order = nullptr;
+  int tiles_s = 1, tiles_d = 1;
   // Row splitting for heavy-tailed degree distributions.  When a CSR has a row longer than the segment length,
   // its work items are SEGMENTS (at most seg_len neighbours of one row) instead of rows: a heavy row is spread over
   // several warps whose partial results go to scratch slots and are merged by a combine kernel.  Empty = no split.

@@ -107,11 +107,18 @@ __global__ void k_pack_keep(int64_t n_edges, const uint8_t* __restrict__ keep, u
   }
 }
 
+// `order` (optional): the CSR positions in the order they are to be visited — the cache-blocked traversal of the
+// out-CSR (common.cuh `out_tile_order`).  With the canonical edge numbering a (source block x destination block)
+// tile is a set of RUNS on both sides: consecutive threads still write consecutive CSR positions, and the records
+// they read lie inside a few-MB window of the edge-ordered array that the L2 holds until every 128-byte line
+// (4 records) has been used — instead of one DRAM line fill per 32-byte record.
 template <int VEC, int PF>
 __global__ void k_edge_stage(int64_t n_edges, int h0, int Hn, const int32_t* __restrict__ eid,
+                             const int32_t* __restrict__ order,
                              const float* __restrict__ src, int64_t ld, const uint8_t* __restrict__ keep,
                              const uint32_t* __restrict__ keep_bits, float* __restrict__ dst) {
-  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_edges; p += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_edges; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = order ? __ldg(order + t) : t;
     const int64_t e = __ldg(eid + p);
     float v[kHMax];
 #pragma unroll
@@ -128,8 +135,10 @@ __global__ void k_edge_stage(int64_t n_edges, int h0, int Hn, const int32_t* __r
 // and receive zeros.
 template <int VEC>
 __global__ void k_edge_unstage(int64_t n_edges, int h0, int Hn, int Hw, const int32_t* __restrict__ eid,
+                               const int32_t* __restrict__ order,
                                const float* __restrict__ gz, float* __restrict__ dst, int64_t ld) {
-  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_edges; p += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_edges; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = order ? __ldg(order + t) : t;
     const int64_t e = __ldg(eid + p);
     float v[kHMax];
 #pragma unroll
@@ -199,12 +208,14 @@ static inline int grid_for(int64_t n, int block = 256) {
     default: { constexpr int PF = 0; CALL; break; }    \
   }
 
-static int stage_one(const botgat_graph* g, const int32_t* eid, int H, const float* src, int64_t ld,
+static int stage_one(const botgat_graph* g, const int32_t* eid, const int32_t* order, int H, const float* src, int64_t ld,
                      const uint8_t* keep, float* dst, cudaStream_t st) {
   const int pf = env_pf();
   // large masks are looked up as bits (L2-resident); the scratch words come from and return to the stream-ordered pool
   uint32_t* keep_bits = nullptr;
-  if (keep && src && g->n_edges >= (1 << 20)) {  // keep alone: the byte lookup is cheaper than pack + bit lookup (measured)
+  // (not for the in-order pass of a canonically numbered graph: its byte lookups are coalesced)
+  const bool coalesced = eid == g->in_eid && g->in_eid_identity;
+  if (keep && src && g->n_edges >= (1 << 20) && !coalesced) {  // keep alone: the byte lookup is cheaper than pack + bit lookup (measured)
     BG_CHECK(cudaMallocAsync(&keep_bits, sizeof(uint32_t) * (size_t)((g->n_edges + 31) / 32), st));
     k_pack_keep<<<grid_for(g->n_edges), 256, 0, st>>>(g->n_edges, keep, keep_bits);
     BG_LAUNCHED(1);
@@ -217,9 +228,9 @@ static int stage_one(const botgat_graph* g, const int32_t* eid, int H, const flo
     const int Hn = std::min(kHMax, H - h0);
     const int vec = src ? record_vec(src + h0, ld, Hn) : 1;
     const int grid = grid_for(g->n_edges);
-    if (vec == 4) { BG_PF_SWITCH((k_edge_stage<4, PF><<<grid, 256, 0, st>>>(g->n_edges, h0, Hn, eid, src, ld, keep, keep_bits, dst))) }
-    else if (vec == 2) { BG_PF_SWITCH((k_edge_stage<2, PF><<<grid, 256, 0, st>>>(g->n_edges, h0, Hn, eid, src, ld, keep, keep_bits, dst))) }
-    else { BG_PF_SWITCH((k_edge_stage<1, PF><<<grid, 256, 0, st>>>(g->n_edges, h0, Hn, eid, src, ld, keep, keep_bits, dst))) }
+    if (vec == 4) { BG_PF_SWITCH((k_edge_stage<4, PF><<<grid, 256, 0, st>>>(g->n_edges, h0, Hn, eid, order, src, ld, keep, keep_bits, dst))) }
+    else if (vec == 2) { BG_PF_SWITCH((k_edge_stage<2, PF><<<grid, 256, 0, st>>>(g->n_edges, h0, Hn, eid, order, src, ld, keep, keep_bits, dst))) }
+    else { BG_PF_SWITCH((k_edge_stage<1, PF><<<grid, 256, 0, st>>>(g->n_edges, h0, Hn, eid, order, src, ld, keep, keep_bits, dst))) }
     BG_LAUNCHED(1);
     BG_CHECK(cudaGetLastError());
   }
@@ -243,12 +254,13 @@ extern "C" int botgat_edge_stage(const botgat_graph* g, int order, int32_t H, co
   DeviceGuard guard(g->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int32_t* eid = order == BOTGAT_ORDER_IN ? g->in_eid : g->out_eid;
+  const int32_t* visit = order == BOTGAT_ORDER_OUT ? g->out_tile_order : nullptr;
   if (eb) {
-    int rc = stage_one(g, eid, ee ? H : 1, ee, ld_ee, keep, eb, st);
+    int rc = stage_one(g, eid, visit, ee ? H : 1, ee, ld_ee, keep, eb, st);
     if (rc) return rc;
   }
   if (am) {
-    int rc = stage_one(g, eid, H, attn_mul, ld_am, nullptr, am, st);
+    int rc = stage_one(g, eid, visit, H, attn_mul, ld_am, nullptr, am, st);
     if (rc) return rc;
   }
   return 0;
@@ -264,14 +276,15 @@ extern "C" int botgat_edge_unstage(const botgat_graph* g, int order, int32_t H, 
   DeviceGuard guard(g->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int32_t* eid = order == BOTGAT_ORDER_IN ? g->in_eid : g->out_eid;
+  const int32_t* visit = order == BOTGAT_ORDER_OUT ? g->out_tile_order : nullptr;
   for (int h0 = 0; h0 < ld_gee; h0 += kHMax) {
     const int Hn = std::max(0, std::min(kHMax, H - h0));              // heads in this pass
     const int Hw = (int)std::min<int64_t>(kHMax, ld_gee - h0);        // floats written (heads + zeroed padding)
     const int vec = record_vec(grad_ee + h0, ld_gee, Hw);
     const int grid = grid_for(g->n_edges);
-    if (vec == 4) k_edge_unstage<4><<<grid, 256, 0, st>>>(g->n_edges, h0, Hn, Hw, eid, gz, grad_ee, ld_gee);
-    else if (vec == 2) k_edge_unstage<2><<<grid, 256, 0, st>>>(g->n_edges, h0, Hn, Hw, eid, gz, grad_ee, ld_gee);
-    else k_edge_unstage<1><<<grid, 256, 0, st>>>(g->n_edges, h0, Hn, Hw, eid, gz, grad_ee, ld_gee);
+    if (vec == 4) k_edge_unstage<4><<<grid, 256, 0, st>>>(g->n_edges, h0, Hn, Hw, eid, visit, gz, grad_ee, ld_gee);
+    else if (vec == 2) k_edge_unstage<2><<<grid, 256, 0, st>>>(g->n_edges, h0, Hn, Hw, eid, visit, gz, grad_ee, ld_gee);
+    else k_edge_unstage<1><<<grid, 256, 0, st>>>(g->n_edges, h0, Hn, Hw, eid, visit, gz, grad_ee, ld_gee);
     BG_LAUNCHED(1);
     BG_CHECK(cudaGetLastError());
   }

@@ -143,6 +143,27 @@ static inline int grid_for(int64_t n, int block = 256) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(b, 148 * 32));
 }
 
+// *flag = 1 unless eid[p] == p everywhere
+__global__ void k_check_identity(int64_t n, const int32_t* __restrict__ eid, int* __restrict__ flag) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (eid[i] != (int32_t)i) *flag = 1;
+}
+
+// tile key of every out-CSR position: (source block, destination block), source-block-major; one warp per row
+__global__ void k_tile_keys(int n_src, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                            int rows_per_s, int rows_per_d, int tiles_d, int32_t* __restrict__ keys,
+                            int32_t* __restrict__ iota) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < n_src; r += nwarps) {
+    const int ts = r / rows_per_s;
+    for (int p = indptr[r] + lane; p < indptr[r + 1]; p += 32) {
+      keys[p] = ts * tiles_d + indices[p] / rows_per_d;
+      iota[p] = p;
+    }
+  }
+}
+
 static int bits_for(int64_t n) {
   int b = 1;
   while ((1ll << b) < n) ++b;
@@ -214,6 +235,7 @@ static void destroy_impl(botgat_graph* g, bool async, cudaStream_t st) {
     // cudaFree of pool memory synchronises, then releases; it is also the fallback if the stream is unusable
     if (!async || cudaFreeAsync(q, st) != cudaSuccess) { cudaGetLastError(); cudaFree(q); }
   }
+  if (g->out_tile_order && (!async || cudaFreeAsync(g->out_tile_order, st) != cudaSuccess)) { cudaGetLastError(); cudaFree(g->out_tile_order); }
   free_segments(&g->seg_in, async, st); free_segments(&g->seg_out, async, st);
   delete g;
 }
@@ -251,11 +273,11 @@ extern "C" int botgat_graph_create(int64_t n_src, int64_t n_dst, int64_t n_edges
   BG_CHECK(cudaMallocAsync(&g->out_deg, sizeof(int32_t) * (n_src + 1), st));
 
   int32_t *src32 = nullptr, *dst32 = nullptr, *iota = nullptr, *ktmp = nullptr;
-  int* flags = nullptr;  // [bad, max_in, zero_in, max_out, zero_out]
+  int* flags = nullptr;  // [bad, max_in, zero_in, max_out, zero_out, in_eid is not the identity]
   BG_CHECK(cudaMallocAsync(&src32, eb, st)); BG_CHECK(cudaMallocAsync(&dst32, eb, st));
   BG_CHECK(cudaMallocAsync(&iota, eb, st)); BG_CHECK(cudaMallocAsync(&ktmp, eb, st));
-  BG_CHECK(cudaMallocAsync(&flags, sizeof(int) * 5, st));
-  BG_CHECK(cudaMemsetAsync(flags, 0, sizeof(int) * 5, st));
+  BG_CHECK(cudaMallocAsync(&flags, sizeof(int) * 6, st));
+  BG_CHECK(cudaMemsetAsync(flags, 0, sizeof(int) * 6, st));
   if (n_edges > 0) {
     k_narrow_and_check<<<grid_for(n_edges), 256, 0, st>>>(n_edges, src, n_src, src32, iota, flags); BG_LAUNCHED(1);
     k_narrow_and_check<<<grid_for(n_edges), 256, 0, st>>>(n_edges, dst, n_dst, dst32, nullptr, flags); BG_LAUNCHED(1);
@@ -267,15 +289,55 @@ extern "C" int botgat_graph_create(int64_t n_src, int64_t n_dst, int64_t n_edges
   if (rc) return rc;
   if (n_dst > 0) k_deg_stats<<<grid_for(n_dst), 256, 0, st>>>(n_dst, g->in_deg, flags + 1); BG_LAUNCHED(1);
   if (n_src > 0) k_deg_stats<<<grid_for(n_src), 256, 0, st>>>(n_src, g->out_deg, flags + 3); BG_LAUNCHED(1);
+  if (n_edges > 0) k_check_identity<<<grid_for(n_edges), 256, 0, st>>>(n_edges, g->in_eid, flags + 5); BG_LAUNCHED(1);
   BG_CHECK(cudaGetLastError());
-  int h[5];
+  int h[6];
   BG_CHECK(cudaMemcpyAsync(h, flags, sizeof(h), cudaMemcpyDeviceToHost, st));
   BG_CHECK(cudaFreeAsync(src32, st)); BG_CHECK(cudaFreeAsync(dst32, st));
-  BG_CHECK(cudaFreeAsync(iota, st)); BG_CHECK(cudaFreeAsync(ktmp, st));
   BG_CHECK(cudaFreeAsync(flags, st));
   BG_CHECK(cudaStreamSynchronize(st));
+  if (h[0] != 0) { cudaFreeAsync(iota, st); cudaFreeAsync(ktmp, st); }
   BG_REQUIRE(h[0] == 0, "graph_create: node id out of range [0,n_src) / [0,n_dst)");
   g->max_in_deg = h[1]; g->has_zero_in_degree = h[2] > 0; g->max_out_deg = h[3];
+  g->in_eid_identity = h[5] == 0;
+  // Cache-blocked out-CSR traversal for the in <-> out record transposes (edge_ops.cu).  Worth it only when both
+  // sides of a (source block x destination block) tile are RUNS inside their CSR rows — which needs sorted neighbour
+  // lists (the canonical numbering) and enough neighbours per row and block.
+  {
+    int ts = 1, td = 1;
+    const char* force = getenv("BOTGAT_TILES");  // "ts,td" (tests / sweeps); "0" = off
+    if (force && *force) {
+      if (sscanf(force, "%d,%d", &ts, &td) != 2) ts = td = 1;
+    } else if (g->in_eid_identity && n_edges >= (1 << 22) && n_src > 0 && n_dst > 0) {
+      const double avg_in = (double)n_edges / n_dst, avg_out = (double)n_edges / n_src;
+      const int cap_s = std::max(1, (int)(avg_in / 16)), cap_d = std::max(1, (int)(avg_out / 16));  // runs >= 16 records
+      const double need = (double)n_edges * 32.0 / ((double)env_int("BOTGAT_TILE_MB", 20) * (1 << 20));  // tiles wanted
+      int want = 1;
+      while ((double)want * want < need) ++want;
+      ts = std::min(want, cap_s); td = std::min(want, cap_d);
+      while ((double)ts * td < need && ts < cap_s) ++ts;
+      while ((double)ts * td < need && td < cap_d) ++td;
+      if ((double)ts * td < need * 0.5) ts = td = 1;  // rows too short to block this graph down to the L2: plain order
+    }
+    ts = std::max(1, std::min(ts, 64)); td = std::max(1, std::min(td, 64));
+    if (ts * td > 1 && n_edges > 0 && n_src > 0 && n_dst > 0) {
+      const int rows_per_s = (int)((n_src + ts - 1) / ts), rows_per_d = (int)((n_dst + td - 1) / td);
+      BG_CHECK(cudaMallocAsync(&g->out_tile_order, eb, st));
+      k_tile_keys<<<grid_for(n_src * 32), 256, 0, st>>>((int)n_src, g->out_indptr, g->out_indices, rows_per_s, rows_per_d,
+                                                       td, ktmp, iota); BG_LAUNCHED(1);
+      int32_t* ksorted = nullptr;
+      BG_CHECK(cudaMallocAsync(&ksorted, eb, st));
+      size_t tmp_bytes = 0;
+      const int kbits = bits_for((int64_t)ts * td);
+      BG_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ktmp, ksorted, iota, g->out_tile_order, (int)n_edges, 0, kbits, st));
+      void* tmp = nullptr;
+      BG_CHECK(cudaMallocAsync(&tmp, tmp_bytes, st));
+      BG_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, ktmp, ksorted, iota, g->out_tile_order, (int)n_edges, 0, kbits, st)); BG_LAUNCHED(1);
+      BG_CHECK(cudaFreeAsync(tmp, st)); BG_CHECK(cudaFreeAsync(ksorted, st));
+      g->tiles_s = ts; g->tiles_d = td;
+    }
+  }
+  BG_CHECK(cudaFreeAsync(iota, st)); BG_CHECK(cudaFreeAsync(ktmp, st));
   // heavy rows: split into segments (no-op for graphs whose longest row fits one segment)
   rc = build_segments((int)n_dst, g->in_indptr, g->in_deg, g->max_in_deg, &g->seg_in, st);
   if (rc) return rc;
@@ -308,6 +370,7 @@ extern "C" int botgat_graph_get_info(const botgat_graph* g, botgat_graph_info* i
   info->max_in_deg = g->max_in_deg; info->max_out_deg = g->max_out_deg;
   info->has_zero_in_degree = g->has_zero_in_degree; info->device = g->device;
   info->n_slots_in = g->seg_in.n_slots; info->n_slots_out = g->seg_out.n_slots;
+  info->in_eid_identity = g->in_eid_identity; info->tiles_src = g->tiles_s; info->tiles_dst = g->tiles_d; info->reserved_ = 0;
   return 0;
 }
 

@@ -306,10 +306,11 @@ class GATFusedFn(torch.autograd.Function):
       graph      bot_b200.Graph
       ft         (N_s,H,D)  projected source features, unscaled
       el         (N_s,H)    er (N_d,H)|None
-      ee         (E,Hp>=H)|None, edge-id order; columns >= H are padding (Hp = 8 keeps every record inside one
-                 32-byte DRAM sector, see ``pad_heads``); the gradient comes back with the same shape
-      keep       (E,) bool/uint8 | None   edge-drop keep set (edge-id order)
-      attn_mul   (E,H) | None   explicit attention-dropout multiplier (edge-id order)
+      ee         (E,Hp>=H)|None, CANONICAL edge order (``gat_fused`` converts from edge-id order); columns >= H are
+                 padding (Hp = 8 keeps every record inside one 32-byte DRAM sector, see ``pad_heads``); the gradient
+                 comes back with the same shape
+      keep       (E,) bool/uint8 | None   edge-drop keep set (canonical order)
+      attn_mul   (E,H) | None   explicit attention-dropout multiplier (canonical order)
       src_scale  (N_s,)|None   dst_scale (N_d,)|None
       slope      leaky_relu slope
       attn_p, seed   in-kernel Philox attention dropout (used when attn_mul is None and attn_p > 0)
@@ -557,8 +558,10 @@ class EdgeEmbedding:
     the layer turns it into its logits with one fused kernel (:class:`EdgeMLPLogits`) when the shapes allow
     (C <= 8 raw features, edge_emb <= 16, H <= 8 and ``efeat`` not requiring grad), else materialises it."""
 
-    def __init__(self, efeat, encoder):
-        self.efeat, self.encoder = efeat, encoder
+    def __init__(self, efeat, encoder, canonical=False):
+        # ``canonical``: rows of ``efeat`` are in the graph's canonical edge order (``graph.edata.canonical(key)``)
+        # rather than edge-id order; the logits then come out canonical too and the layer skips the permutation
+        self.efeat, self.encoder, self.canonical = efeat, encoder, canonical
 
     def materialize(self):
         return torch.relu(self.encoder(self.efeat))
@@ -599,9 +602,39 @@ class Hooks:
         self.head_chunks, self.pre_head, self.post_src_head = head_chunks, pre_head, post_src_head
 
 
+class _ToCanonical(torch.autograd.Function):
+    """Rows of a per-edge tensor from edge-id order to the graph's canonical order (and the gradient back)."""
+
+    @staticmethod
+    def forward(ctx, t, graph):
+        ctx.graph = graph
+        return t.index_select(0, graph.edge_perm())
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.index_select(0, ctx.graph.canonical_edge_ids()), None
+
+
+def to_canonical(graph, t):
+    """Per-edge tensor (E, ...) in edge-id order -> the graph's canonical order (``Graph`` docstring); differentiable.
+    A no-op for graphs whose two orders coincide (the sampler's blocks, COOs given sorted by (dst, src))."""
+    if t is None or graph.edge_perm() is None:
+        return t
+    if t.shape[0] != graph.number_of_edges():
+        raise ValueError("per-edge operand must have one row per edge")
+    return _ToCanonical.apply(t, graph)
+
+
 def gat_fused(graph, ft, el, er=None, ee=None, keep=None, attn_mul=None, src_scale=None, dst_scale=None,
-              slope=0.2, attn_p=0.0, seed=0, hooks=None):
-    """Functional form of :class:`GATFusedFn` (accepts the reference's trailing-1 shapes, e.g. el (N,H,1))."""
+              slope=0.2, attn_p=0.0, seed=0, hooks=None, edge_order="eid"):
+    """Functional form of :class:`GATFusedFn` (accepts the reference's trailing-1 shapes, e.g. el (N,H,1)).
+
+    ``edge_order``: order of the rows of ``ee`` / ``keep`` / ``attn_mul``.  "eid" (default) = edge-id order, DGL's
+    ``edata`` semantics — permuted to the canonical order here, one random pass per operand and step; "canonical" =
+    already in the graph's canonical order (``graph.edata.canonical(key)``, what the edge-logit producers emit from
+    canonical features, what ``edge_drop_keep`` draws): no permutation.  The gradient of ``ee`` comes back in the order
+    it was given in.  The in-kernel attention dropout is keyed on the canonical edge number
+    (``graph.canonical_edge_ids()``)."""
     H = ft.shape[1]
     el = el.reshape(-1, H)
     er = None if er is None else er.reshape(-1, H)
@@ -609,4 +642,8 @@ def gat_fused(graph, ft, el, er=None, ee=None, keep=None, attn_mul=None, src_sca
         ee = ee.reshape(ee.shape[0], -1)
     if attn_mul is not None and attn_mul.dim() == 3:
         attn_mul = attn_mul.reshape(attn_mul.shape[0], -1)
+    if edge_order == "eid":
+        ee, keep, attn_mul = to_canonical(graph, ee), to_canonical(graph, keep), to_canonical(graph, attn_mul)
+    elif edge_order != "canonical":
+        raise ValueError(f"edge_order must be 'eid' or 'canonical', got {edge_order!r}")
     return GATFusedFn.apply(graph, ft, el, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed, hooks)

@@ -37,11 +37,42 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
 
 
+class EdgeFrame(dict):
+    """``graph.edata``.  What the user reads and writes is in EDGE-ID order, as in DGL (``edata`` is indexed by
+    edge id, src/ogbn-proteins/models.py:130-133).  The kernels stream per-edge operands in the graph's CANONICAL
+    order (= in-CSR order, see :class:`Graph`); ``canonical(key)`` is the same tensor in that order, permuted ONCE
+    per assignment and cached — static edge features therefore never pay a per-step permutation."""
+
+    def __init__(self, graph):
+        super().__init__()
+        self._graph = graph
+        self._canon = {}
+
+    def canonical(self, key):
+        t = self[key]
+        hit = self._canon.get(key)
+        if hit is None or hit[0] is not t:
+            perm = self._graph.edge_perm() if t.is_cuda else None
+            hit = (t, t if perm is None else t.index_select(0, perm))
+            self._canon[key] = hit
+        return hit[1]
+
+
 class Graph:
     """Homogeneous graph or bipartite block (``is_block=True``: dst nodes are the
-    first ``num_dst_nodes`` src nodes, as in DGL message-flow blocks)."""
+    first ``num_dst_nodes`` src nodes, as in DGL message-flow blocks).
 
-    def __init__(self, src, dst, num_src_nodes=None, num_dst_nodes=None, is_block=False):
+    Edge order.  Edge ids are the positions in the COO the graph was built from (DGL semantics) and everything
+    user-facing (``edges()``, ``edata[...]``, ``structure("in_eid")``) speaks edge ids.  Internally (``canonical=True``,
+    the default) the device structure is built from the COO sorted by (dst, src): the library's own edge numbering
+    then EQUALS the in-CSR position, neighbour lists are sorted in both CSRs, and per-edge operands given in that
+    canonical order (``EdgeFrame.canonical``, ``functional.gat_fused(..., edge_order="canonical")``) need no
+    edge-id -> CSR permutation pass at all in the forward and a cache-blocked one in the backward
+    (csrc/edge_ops.cu).  ``edge_perm()`` is the canonical -> edge-id map, ``canonical_edge_ids()`` its inverse.
+    ``canonical=False`` builds the structure from the COO as given (DGL's order: inside a row, increasing edge id);
+    ``presorted=True`` promises a COO already sorted by dst (the sampler's blocks) and skips the sort."""
+
+    def __init__(self, src, dst, num_src_nodes=None, num_dst_nodes=None, is_block=False, canonical=True, presorted=False):
         src = torch.as_tensor(src, dtype=torch.int64)
         dst = torch.as_tensor(dst, dtype=torch.int64)
         if src.shape != dst.shape or src.dim() != 1:
@@ -54,7 +85,9 @@ class Graph:
         self._n_src = int(num_src_nodes)
         self._n_dst = int(self._n_src if num_dst_nodes is None else num_dst_nodes)
         self.is_block = bool(is_block)
-        self.edata = {}
+        self._canonical, self._presorted = bool(canonical), bool(presorted)
+        self._perm = self._inv = None    # canonical position -> edge id, and back (None = identity)
+        self.edata = EdgeFrame(self)
         if self.is_block or self._n_src != self._n_dst:
             self.srcdata, self.dstdata = {}, {}
             self.ndata = self.srcdata
@@ -79,10 +112,23 @@ class Graph:
         _require_cuda(self._src, "graph structure")
         lib = _lib.load()
         h = C.c_void_p()
+        src, dst = self._src, self._dst
         with torch.cuda.device(self._src.device):
-            rc = lib.botgat_graph_create(self._n_src, self._n_dst, self._src.numel(), _lib.ptr(self._src),
-                                         _lib.ptr(self._dst), self._src.device.index, _stream(), C.byref(h))
+            if self._canonical and not self._presorted and src.numel() > 1:
+                # canonical edge order = COO sorted by (dst, src), ties by edge id (a data movement, not arithmetic;
+                # out-of-range ids are caught by botgat_graph_create below)
+                key = dst * max(self._n_src, 1) + src
+                if not bool((key[1:] >= key[:-1]).all()):
+                    perm = torch.argsort(key, stable=True)
+                    src, dst = src.index_select(0, perm), dst.index_select(0, perm)
+                    self._perm = perm
+                del key
+            rc = lib.botgat_graph_create(self._n_src, self._n_dst, src.numel(), _lib.ptr(src),
+                                         _lib.ptr(dst), self._src.device.index, _stream(), C.byref(h))
+        if rc != 0:
+            self._perm = None
         _lib.check(rc, "botgat_graph_create")
+        del src, dst
         self._handle = h
         info = _lib.GraphInfo()
         _lib.check(lib.botgat_graph_get_info(h, C.byref(info)), "botgat_graph_get_info")
@@ -106,6 +152,21 @@ class Graph:
                     _lib._lib.botgat_graph_destroy(h)
                 except Exception:
                     pass
+
+    def edge_perm(self):
+        """canonical position -> edge id (int64, device), or None when the two orders coincide."""
+        self._ensure()
+        return self._perm
+
+    def canonical_edge_ids(self):
+        """edge id -> canonical position (the library's own edge numbering; the in-kernel Philox streams are keyed
+        on it), or None when the two orders coincide."""
+        self._ensure()
+        if self._perm is not None and self._inv is None:
+            inv = torch.empty_like(self._perm)
+            inv[self._perm] = torch.arange(self._perm.numel(), device=self._perm.device)
+            self._inv = inv
+        return self._inv
 
     def create_formats_(self):
         """``graph.create_formats_()`` (run.py:146): materialise CSR + CSC now."""
@@ -144,7 +205,10 @@ class Graph:
         if n.value == 0:
             return torch.empty(0, dtype=torch.int64, device=self.device)
         view = torch.as_tensor(_DevArray(p.value, n.value), device=self.device)  # zero-copy view of library memory
-        return view.long()  # the copy is what escapes
+        out = view.long()  # the copy is what escapes
+        if name.endswith("_eid") and self._perm is not None:
+            out = self._perm.index_select(0, out)   # the library numbers edges canonically; users see edge ids
+        return out
 
     def in_degrees(self):
         if "in_deg" not in self._cache:
@@ -186,7 +250,8 @@ class Graph:
             device = torch.device("cuda", torch.cuda.current_device())
         if device == self.device:
             return self
-        g = Graph(self._src.to(device), self._dst.to(device), self._n_src, self._n_dst, self.is_block)
+        g = Graph(self._src.to(device), self._dst.to(device), self._n_src, self._n_dst, self.is_block,
+                  canonical=self._canonical, presorted=self._presorted)
         for name in ("srcdata", "dstdata", "edata"):
             getattr(g, name).update({k: v.to(device) for k, v in getattr(self, name).items()})
         return g
@@ -260,11 +325,11 @@ def add_self_loop(g):
     return g.add_self_loop()
 
 
-def create_block(data, num_src_nodes, num_dst_nodes, device=None):
+def create_block(data, num_src_nodes, num_dst_nodes, device=None, **kw):
     """``dgl.create_block`` look-alike: bipartite block whose dst nodes are a prefix of src."""
     src, dst = data
     src = torch.as_tensor(src, dtype=torch.int64)
     dst = torch.as_tensor(dst, dtype=torch.int64)
     if device is not None:
         src, dst = src.to(device), dst.to(device)
-    return Graph(src, dst, num_src_nodes, num_dst_nodes, is_block=True)
+    return Graph(src, dst, num_src_nodes, num_dst_nodes, is_block=True, **kw)

@@ -15,7 +15,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .functional import gat_fused
+from .functional import gat_fused, to_canonical
 
 
 edge_drop_mode = "select"   # "randperm": torch.randperm exactly as the reference calls it (replays its generator)
@@ -204,8 +204,12 @@ class GATConv(nn.Module):
                     attn_p = self.attn_drop.p
                     seed = int(torch.randint(0, 2**62, (1,)).item())
 
+            # per-edge operands in the graph's canonical order (bot_b200.Graph): the selection draw's keep set already
+            # is; the literal randperm replay / an "exact" mask without edge-drop are in edge-id order
+            if not isinstance(eids, KeptEdges):
+                keep, attn_mul = to_canonical(graph, keep), to_canonical(graph, attn_mul)
             rst = gat_fused(graph, ft, el, er, None, keep, attn_mul, src_scale, dst_scale,
-                            self._negative_slope, attn_p, seed)                # models.py:523-555
+                            self._negative_slope, attn_p, seed, edge_order="canonical")   # models.py:523-555
 
             if self.res_fc is not None:                                       # models.py:557-560
                 rst = rst + self.res_fc(h_dst).view(h_dst.shape[0], -1, D)

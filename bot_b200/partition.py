@@ -244,17 +244,24 @@ class PartitionedGraph:
         return outs[0] if len(outs) == 1 else tuple(outs)
 
     def gat(self, ft_own, el_own, er=None, ee=None, keep=None, attn_mul=None, src_scale=None, dst_scale=None,
-            slope=0.2, attn_p=0.0, seed=0):
+            slope=0.2, attn_p=0.0, seed=0, edge_order="eid"):
         """The partitioned layer in one call: halo exchange + ``gat_fused`` on the local block, with the collectives
         overlapped with the work that does not depend on them (dense plan):
           forward : all-gather of [ft], [el]  ||  edge staging            -> forward gather kernel
           backward: node + src pass -> reduce-scatter of grad_ft, grad_el  ||  edge phase (grad_ee, grad_er)
-        ``src_scale`` is given for the LOCAL source numbering (``halo_gather`` a row-sharded one)."""
-        from .functional import Hooks, gat_fused
+        ``src_scale`` is given for the LOCAL source numbering (``halo_gather`` a row-sharded one).  ``edge_order``:
+        order of the per-edge operands' rows, "eid" = local edge order (``local_edges``), "canonical" = the local
+        block's canonical order (``self.local.edge_perm()``), see ``functional.gat_fused``."""
+        from .functional import Hooks, gat_fused, to_canonical
+
+        if edge_order == "eid" and isinstance(self.local, Graph):
+            ee, keep, attn_mul = (to_canonical(self.local, t) for t in (ee, keep, attn_mul))
+        edge_order = "canonical"
 
         if self.world == 1 or self.plan != "dense":
             ft_all, el_all = self.halo_gather(ft_own, el_own)
-            return gat_fused(self.local, ft_all, el_all, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed)
+            return gat_fused(self.local, ft_all, el_all, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed,
+                             edge_order=edge_order)
         st = _HaloState()
         if self.pipeline_heads and ft_own.dim() == 3 and ft_own.shape[1] > 1:
             return self._gat_head_pipelined(st, ft_own, el_own, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed)
@@ -272,7 +279,7 @@ class PartitionedGraph:
                 st.bwd[key] = (work, out)
 
         out = gat_fused(self.local, ft_all, el_all, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed,
-                        hooks=Hooks(pre_kernel, post_src))
+                        hooks=Hooks(pre_kernel, post_src), edge_order=edge_order)
         return out
 
     def _gat_head_pipelined(self, st, ft_own, el_own, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed):
@@ -306,7 +313,8 @@ class PartitionedGraph:
                 st.bwd["el"] = (w, out)
 
         return gat_fused(self.local, ft_all, el_all, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed,
-                         hooks=Hooks(head_chunks=chunks, pre_head=pre_head, post_src_head=post_src_head))
+                         hooks=Hooks(head_chunks=chunks, pre_head=pre_head, post_src_head=post_src_head),
+                         edge_order="canonical")
 
     def owned_slice(self, full_table):
         """Rows of a replicated (N, ...) table this rank owns."""

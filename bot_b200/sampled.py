@@ -19,8 +19,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .functional import Deferred, EdgeEmbedding, GATConvSampledFn, edge_logits, gat_fused
-from .no_sampling import draw_attn_mul, draw_edge_keep
+from .functional import Deferred, EdgeEmbedding, GATConvSampledFn, edge_logits, gat_fused, to_canonical
+from .no_sampling import KeptEdges, draw_attn_mul, draw_edge_keep
 
 
 # Fold the layer's four node-side Linears into two GEMMs (functional.GATConvSampledFn).  False: one nn.Linear call
@@ -115,8 +115,15 @@ class GATConv(nn.Module):
                 # (functional.pad_heads); padding columns are ignored by the kernels and get zero gradient
                 if isinstance(feat_edge, EdgeEmbedding):   # encoder + ReLU + this Linear in one kernel
                     ee = feat_edge.logits(self.attn_edge_fc.weight)
-                else:
-                    ee = edge_logits(feat_edge, self.attn_edge_fc.weight)      # (E, pad_heads(H))
+                    if not feat_edge.canonical:
+                        ee = to_canonical(graph, ee)
+                else:                                      # a plain tensor is in edge-id order (DGL edata semantics)
+                    ee = to_canonical(graph, edge_logits(feat_edge, self.attn_edge_fc.weight))   # (E, pad_heads(H))
+            # every per-edge operand is now brought to the graph's canonical order (bot_b200.Graph): the keep set of
+            # the selection draw already is (it is a uniformly random subset of positions either way); the literal
+            # randperm replay and an "exact" dropout mask without edge-drop are in edge-id order
+            if not isinstance(eids, KeptEdges):
+                keep, attn_mul = to_canonical(graph, keep), to_canonical(graph, attn_mul)
 
             if fold:
                 # the four node-side Linears (models.py:106-108,122-124) as two GEMMs whose outputs the kernels
@@ -128,7 +135,7 @@ class GATConv(nn.Module):
                                              dst_scale, H, D, self._negative_slope, attn_p, seed)
             else:
                 rst = gat_fused(graph, ft, el, er, ee, keep, attn_mul, None, dst_scale,
-                                self._negative_slope, attn_p, seed)            # models.py:125-156
+                                self._negative_slope, attn_p, seed, edge_order="canonical")   # models.py:125-156
                 rst = rst + resid                                             # models.py:159-160
             if self.activation is not None:
                 rst = self.activation(rst, inplace=True)
@@ -158,7 +165,8 @@ class _SampledGAT(nn.Module):
             efeat_emb = None
             if self.edge_encoder is not None:
                 # relu(edge_encoder[i](efeat)) (models.py:245-247), left to the layer to fuse with attn_edge_fc
-                efeat_emb = EdgeEmbedding(subgraphs[i].edata["feat"], self.edge_encoder[i])
+                # static edge features are kept in the graph's canonical order (permuted once, EdgeFrame.canonical)
+                efeat_emb = EdgeEmbedding(subgraphs[i].edata.canonical("feat"), self.edge_encoder[i], canonical=True)
             h = self.convs[i](subgraphs[i], h, efeat_emb).flatten(1, -1)
             if h_last is not None and (always_residual or self.residual):
                 h = h + h_last[: h.shape[0], :]

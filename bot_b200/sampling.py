@@ -46,6 +46,10 @@ class _LazyFrame(dict):
     def keys(self):
         return list(dict.fromkeys(list(dict.keys(self)) + list(self._parent.keys())))
 
+    def canonical(self, key):
+        """A block's edges are emitted destination by destination: its own order IS its canonical order."""
+        return self[key]
+
 
 def sample_neighbors(g: Graph, seeds, fanout, seed=0):
     """Uniform sample without replacement of ``fanout`` in-edges per seed (all of them for in-degree <= fanout or
@@ -70,6 +74,9 @@ def sample_neighbors(g: Graph, seeds, fanout, seed=0):
                        "botgat_sample_neighbors")
     if n == 0:
         offsets.zero_()
+    perm = g.edge_perm()
+    if perm is not None and eid.numel():
+        eid = perm.index_select(0, eid)   # the library numbers edges canonically; callers see edge ids
     return src, dst, eid, offsets
 
 
@@ -91,7 +98,8 @@ def to_block(g: Graph, seeds, src, dst_pos, eid):
                                             dev.index if dev.index is not None else torch.cuda.current_device(), _stream()),
                    "botgat_block_compact")
     src_nodes = src_nodes[: n_src.value]
-    block = Graph(src_local, dst_pos, n_src.value, n_seeds, is_block=True)
+    # a frontier lists its edges seed by seed, i.e. sorted by destination: already canonical
+    block = Graph(src_local, dst_pos, n_src.value, n_seeds, is_block=True, presorted=True)
     block.srcdata = _LazyFrame(g.ndata, src_nodes)
     block.dstdata = _LazyFrame(g.ndata, seeds)
     block.ndata = block.srcdata

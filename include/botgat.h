@@ -31,7 +31,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define BOTGAT_ABI_VERSION 2
+#define BOTGAT_ABI_VERSION 3
 
 typedef struct botgat_graph botgat_graph;
 
@@ -91,6 +91,13 @@ typedef struct {
    *   backward scratch = n_slots_out * r4(H * (D + 1)) + n_slots_in * H floats
    * Both are 0 for graphs without heavy rows. */
   int64_t n_slots_in, n_slots_out;
+  /* 1 when the library's edge numbering equals the in-CSR position (the COO was given sorted by destination):
+   * edge-ordered operands then stream coalesced through botgat_edge_stage(BOTGAT_ORDER_IN) / botgat_edge_reduce_dst */
+  int32_t in_eid_identity;
+  /* cache-blocked out-CSR traversal used by botgat_edge_stage / botgat_edge_unstage(BOTGAT_ORDER_OUT):
+   * tiles_src x tiles_dst node blocks (1 x 1 = plain order) */
+  int32_t tiles_src, tiles_dst;
+  int32_t reserved_;
 } botgat_graph_info;
 int botgat_graph_get_info(const botgat_graph* g, botgat_graph_info* info /* HOST */);
 

@@ -101,8 +101,10 @@ class BigGraph:
         self.out_indptr[1:] = torch.cumsum(self.out_counts, 0)
 
 
-def gat_sparse_big_forward(g: BigGraph, ft, el, er=None, ee=None, slope=0.2):
-    """Forward without E*H*D temporaries.  Returns (out, alpha_csr, s_csr)."""
+def gat_sparse_big_forward(g: BigGraph, ft, el, er=None, ee=None, slope=0.2, keep=None, attn_mul=None, src_scale=None,
+                           dst_scale=None):
+    """Forward without E*H*D temporaries; same arguments as ``gat_sparse`` (``keep`` (E,) bool and ``attn_mul``
+    (E,H) in edge-id order).  Returns (out, saved) with ``saved`` = what the explicit backward needs."""
     H = ft.shape[1]
     z = el.index_select(0, g.in_src)
     if er is not None:
@@ -110,40 +112,57 @@ def gat_sparse_big_forward(g: BigGraph, ft, el, er=None, ee=None, slope=0.2):
     if ee is not None:
         z = z + ee.index_select(0, g.in_eid)
     s = F.leaky_relu(z, slope)
+    if keep is not None:                                           # softmax over the kept edges only, models.py:534-537
+        s = torch.where(keep.index_select(0, g.in_eid).view(-1, 1), s, torch.full_like(s, float("-inf")))
     m = torch.segment_reduce(s, "max", lengths=g.in_counts, initial=float("-inf"))
+    m = torch.where(torch.isinf(m), torch.zeros_like(m), m)        # rows without a kept edge
     p = torch.exp(s - m.index_select(0, g.in_dst))
-    ssum = torch.segment_reduce(p, "sum", lengths=g.in_counts)
-    a = p / ssum.index_select(0, g.in_dst)
-    out = torch.empty((g.n_dst,) + tuple(ft.shape[1:]), dtype=ft.dtype)
+    ssum = torch.segment_reduce(p, "sum", lengths=g.in_counts, initial=0.0)
+    a = p / ssum.index_select(0, g.in_dst).clamp(min=torch.finfo(p.dtype).tiny)
+    am = attn_mul.index_select(0, g.in_eid) if attn_mul is not None else None
+    at = a if am is None else a * am                               # attention dropout, models.py:537/544
+    fts = ft if src_scale is None else ft * src_scale.view(-1, 1, 1)   # models.py:500-505
+    acc = torch.empty((g.n_dst,) + tuple(ft.shape[1:]), dtype=ft.dtype)
     for h in range(H):
-        A = torch.sparse_csr_tensor(g.in_indptr, g.in_src, a[:, h].contiguous(), size=(g.n_dst, g.n_src))
-        out[:, h, :] = A @ ft[:, h, :]
-    return out, a, z
+        A = torch.sparse_csr_tensor(g.in_indptr, g.in_src, at[:, h].contiguous(), size=(g.n_dst, g.n_src))
+        acc[:, h, :] = A @ fts[:, h, :]
+    out = acc if dst_scale is None else acc * dst_scale.view(-1, 1, 1)  # models.py:550-555
+    return out, (a, am, z, acc, fts)
 
 
-def gat_sparse_big_backward(g: BigGraph, ft, a, z, out, gout, slope=0.2, need_er=True, need_ee=True):
+def gat_sparse_big_backward(g: BigGraph, saved, gout, slope=0.2, need_er=True, need_ee=True, keep=None, src_scale=None,
+                            dst_scale=None):
     """Explicit adjoint.  Returns grad_ft, grad_el, grad_er, grad_ee."""
-    H = ft.shape[1]
-    # d_k = <ft[src_k], g[dst_k]> without materialising E*H*D: chunk over edges
+    a, am, z, acc, fts = saved
+    H = fts.shape[1]
+    gp = gout if dst_scale is None else gout * dst_scale.view(-1, 1, 1)
+    # d_k = <src_scale * ft[src_k], g'[dst_k]> without materialising E*H*D: chunk over edges
     E = a.shape[0]
     d = torch.empty_like(a)
     chunk = 1 << 20
     for lo in range(0, E, chunk):
         hi = min(E, lo + chunk)
-        d[lo:hi] = (ft.index_select(0, g.in_src[lo:hi]) * gout.index_select(0, g.in_dst[lo:hi])).sum(-1)
-    t = (out * gout).sum(-1)                                   # (N_d,H)
+        d[lo:hi] = (fts.index_select(0, g.in_src[lo:hi]) * gp.index_select(0, g.in_dst[lo:hi])).sum(-1)
+    t = (acc * gp).sum(-1)                                     # (N_d,H)
+    if am is not None:
+        d = d * am
     gs = a * (d - t.index_select(0, g.in_dst))
     gz = gs * torch.where(z > 0, torch.ones_like(z), torch.full_like(z, slope))
-    grad_er = torch.segment_reduce(gz, "sum", lengths=g.in_counts) if need_er else None
+    if keep is not None:
+        gz = torch.where(keep.index_select(0, g.in_eid).view(-1, 1), gz, torch.zeros_like(gz))
+    grad_er = torch.segment_reduce(gz, "sum", lengths=g.in_counts, initial=0.0) if need_er else None
     grad_ee = None
     if need_ee:
         grad_ee = torch.empty_like(gz)
         grad_ee[g.in_eid] = gz
     gz_out = gz.index_select(0, g.out_pos_in)
-    a_out = a.index_select(0, g.out_pos_in)
-    grad_el = torch.segment_reduce(gz_out, "sum", lengths=g.out_counts)
-    grad_ft = torch.empty_like(ft)
+    at = a if am is None else a * am
+    a_out = at.index_select(0, g.out_pos_in)
+    grad_el = torch.segment_reduce(gz_out, "sum", lengths=g.out_counts, initial=0.0)
+    grad_ft = torch.empty_like(fts)
     for h in range(H):
         AT = torch.sparse_csr_tensor(g.out_indptr, g.out_dst, a_out[:, h].contiguous(), size=(g.n_src, g.n_dst))
-        grad_ft[:, h, :] = AT @ gout[:, h, :]
+        grad_ft[:, h, :] = AT @ gp[:, h, :]
+    if src_scale is not None:
+        grad_ft = grad_ft * src_scale.view(-1, 1, 1)
     return grad_ft, grad_el, grad_er, grad_ee

@@ -44,24 +44,38 @@ def add_self_loop(src, dst, n_nodes):
     return np.concatenate([src, loop]), np.concatenate([dst, loop])
 
 
-def build_csr(key, other, n_rows):
-    """Stable COO -> CSR keyed on ``key``.
+def build_csr(key, other, n_rows, sort_neighbours=False):
+    """Stable COO -> CSR keyed on ``key``: inside a row, increasing edge id (DGL's counting sort) or, with
+    ``sort_neighbours``, increasing (neighbour id, edge id) — the canonical order of ``bot_b200.Graph``.
 
     Returns (indptr[n_rows+1], indices[E] = other in row order, eid[E]).
     """
     key, other = _i64(key), _i64(other)
-    eid = np.argsort(key, kind="stable").astype(np.int64)
+    if sort_neighbours:
+        eid = np.lexsort((np.arange(key.shape[0]), other, key)).astype(np.int64)
+    else:
+        eid = np.argsort(key, kind="stable").astype(np.int64)
     counts = np.bincount(key, minlength=n_rows).astype(np.int64)
     indptr = np.zeros(n_rows + 1, dtype=np.int64)
     np.cumsum(counts, out=indptr[1:])
     return indptr, other[eid], eid
 
 
-def build_formats(src, dst, n_src, n_dst):
-    """All structure arrays ``botgat_graph_create`` must reproduce bit-exactly."""
+def canonical_edge_ids(src, dst):
+    """Canonical position of every edge id: rank of (dst, src, edge id) — ``bot_b200.Graph.canonical_edge_ids``."""
     src, dst = _i64(src), _i64(dst)
-    in_indptr, in_indices, in_eid = build_csr(dst, src, n_dst)     # CSC: rows = dst
-    out_indptr, out_indices, out_eid = build_csr(src, dst, n_src)  # CSR: rows = src
+    perm = np.lexsort((np.arange(src.shape[0]), src, dst))
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(perm.shape[0])
+    return inv.astype(np.int64)
+
+
+def build_formats(src, dst, n_src, n_dst, canonical=False):
+    """All structure arrays the device graph must reproduce bit-exactly: ``botgat_graph_create`` on the COO as
+    given (DGL's order), or — ``canonical`` — ``bot_b200.Graph``'s default, neighbour lists sorted by id."""
+    src, dst = _i64(src), _i64(dst)
+    in_indptr, in_indices, in_eid = build_csr(dst, src, n_dst, canonical)     # CSC: rows = dst
+    out_indptr, out_indices, out_eid = build_csr(src, dst, n_src, canonical)  # CSR: rows = src
     return {
         "in_indptr": in_indptr, "in_indices": in_indices, "in_eid": in_eid,
         "out_indptr": out_indptr, "out_indices": out_indices, "out_eid": out_eid,

@@ -36,12 +36,17 @@ def _synth(n, e, dev, seed, power_law=0.0):
     return src, dst
 
 
-def _check(name, dev, graph, src, dst, n_src, n_dst, H, D, *, er, ee, edge_drop, attn_p, symm, n_v, n_u, extra_rows=(), seed=0):
-    """One full-size layer step on the GPU vs the row-subsample oracle.  Returns the error dict."""
+def _check(name, dev, graph, src, dst, n_src, n_dst, H, D, *, er, ee, edge_drop, attn_p, symm, n_v, n_u, extra_rows=(), seed=0,
+           canonical=False):
+    """One full-size layer step on the GPU vs the row-subsample oracle.  Returns the error dict.
+    ``canonical``: the per-edge operands are given in the graph's canonical order (the production path: no
+    permutation pass); the oracle then sees the COO in that same order."""
     from bot_b200 import functional
     from bot_b200.functional import gat_fused
 
     E = src.numel()
+    if canonical and graph.edge_perm() is not None:
+        src, dst = src[graph.edge_perm()], dst[graph.edge_perm()]
     gen = torch.Generator(device=dev).manual_seed(seed + 100)
     ft = torch.randn(n_src, H, D, device=dev, generator=gen).requires_grad_(True)
     el = torch.randn(n_src, H, device=dev, generator=gen).requires_grad_(True)
@@ -52,7 +57,8 @@ def _check(name, dev, graph, src, dst, n_src, n_dst, H, D, *, er, ee, edge_drop,
     cs = graph.deg_scale("out", -0.5) if symm else None
     ds = graph.deg_scale("in", 0.5) if symm else None
     pseed = 987654321 + seed
-    out = gat_fused(graph, ft, el, er_t, ee_t, keep, None, cs, ds, SLOPE, attn_p, pseed)
+    out = gat_fused(graph, ft, el, er_t, ee_t, keep, None, cs, ds, SLOPE, attn_p, pseed,
+                    edge_order="canonical" if canonical else "eid")
     out.backward(gout)
     torch.cuda.synchronize()
     assert torch.isfinite(out).all() and torch.isfinite(ft.grad).all()
@@ -71,8 +77,10 @@ def _check(name, dev, graph, src, dst, n_src, n_dst, H, D, *, er, ee, edge_drop,
         assert torch.equal(cs_ref, cs) and torch.equal(ds_ref, ds)
     sub = gat_rows.build_sub(src, dst, n_src, n_dst, W, ft=ft, el=el, er=er_t, ee=ee_t, keep=keep, src_scale=cs, dst_scale=ds,
                              gout=gout)
-    if attn_p > 0:
-        sub["attn_mul"] = philox_attn_mul(pseed, 0, H, attn_p, eids=sub["eid"].numpy()).double()
+    if attn_p > 0:   # the in-kernel stream is keyed on the graph's canonical edge number
+        cid = graph.canonical_edge_ids()
+        ids = sub["eid"] if (cid is None or canonical) else cid[sub["eid"].to(dev)].cpu()
+        sub["attn_mul"] = philox_attn_mul(pseed, 0, H, attn_p, eids=ids.numpy()).double()
     ref = gat_rows.eval_explicit(sub, SLOPE)
     Wd, Ud, comp = sub["W"].to(dev), sub["U"].to(dev), sub["complete"]
     assert int(comp.sum()) >= min(n_u, int(cand.numel())), "sampled sources must be complete in the sub-problem"
@@ -108,6 +116,10 @@ def test_proteins_full_size_values(cuda):
     src, dst = _synth(n, e, cuda, 0)
     g = bot_b200.Graph(src, dst, n)
     _check("proteins", cuda, g, src, dst, n, n, 6, 80, er=True, ee=True, edge_drop=0.1, attn_p=0.0, symm=False, n_v=1000, n_u=16)
+    # the production path: operands already in canonical order, blocked in <-> out transposes in the backward
+    assert g._info.in_eid_identity == 1 and g._info.tiles_src * g._info.tiles_dst > 1
+    _check("proteins-canonical", cuda, g, src, dst, n, n, 6, 80, er=True, ee=True, edge_drop=0.1, attn_p=0.2, symm=False, n_v=1000,
+           n_u=16, seed=7, canonical=True)
 
 
 def test_proteins_skewed_full_size_values(cuda):
@@ -172,4 +184,4 @@ def test_rank_block_of_8_full_size_values(cuda):
     del src, dst
     g = part.local
     _check("proteins-rank3of8", cuda, g, part.lsrc, part.ldst, part.n_src_local, part.n_own, 6, 80, er=True, ee=True, edge_drop=0.1,
-           attn_p=0.0, symm=False, n_v=500, n_u=32, seed=6)
+           attn_p=0.0, symm=False, n_v=500, n_u=32, seed=6, canonical=True)

@@ -9,13 +9,19 @@ from util import check_case, engine_run, make_case, oracle_run, rel_err, FWD_TOL
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("canonical", [False, True])
 @pytest.mark.parametrize("n,e,seed", [(1, 0, 0), (7, 3, 1), (100, 1000, 2), (2708, 13264, 3), (5000, 200000, 4)])
-def test_structure_bit_exact(cuda, n, e, seed):
+def test_structure_bit_exact(cuda, n, e, seed, canonical):
+    """DGL's order (stable by edge id inside a row) and the default canonical order (neighbour lists sorted by id);
+    row pointers, degrees and the edge-id maps are exact in both."""
     import bot_b200
 
     src, dst = graph_ref.synthetic_coo(n, e, seed, power_law=0.8 if seed == 4 else 0.0)
-    ref = graph_ref.build_formats(src, dst, n, n)
-    g = bot_b200.Graph(torch.from_numpy(src).to(cuda), torch.from_numpy(dst).to(cuda), n)
+    ref = graph_ref.build_formats(src, dst, n, n, canonical=canonical)
+    g = bot_b200.Graph(torch.from_numpy(src).to(cuda), torch.from_numpy(dst).to(cuda), n, canonical=canonical)
+    if canonical and e > 1:
+        assert np.array_equal(g.canonical_edge_ids().cpu().numpy(), graph_ref.canonical_edge_ids(src, dst))
+        assert g._info.in_eid_identity == 1
     for name, arr in ref.items():
         got = g.structure(name).cpu().numpy()
         assert got.dtype == np.int64 and got.shape == arr.shape, name
@@ -30,10 +36,11 @@ def test_block_structure(cuda):
     n_src, n_dst, e = 300, 40, 2000
     src = rng.integers(0, n_src, e)
     dst = rng.integers(0, n_dst, e)
-    ref = graph_ref.build_formats(src, dst, n_src, n_dst)
-    g = bot_b200.create_block((src, dst), n_src, n_dst, device=cuda)
-    for name, arr in ref.items():
-        assert np.array_equal(g.structure(name).cpu().numpy(), arr), name
+    for canonical in (False, True):
+        ref = graph_ref.build_formats(src, dst, n_src, n_dst, canonical=canonical)
+        g = bot_b200.create_block((src, dst), n_src, n_dst, device=cuda, canonical=canonical)
+        for name, arr in ref.items():
+            assert np.array_equal(g.structure(name).cpu().numpy(), arr), name
 
 
 def test_preprocess_bit_exact(cuda):
@@ -464,7 +471,8 @@ def test_fused_philox_attention_dropout(cuda, H):
 
     p, seed = 0.3, 0x1234_5678_9ABC_DEF1
     c = make_case(300, 300, 9000, H, 16, ee=True, keep_p=0.1, seed=40 + H)
-    c["attn_mul"] = philox_attn_mul(seed, 9000, H, p)
+    # the stream is keyed on the graph's canonical edge number
+    c["attn_mul"] = philox_attn_mul(seed, 9000, H, p, eids=graph_ref.canonical_edge_ids(c["src"].numpy(), c["dst"].numpy()))
     frac = float((c["attn_mul"] == 0).float().mean())
     assert abs(frac - p) < 0.03
     ref_out, ref_g = oracle_run(c)
@@ -485,7 +493,8 @@ def test_partition_abi_bit_exact(cuda, parts):
     src, dst = graph_ref.synthetic_coo(n, e, 12, power_law=0.7)
     f = graph_ref.build_formats(src, dst, n, n)
     ref_b = graph_ref.partition_bounds(f["in_indptr"], parts)
-    g = bot_b200.Graph(torch.from_numpy(src).to(cuda), torch.from_numpy(dst).to(cuda), n)
+    # ABI-level check in the library's own edge numbering: build from the COO as given
+    g = bot_b200.Graph(torch.from_numpy(src).to(cuda), torch.from_numpy(dst).to(cuda), n, canonical=False)
     assert np.array_equal(partition_bounds_device(g, parts).numpy(), ref_b)
     assert np.array_equal(partition_bounds(torch.from_numpy(dst).to(cuda), n, parts).cpu().numpy(), ref_b)
     for r in range(parts):
@@ -694,3 +703,60 @@ def test_zero_negative_slope(cuda, monkeypatch, lowdeg):
     assert rel_err(out, ref_out) <= FWD_TOL
     for k in ("ft", "el", "er", "ee"):
         assert rel_err(g[k], ref_g[k]) <= 1e-4, k
+
+
+@pytest.mark.parametrize("tiles", [None, "3,2", "1,4"])
+def test_canonical_edge_operands(cuda, monkeypatch, tiles):
+    """Operands given in the graph's canonical order (no permutation pass) give bit-identical results to the same
+    operands given in edge-id order; the cache-blocked out-CSR traversal (forced here on a small graph) changes the
+    order edges are visited in, never a value."""
+    import bot_b200
+    from bot_b200.functional import gat_fused
+
+    if tiles:
+        monkeypatch.setenv("BOTGAT_TILES", tiles)
+    c = make_case(500, 500, 40000, 6, 16, ee=True, keep_p=0.2, attn_p=0.3, seed=77)
+    ref_out, ref_g = oracle_run(c)
+    g = bot_b200.Graph(c["src"].to(cuda), c["dst"].to(cuda), 500)
+    perm = g.edge_perm()
+    assert perm is not None and g._info.in_eid_identity == 1
+    if tiles:
+        assert (g._info.tiles_src, g._info.tiles_dst) == tuple(int(x) for x in tiles.split(","))
+
+    def run(order):
+        ft, el, er = (c[k].to(cuda).clone().requires_grad_(True) for k in ("ft", "el", "er"))
+        ee, keep, mul = c["ee"].to(cuda), c["keep"].to(cuda), c["attn_mul"].to(cuda)
+        if order == "canonical":
+            ee, keep, mul = ee[perm], keep[perm], mul[perm]
+        ee = ee.clone().requires_grad_(True)
+        out = gat_fused(g, ft, el, er, ee, keep, mul, edge_order=order)
+        out.backward(c["gout"].to(cuda))
+        return out.detach(), ft.grad, el.grad, er.grad, ee.grad
+
+    a, b = run("eid"), run("canonical")
+    assert rel_err(a[0], ref_out) <= FWD_TOL
+    for x, k in zip(a[1:], ("ft", "el", "er", "ee")):
+        assert rel_err(x, ref_g[k]) <= 1e-4, k
+    for x, y in zip(a[:4], b[:4]):
+        assert torch.equal(x, y)
+    assert torch.equal(a[4][perm], b[4])
+
+
+def test_edge_frame_canonical_view(cuda):
+    """graph.edata speaks edge ids; .canonical(key) is the same rows in canonical order, permuted once per assignment."""
+    import bot_b200
+
+    src, dst = graph_ref.synthetic_coo(50, 400, 5)
+    g = bot_b200.Graph(torch.from_numpy(src).to(cuda), torch.from_numpy(dst).to(cuda), 50)
+    x = torch.randn(400, 3, device=cuda)
+    g.edata["feat"] = x
+    c1 = g.edata.canonical("feat")
+    assert g.edata["feat"] is x and torch.equal(c1, x[g.edge_perm()]) and g.edata.canonical("feat") is c1
+    with g.local_scope():
+        g.edata["feat"] = x * 2
+        assert torch.equal(g.edata.canonical("feat"), (x * 2)[g.edge_perm()])
+    assert torch.equal(g.edata.canonical("feat"), x[g.edge_perm()])
+    # a COO already sorted by (dst, src) needs no permutation at all
+    order = np.lexsort((src, dst))
+    g2 = bot_b200.Graph(torch.from_numpy(src[order]).to(cuda), torch.from_numpy(dst[order]).to(cuda), 50)
+    assert g2.edge_perm() is None and g2.canonical_edge_ids() is None

@@ -15,7 +15,7 @@ def _graph(cuda, n=600, e=30000, seed=0, power_law=0.9):
 
     src, dst = graph_ref.synthetic_coo(n, e, seed, power_law=power_law)
     g = bot_b200.Graph(torch.from_numpy(src).to(cuda), torch.from_numpy(dst).to(cuda), n)
-    ref = graph_ref.build_formats(src, dst, n, n)
+    ref = graph_ref.build_formats(src, dst, n, n, canonical=True)   # the sampler walks the graph's own (canonical) rows
     return g, ref
 
 

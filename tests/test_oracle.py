@@ -62,15 +62,23 @@ def test_gradcheck_fp64():
     assert torch.autograd.gradcheck(f, (ft, el, er, ee), eps=1e-6, atol=1e-6)
 
 
-def test_big_form_equals_materialising_form():
-    c = make_case(80, 80, 900, 3, 8, ee=True, seed=5)
-    out, g = oracle_run(c, torch.float32)
+@pytest.mark.parametrize("kw", [dict(ee=True), dict(ee=True, keep_p=0.3), dict(er=False, symm=True, attn_p=0.2, self_loops=True),
+                                dict(ee=True, keep_p=0.2, attn_p=0.1, symm=True)])
+def test_big_form_equals_materialising_form(kw):
+    """The non-materialising form timed as the CPU arm (bench.py) == the parity reference, every flag."""
+    c = make_case(80, 80, 900, 3, 8, seed=5, **kw)
+    out, g = oracle_run(c, torch.float64)
     bg = gat_ref.BigGraph(c["src"], c["dst"], 80, 80)
-    o2, a, z = gat_ref.gat_sparse_big_forward(bg, c["ft"], c["el"], c["er"], c["ee"])
-    gft, gel, ger, gee = gat_ref.gat_sparse_big_backward(bg, c["ft"], a, z, o2, c["gout"])
-    assert torch.allclose(out, o2, rtol=1e-5, atol=1e-6)
+    f64 = lambda t: None if t is None else t.double()  # noqa: E731
+    o2, saved = gat_ref.gat_sparse_big_forward(bg, f64(c["ft"]), f64(c["el"]), f64(c["er"]), f64(c["ee"]), 0.2, c["keep"],
+                                               f64(c["attn_mul"]), f64(c["src_scale"]), f64(c["dst_scale"]))
+    gft, gel, ger, gee = gat_ref.gat_sparse_big_backward(bg, saved, c["gout"].double(), 0.2, c["er"] is not None, c["ee"] is not None,
+                                                         c["keep"], f64(c["src_scale"]), f64(c["dst_scale"]))
+    assert torch.allclose(out, o2, rtol=1e-10, atol=1e-12)
     for got, want in ((gft, g["ft"]), (gel, g["el"]), (ger, g["er"]), (gee, g["ee"])):
-        assert torch.allclose(got, want, rtol=1e-4, atol=1e-5)
+        if want is None:
+            continue
+        assert torch.allclose(got, want, rtol=1e-9, atol=1e-11)
 
 
 def test_graph_oracle_known_answers():

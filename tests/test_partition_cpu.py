@@ -106,7 +106,7 @@ def _worker(rank, world, port, plan, seed, ret):
 
 
 def _fake_gat_fused(graph, ft, el, er=None, ee=None, keep=None, attn_mul=None, src_scale=None, dst_scale=None,
-                    slope=0.2, attn_p=0.0, seed=0, hooks=None):
+                    slope=0.2, attn_p=0.0, seed=0, hooks=None, edge_order="canonical"):
     """CPU stand-in for bot_b200.functional.gat_fused (oracle math) that honours the Hooks protocol, so that
     PartitionedGraph.gat's overlap logic (async all-gather / early reduce-scatter) can run under gloo."""
     lsrc, ldst, n_dst = graph
