@@ -227,7 +227,10 @@ static int stage_one(const botgat_graph* g, const int32_t* eid, const int32_t* o
   for (int h0 = 0; h0 < H; h0 += kHMax) {
     const int Hn = std::min(kHMax, H - h0);
     const int vec = src ? record_vec(src + h0, ld, Hn) : 1;
-    const int grid = grid_for(g->n_edges);
+    // cache-blocked traversal: ONE position per thread and no grid-stride loop, so that the blocks resident at any
+    // time cover one contiguous window of the visiting order (a grid-stride loop would interleave ~30 far-apart
+    // windows, i.e. ~30 tiles, and the L2 would hold none of them)
+    const int grid = order ? (int)((g->n_edges + 255) / 256) : grid_for(g->n_edges);
     if (vec == 4) { BG_PF_SWITCH((k_edge_stage<4, PF><<<grid, 256, 0, st>>>(g->n_edges, h0, Hn, eid, order, src, ld, keep, keep_bits, dst))) }
     else if (vec == 2) { BG_PF_SWITCH((k_edge_stage<2, PF><<<grid, 256, 0, st>>>(g->n_edges, h0, Hn, eid, order, src, ld, keep, keep_bits, dst))) }
     else { BG_PF_SWITCH((k_edge_stage<1, PF><<<grid, 256, 0, st>>>(g->n_edges, h0, Hn, eid, order, src, ld, keep, keep_bits, dst))) }
@@ -281,7 +284,7 @@ extern "C" int botgat_edge_unstage(const botgat_graph* g, int order, int32_t H, 
     const int Hn = std::max(0, std::min(kHMax, H - h0));              // heads in this pass
     const int Hw = (int)std::min<int64_t>(kHMax, ld_gee - h0);        // floats written (heads + zeroed padding)
     const int vec = record_vec(grad_ee + h0, ld_gee, Hw);
-    const int grid = grid_for(g->n_edges);
+    const int grid = visit ? (int)((g->n_edges + 255) / 256) : grid_for(g->n_edges);  // see stage_one
     if (vec == 4) k_edge_unstage<4><<<grid, 256, 0, st>>>(g->n_edges, h0, Hn, Hw, eid, visit, gz, grad_ee, ld_gee);
     else if (vec == 2) k_edge_unstage<2><<<grid, 256, 0, st>>>(g->n_edges, h0, Hn, Hw, eid, visit, gz, grad_ee, ld_gee);
     else k_edge_unstage<1><<<grid, 256, 0, st>>>(g->n_edges, h0, Hn, Hw, eid, visit, gz, grad_ee, ld_gee);
