@@ -380,7 +380,10 @@ class GATConvSampledFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, graph, x_src, x_dst, w_src, w_dst, b_dst, ee, keep, attn_mul, dst_scale, H, D, slope, attn_p, seed):
+    def forward(ctx, graph, x_src, x_dst, w_src, w_dst, b_dst, ee, keep, attn_mul, dst_scale, H, D, slope, attn_p, seed,
+                src_scale=None):
+        # ``src_scale`` (full-graph variant, src/no-sampling/models.py:500-505,517): applied to the gathered rows by
+        # the kernels and to el here — the logit and the messages see the SCALED projection, er / the residual do not
         x_src, x_dst = _f32c(x_src, "feat_src"), _f32c(x_dst, "feat_dst")
         N_s, N_d, HD = graph.number_of_src_nodes(), graph.number_of_dst_nodes(), H * D
         if x_src.shape[0] != N_s or x_dst.shape[0] != N_d:
@@ -390,25 +393,25 @@ class GATConvSampledFn(torch.autograd.Function):
         ws, wd = _pad_rows(w_src, P), _pad_rows(w_dst, P)
         bd = torch.cat([b_dst, b_dst.new_zeros(P - HD)])
         ee, ld_ee, keep, attn_mul, ld_am = _check_edge_operands(graph, H, ee, keep, attn_mul)
-        dst_scale = _f32c(dst_scale, "dst_scale")
+        dst_scale, src_scale = _f32c(dst_scale, "dst_scale"), _f32c(src_scale, "src_scale")
         with torch.cuda.device(x_src.device):
             Ys = x_src @ ws.t()
             Yd = torch.addmm(bd, x_dst, wd.t())
-            el = Ys[:, HD:HD + H].contiguous()
+            el = Ys[:, HD:HD + H].contiguous() if src_scale is None else Ys[:, HD:HD + H] * src_scale.unsqueeze(-1)
             er = Yd[:, HD:HD + H].contiguous() if has_er else None
             out, row_max, row_sum, pre, attn_p_used = _forward_core(
-                graph, Ys, H, D, el, er, ee, ld_ee, keep, attn_mul, ld_am, None, dst_scale, slope, attn_p, seed, None,
+                graph, Ys, H, D, el, er, ee, ld_ee, keep, attn_mul, ld_am, src_scale, dst_scale, slope, attn_p, seed, None,
                 any(ctx.needs_input_grad))
             rst = out + Yd[:, :HD].view(N_d, H, D)                                    # models.py:159-160
         ctx.graph, ctx.pre, ctx.same_x = graph, pre, x_dst is x_src or x_dst.data_ptr() == x_src.data_ptr() and N_s == N_d
         ctx.cfg = (H, D, edge_mode == "staged", float(slope), attn_p_used, int(seed))
         ctx.dims = (P, has_er, w_src.shape[0], w_dst.shape[0])
-        ctx.save_for_backward(x_src, x_dst, ws, wd, Ys, el, er, ee, keep, attn_mul, dst_scale, out, row_max, row_sum)
+        ctx.save_for_backward(x_src, x_dst, ws, wd, Ys, el, er, ee, keep, attn_mul, dst_scale, out, row_max, row_sum, src_scale)
         return rst
 
     @staticmethod
     def backward(ctx, grst):
-        x_src, x_dst, ws, wd, Ys, el, er, ee, keep, attn_mul, dst_scale, out, row_max, row_sum = ctx.saved_tensors
+        x_src, x_dst, ws, wd, Ys, el, er, ee, keep, attn_mul, dst_scale, out, row_max, row_sum, src_scale = ctx.saved_tensors
         H, D = ctx.cfg[0], ctx.cfg[1]
         P, has_er, rows_s, rows_d = ctx.dims
         HD = H * D
@@ -421,9 +424,9 @@ class GATConvSampledFn(torch.autograd.Function):
             gYs = torch.empty((N_s, P), dtype=torch.float32, device=dev)
             gYd = torch.empty((N_d, P), dtype=torch.float32, device=dev)
             grad_el, grad_er, grad_ee = _backward_core(
-                ctx.graph, ctx.cfg, ctx.pre, None, Ys, el, er, ee, keep, attn_mul, None, dst_scale, out, row_max, row_sum,
+                ctx.graph, ctx.cfg, ctx.pre, None, Ys, el, er, ee, keep, attn_mul, src_scale, dst_scale, out, row_max, row_sum,
                 grst, gYs, has_er, need_ee)
-            gYs[:, HD:HD + H] = grad_el
+            gYs[:, HD:HD + H] = grad_el if src_scale is None else grad_el * src_scale.unsqueeze(-1)
             gYs[:, HD + H:].zero_()
             gYd[:, :HD] = grst.view(N_d, HD)
             if has_er:
@@ -440,7 +443,7 @@ class GATConvSampledFn(torch.autograd.Function):
             else:
                 gx_s = gYs @ ws if need[1] else None
                 gx_d = gYd @ wd if need[2] else None
-        return (None, gx_s, gx_d, gw_s, gw_d, gb, grad_ee, None, None, None, None, None, None, None, None)
+        return (None, gx_s, gx_d, gw_s, gw_d, gb, grad_ee, None, None, None, None, None, None, None, None, None)
 
 
 class EdgeLogitProj(torch.autograd.Function):

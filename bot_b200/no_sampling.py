@@ -102,12 +102,18 @@ class ElementWiseLinear(nn.Module):
 class GATConv(nn.Module):
     """GAT layer, full-graph variant (models.py:416-566).
 
-    ``attn_dropout_mode``: "exact" draws the attention-dropout mask with torch's own
-    generator (the reference's semantics, mask materialised once as (E,H)); "fused"
-    draws it inside the kernels from a Philox stream keyed on (seed, edge id, head).
+    ``attn_dropout_mode``: "fused" (default) draws the attention-dropout mask inside the kernels from a
+    Philox stream keyed on (seed, canonical edge number, head) — nothing E-sized is materialised; "exact"
+    draws it with the module's own ``nn.Dropout`` on an (E', H, 1) tensor exactly as the reference does
+    (models.py:537/544; four extra E x H passes per layer and step) and is what the golden-vector tests replay.
+
+    ``fold_logits``: compute ``el`` / ``er`` as extra columns of the ``fc`` / ``res_fc`` GEMMs
+    (``W_el[h] = W[h]^T attn_l[h]``) instead of a pass over the (N, H, D) projection
+    (models.py:517-521); the kernels read ``ft`` in place inside the wide GEMM output.
     """
 
-    attn_dropout_mode = "exact"
+    attn_dropout_mode = "fused"
+    fold_logits = True
 
     def __init__(self, in_feats, out_feats, num_heads=1, feat_drop=0.0, attn_drop=0.0, edge_drop=0.0,
                  negative_slope=0.2, linear=True, activation=None, allow_zero_in_degree=False,
@@ -165,6 +171,10 @@ class GATConv(nn.Module):
             if not self._allow_zero_in_degree and graph.has_zero_in_degree:  # models.py:477-479
                 assert False
             n_dst = graph.number_of_dst_nodes()
+            fold = (self.fold_logits and not isinstance(feat, tuple) and hasattr(self, "fc") and self.res_fc is not None
+                    and feat.is_cuda and feat.dim() == 2 and self._activation is None)
+            if fold:
+                return self._forward_folded(graph, feat, n_dst)
             if isinstance(feat, tuple):                                      # models.py:481-488
                 h_src, h_dst = self.feat_drop(feat[0]), self.feat_drop(feat[1])
                 if not hasattr(self, "fc_src"):
@@ -192,22 +202,7 @@ class GATConv(nn.Module):
             if self.attn_r is not None:
                 er = torch.einsum("nhd,hd->nh", ft_dst, self.attn_r[0])       # models.py:521
 
-            E = graph.number_of_edges()
-            keep = attn_mul = eids = None
-            attn_p, seed = 0.0, 0
-            if self.training and self.edge_drop > 0:                          # models.py:528-537
-                keep, eids = draw_edge_keep(E, self.edge_drop, ft.device)
-            if self.training and self.attn_drop.p > 0:
-                if self.attn_dropout_mode == "exact":
-                    attn_mul = draw_attn_mul(self.attn_drop, E, H, ft.device, eids)
-                else:
-                    attn_p = self.attn_drop.p
-                    seed = int(torch.randint(0, 2**62, (1,)).item())
-
-            # per-edge operands in the graph's canonical order (bot_b200.Graph): the selection draw's keep set already
-            # is; the literal randperm replay / an "exact" mask without edge-drop are in edge-id order
-            if not isinstance(eids, KeptEdges):
-                keep, attn_mul = to_canonical(graph, keep), to_canonical(graph, attn_mul)
+            keep, attn_mul, attn_p, seed = self._draw(graph, graph.number_of_edges(), H, ft.device)   # models.py:528-537
             rst = gat_fused(graph, ft, el, er, None, keep, attn_mul, src_scale, dst_scale,
                             self._negative_slope, attn_p, seed, edge_order="canonical")   # models.py:523-555
 
@@ -216,6 +211,44 @@ class GATConv(nn.Module):
             if self._activation is not None:
                 rst = self._activation(rst)
             return rst
+
+
+    def _draw(self, graph, E, H, device):
+        """Edge-drop keep set and attention dropout of one forward, in the graph's canonical edge order."""
+        keep = attn_mul = eids = None
+        attn_p, seed = 0.0, 0
+        if self.training and self.edge_drop > 0:                              # models.py:528-537
+            keep, eids = draw_edge_keep(E, self.edge_drop, device)
+        if self.training and self.attn_drop.p > 0:
+            if self.attn_dropout_mode == "exact":
+                attn_mul = draw_attn_mul(self.attn_drop, E, H, device, eids)
+            else:
+                attn_p = self.attn_drop.p
+                seed = int(torch.randint(0, 2**62, (1,)).item())
+        if not isinstance(eids, KeptEdges):   # the literal randperm replay / an "exact" mask alone are in edge-id order
+            keep, attn_mul = to_canonical(graph, keep), to_canonical(graph, attn_mul)
+        return keep, attn_mul, attn_p, seed
+
+    def _forward_folded(self, graph, feat, n_dst):
+        """models.py:490-560 with the logits folded into the projections: ONE wide GEMM per side,
+        ``[ft | el] = h_src @ [W ; W_el]^T`` and ``[res | er] = h_dst @ [W_res ; W_er]^T``, read in place by the kernels."""
+        from .functional import GATConvSampledFn
+
+        H, D = self._num_heads, self._out_feats
+        h_src = self.feat_drop(feat)
+        h_dst = h_src[:n_dst] if graph.is_block else h_src
+        Wv = self.fc.weight.view(H, D, -1)
+        w_src = torch.cat([self.fc.weight, torch.einsum("hdi,hd->hi", Wv, self.attn_l[0])], 0)       # el, models.py:517
+        w_dst = self.res_fc.weight
+        if self.attn_r is not None:                                           # er from the UNSCALED projection, :521
+            w_dst = torch.cat([w_dst, torch.einsum("hdi,hd->hi", Wv, self.attn_r[0])], 0)
+        src_scale = dst_scale = None
+        if self._use_symmetric_norm:
+            src_scale, dst_scale = graph.deg_scale("out", -0.5), graph.deg_scale("in", 0.5)
+        keep, attn_mul, attn_p, seed = self._draw(graph, graph.number_of_edges(), H, feat.device)
+        zero_bias = torch.zeros(H * D, dtype=feat.dtype, device=feat.device)   # res_fc has no bias (models.py:453)
+        return GATConvSampledFn.apply(graph, h_src, h_dst, w_src, w_dst, zero_bias, None, keep, attn_mul, dst_scale, H, D,
+                                      self._negative_slope, attn_p, seed, src_scale)
 
 
 class GAT(nn.Module):

@@ -29,7 +29,7 @@ fold_projections = os.environ.get("BOTGAT_FOLD", "1") != "0"
 
 
 class GATConv(nn.Module):
-    attn_dropout_mode = "exact"  # see bot_b200.no_sampling.GATConv
+    attn_dropout_mode = "fused"  # see bot_b200.no_sampling.GATConv
 
     def __init__(self, node_feats, edge_feats, out_feats, n_heads=1, attn_drop=0.0, edge_drop=0.0,
                  negative_slope=0.2, residual=True, activation=None, use_attn_dst=True,

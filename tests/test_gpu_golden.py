@@ -19,6 +19,9 @@ def test_module_matches_reference(cuda, path, monkeypatch):
 
     case = load(path)
     ctor = case["ctor"]
+    # replay the reference's own nn.Dropout draw (the default is the in-kernel Philox stream)
+    monkeypatch.setattr(no_sampling.GATConv, "attn_dropout_mode", "exact")
+    monkeypatch.setattr(sampled.GATConv, "attn_dropout_mode", "exact")
     torch.manual_seed(0)
     cls = no_sampling.GATConv if case["kind"] == "v1" else sampled.GATConv
     conv = cls(**ctor).to(cuda)

@@ -760,3 +760,36 @@ def test_edge_frame_canonical_view(cuda):
     order = np.lexsort((src, dst))
     g2 = bot_b200.Graph(torch.from_numpy(src[order]).to(cuda), torch.from_numpy(dst[order]).to(cuda), 50)
     assert g2.edge_perm() is None and g2.canonical_edge_ids() is None
+
+
+@pytest.mark.parametrize("kind", ["symm_attn_r", "plain", "block", "train_drops"])
+def test_v1_folded_logits_match_unfolded(cuda, kind):
+    """no_sampling.GATConv with el / er folded into the fc / res_fc GEMMs (models.py:517-521) against
+    the op-by-op sequence: outputs and every parameter gradient."""
+    import bot_b200
+    from bot_b200.no_sampling import GATConv
+
+    torch.manual_seed(3)
+    n_src, n_dst = (300, 80) if kind == "block" else (300, 300)
+    src = torch.randint(0, n_src, (6000,), device=cuda)
+    dst = torch.randint(0, n_dst, (6000,), device=cuda)
+    if kind != "block":
+        src, dst = torch.cat([src, torch.arange(300, device=cuda)]), torch.cat([dst, torch.arange(300, device=cuda)])
+    g = bot_b200.Graph(src, dst, n_src, n_dst, is_block=kind == "block")
+    conv = GATConv(40, 16, num_heads=3, use_symmetric_norm=kind == "symm_attn_r", non_interactive_attn=kind != "plain",
+                   edge_drop=0.3 if kind == "train_drops" else 0.0, attn_drop=0.2 if kind == "train_drops" else 0.0).to(cuda)
+    conv.train(kind == "train_drops")
+    x = torch.randn(n_src, 40, device=cuda)
+    res = []
+    for fold in (True, False):
+        conv.fold_logits = fold
+        conv.zero_grad()
+        xi = x.clone().requires_grad_(True)
+        torch.manual_seed(11)          # the same draws in both passes
+        y = conv(g, xi)
+        y.square().sum().backward()
+        res.append((y.detach(), xi.grad, {k: p.grad.clone() for k, p in conv.named_parameters()}))
+    (y1, gx1, gp1), (y2, gx2, gp2) = res
+    assert rel_err(y1, y2) <= FWD_TOL * 2 and rel_err(gx1, gx2) <= 1e-4
+    for k in gp1:
+        assert rel_err(gp1[k], gp2[k]) <= 1e-4, k
