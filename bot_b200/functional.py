@@ -265,7 +265,7 @@ def _backward_core(graph, cfg, pre, hooks, ft2d, el, er, ee, keep, attn_mul, src
     a.ld_gee = grad_ee.stride(0) if grad_ee is not None else 0
     post_src = hooks.post_src if hooks is not None else None
     chunks = hooks.head_chunks if hooks is not None and hooks.head_chunks else None
-    if chunks is not None and len(chunks) > 1:
+    if chunks is not None and (len(chunks) > 1 or getattr(hooks, "force_chunked", False)):
         # src phase head range by head range; the caller's hook ships each range's grad_ft while the next one runs
         a.phases = 1
         _lib.check(lib.botgat_gat_backward(h, C.byref(a), _stream()), "botgat_gat_backward")

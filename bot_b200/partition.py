@@ -151,6 +151,147 @@ class _SparseHalo(torch.autograd.Function):
         return g_own, None, None, None, None
 
 
+class P2PHalo:
+    """Buffers of the peer-memory halo exchange of one layer shape (``botgat_halo_pull`` / ``botgat_halo_pull_reduce``,
+    csrc/halo.cu): this rank's shard ``[ft | el]`` and its table of partial gradients live in symmetric memory
+    (``torch.distributed._symmetric_memory``: every rank maps every other rank's buffer, NVLink peer loads), the
+    gathered table and the reduced gradient shard are ordinary local tensors.  Row width ``P`` = H*D + H padded to 32
+    floats (128-byte rows)."""
+
+    def __init__(self, pg, H, D):
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.H, self.D, self.HD = H, D, H * D
+        self.P = (self.HD + H + 31) // 32 * 32
+        dev = pg.local.device
+        group = pg.group if pg.group is not None else dist.group.WORLD
+        rows = pg.max_own
+        self.shard = symm_mem.empty((rows, self.P), dtype=torch.float32, device=dev)
+        self.gtable = symm_mem.empty((pg.world * rows, self.P), dtype=torch.float32, device=dev)
+        self.h_shard = symm_mem.rendezvous(self.shard, group)
+        self.h_gtable = symm_mem.rendezvous(self.gtable, group)
+        self.shard.zero_()
+        self.gtable.zero_()
+        self.shard_ptrs = (C.c_void_p * pg.world)(*[int(p) for p in self.h_shard.buffer_ptrs])
+        self.gtable_ptrs = (C.c_void_p * pg.world)(*[int(p) for p in self.h_gtable.buffer_ptrs])
+        self.table = torch.zeros((pg.world * rows, self.P), dtype=torch.float32, device=dev)
+        self.gshard = torch.zeros((rows, self.P), dtype=torch.float32, device=dev)
+        self.stream = torch.cuda.Stream(device=dev)
+        self.blocks = int(os.environ.get("BOTGAT_HALO_BLOCKS", "64"))
+        self.world, self.rank, self.rows = pg.world, pg.rank, rows
+
+    def pull(self, col0, width):
+        from . import _lib
+        from .graph import _stream
+
+        _lib.check(_lib.load().botgat_halo_pull(self.world, self.shard_ptrs, self.rows, self.P, col0, width, self.table.data_ptr(),
+                                                self.P, self.blocks, _stream()), "botgat_halo_pull")
+
+    def pull_reduce(self, col0, width):
+        from . import _lib
+        from .graph import _stream
+
+        _lib.check(_lib.load().botgat_halo_pull_reduce(self.world, self.rank, self.gtable_ptrs, self.rows, self.P, col0, width,
+                                                       self.gshard.data_ptr(), self.P, self.blocks, _stream()),
+                   "botgat_halo_pull_reduce")
+
+
+class _P2PGatFn(torch.autograd.Function):
+    """The partitioned layer with the halo exchanged by this repo's own peer-memory kernels instead of NCCL collectives,
+    pipelined per head range on a second stream:
+
+      forward   copy [ft | el] of the owned rows into the symmetric shard -> inter-GPU barrier ->
+                pull(head range k+1)  ||  gather kernel(head range k)
+      backward  src kernel(head range k+1) writes its partial grad_ft into the symmetric gradient table  ||
+                barrier + pull_reduce(head range k) -> owned rows of grad_ft;  grad_el the same after the last range;
+                the edge phase (grad_ee, grad_er) runs beside the tail of the exchange.
+    """
+
+    @staticmethod
+    def forward(ctx, pg, hx, chunks, ft_own, el_own, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed):
+        from . import functional as Fn
+
+        H, D, HD, P = hx.H, hx.D, hx.HD, hx.P
+        n_own = pg.n_own
+        graph = pg.local
+        main = torch.cuda.current_stream()
+        # everybody has finished reading my shard (the pulls of the previous step ended before their kernels did)
+        hx.h_shard.barrier(channel=0)
+        hx.shard[:n_own, :HD].copy_(ft_own.reshape(n_own, HD))
+        hx.shard[:n_own, HD:HD + H].copy_(el_own.reshape(n_own, H))
+        hx.h_shard.barrier(channel=1)        # every shard is written
+        hx.stream.wait_stream(main)
+        events = []
+        with torch.cuda.stream(hx.stream):
+            for i, (hb, hc) in enumerate(chunks):
+                if i == 0:
+                    hx.pull(HD, H)           # el of every source row
+                hx.pull(hb * D, hc * D)
+                ev = torch.cuda.Event()
+                ev.record(hx.stream)
+                events.append(ev)
+        state = {"el": None}
+
+        def pre_head(i):
+            main.wait_event(events[i])
+
+        ee, ld_ee, keep, attn_mul, ld_am = Fn._check_edge_operands(graph, H, ee, keep, attn_mul)
+        # el is needed (contiguous) by the very first launch: wait for chunk 0 (which carries it) up front
+        main.wait_event(events[0])
+        el_all = hx.table[:, HD:HD + H].contiguous()
+        hooks = Fn.Hooks(head_chunks=chunks, pre_head=pre_head)
+        out, row_max, row_sum, pre, attn_p_used = Fn._forward_core(
+            graph, hx.table, H, D, el_all, er, ee, ld_ee, keep, attn_mul, ld_am, src_scale, dst_scale, slope, attn_p, seed,
+            hooks, True)
+        ctx.pg, ctx.hx, ctx.chunks = pg, hx, chunks
+        ctx.cfg = (H, D, Fn.edge_mode == "staged", float(slope), attn_p_used, int(seed))
+        ctx.save_for_backward(el_all, er, ee, keep, attn_mul, src_scale, dst_scale, out, row_max, row_sum)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        from . import functional as Fn
+
+        pg, hx, chunks = ctx.pg, ctx.hx, ctx.chunks
+        el_all, er, ee, keep, attn_mul, src_scale, dst_scale, out, row_max, row_sum = ctx.saved_tensors
+        H, D, HD = hx.H, hx.D, hx.HD
+        n_own = pg.n_own
+        main = torch.cuda.current_stream()
+        gout = gout.contiguous()
+        # everybody has finished reading my gradient table of the previous step
+        hx.h_gtable.barrier(channel=0)
+
+        def post_src_head(i, grad_ft, grad_el):
+            ev = torch.cuda.Event()
+            ev.record(main)
+            hb, hc = chunks[i]
+            last = i == len(chunks) - 1
+            if last:
+                hx.gtable[:, HD:HD + H].copy_(grad_el)      # complete only after the last head range
+                ev = torch.cuda.Event()
+                ev.record(main)
+            with torch.cuda.stream(hx.stream):
+                hx.stream.wait_event(ev)
+                hx.h_gtable.barrier(channel=1 + i)          # every rank has written this column range
+                hx.pull_reduce(hb * D, hc * D)
+                if last:
+                    hx.pull_reduce(HD, H)
+
+        hooks = Fn.Hooks(head_chunks=chunks if len(chunks) > 1 else [chunks[0], ], post_src_head=post_src_head)
+        hooks.force_chunked = True
+        need_er = er is not None and ctx.needs_input_grad[5]
+        need_ee = ee is not None and ctx.needs_input_grad[6]
+        grad_el, grad_er, grad_ee = Fn._backward_core(
+            pg.local, ctx.cfg, None, hooks, hx.table, el_all, er, ee, keep, attn_mul, src_scale, dst_scale, out, row_max, row_sum,
+            gout, hx.gtable, need_er, need_ee)
+        main.wait_stream(hx.stream)
+        grad_ft_own = hx.gshard[:n_own, :HD].reshape(n_own, H, D).clone()
+        grad_el_own = hx.gshard[:n_own, HD:HD + H].clone()
+        return (None, None, None, grad_ft_own, grad_el_own, grad_er, grad_ee, None, None, None, None, None, None, None)
+
+
 class PartitionedGraph:
     """This rank's share of a homogeneous graph.
 
@@ -168,6 +309,11 @@ class PartitionedGraph:
         self.group = group
         # per-head pipelining of the halo exchange in `gat` (see _gat_head_pipelined); opt-in until measured at N = 8
         self.pipeline_heads = os.environ.get("BOTGAT_PIPE_HEADS", "0") == "1"
+        # halo exchange of the dense plan: "nccl" = all_gather_into_tensor / reduce_scatter_tensor of whole tables;
+        # "p2p" = this repo's peer-memory kernels (csrc/halo.cu), pipelined per head range (needs NVLink peer access)
+        self.exchange = os.environ.get("BOTGAT_EXCHANGE", "nccl")
+        self.halo_chunks = int(os.environ.get("BOTGAT_HALO_CHUNKS", "0"))    # head ranges per exchange; 0 = auto
+        self._p2p = {}
         self.world = dist.get_world_size(group) if world is None else world
         self.rank = dist.get_rank(group) if rank is None else rank
         self.n_nodes = n_nodes
@@ -244,7 +390,7 @@ class PartitionedGraph:
         return outs[0] if len(outs) == 1 else tuple(outs)
 
     def gat(self, ft_own, el_own, er=None, ee=None, keep=None, attn_mul=None, src_scale=None, dst_scale=None,
-            slope=0.2, attn_p=0.0, seed=0, edge_order="eid"):
+            slope=0.2, attn_p=0.0, seed=0, edge_order="eid", halo_slot=0):
         """The partitioned layer in one call: halo exchange + ``gat_fused`` on the local block, with the collectives
         overlapped with the work that does not depend on them (dense plan):
           forward : all-gather of [ft], [el]  ||  edge staging            -> forward gather kernel
@@ -258,6 +404,20 @@ class PartitionedGraph:
             ee, keep, attn_mul = (to_canonical(self.local, t) for t in (ee, keep, attn_mul))
         edge_order = "canonical"
 
+        if self.world > 1 and self.plan == "dense" and self.exchange == "p2p" and ft_own.is_cuda and ft_own.dim() == 3:
+            H, D = ft_own.shape[1], ft_own.shape[2]
+            # the exchange buffers hold the gathered table until the layer's backward has run: layers whose forward /
+            # backward overlap in time (a multi-layer model) each need their own ``halo_slot``
+            hx = self._p2p.get((H, D, halo_slot))
+            if hx is None:
+                hx = self._p2p[(H, D, halo_slot)] = P2PHalo(self, H, D)
+            n = max(1, min(H, self.halo_chunks if self.halo_chunks > 0 else (H if hx.table.numel() * 4 >= (1 << 30) else 2)))
+            if self.local._info.n_slots_in or self.local._info.n_slots_out:
+                n = 1     # split (heavy) rows need the full head range in one launch
+            bounds = [round(i * H / n) for i in range(n + 1)]
+            chunks = [(bounds[i], bounds[i + 1] - bounds[i]) for i in range(n) if bounds[i + 1] > bounds[i]]
+            return _P2PGatFn.apply(self, hx, chunks, ft_own, el_own, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p,
+                                   seed)
         if self.world == 1 or self.plan != "dense":
             ft_all, el_all = self.halo_gather(ft_own, el_own)
             return gat_fused(self.local, ft_all, el_all, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed,

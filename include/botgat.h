@@ -310,6 +310,26 @@ int botgat_rows_scatter_add(float* table, int64_t ld, int64_t width, const int64
                             const float* in /* (n_rows,width), rows unique */, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Halo exchange through NVLink peer memory (SURVEY.md section 8b `botgat_halo_exchange`; no reference implementation).
+ * The exchange of the row-sharded source table [ft | el] of the partitioned layer, one COLUMN RANGE (= head range) at
+ * a time, by peer loads from buffers every rank has mapped (CUDA VMM / torch symmetric memory) — so that the transfer
+ * of head range k+1 overlaps the gather kernel of head range k and nothing is repacked.  The caller provides the
+ * inter-GPU barriers (peers' buffers written before a pull, read before they are overwritten).
+ *   world <= 16; peer_* : HOST arrays of `world` DEVICE pointers (entry `r` = rank r's buffer, own rank included).
+ *   n_blocks : grid size (0 = 64 blocks of 512 threads); the exchange shares the GPU with the kernel it overlaps.
+ *
+ * botgat_halo_pull (forward, the all-gather):
+ *   table[r * rows_per_rank + i, col0 : col0 + width] = peer_shards[r][i, col0 : col0 + width]   for r = 0..world-1
+ * botgat_halo_pull_reduce (backward, the reduce-scatter; summed in the FIXED order r = 0..world-1, deterministic):
+ *   out[i, col0 : col0 + width] = sum_r peer_tables[r][rank * rows_per_rank + i, col0 : col0 + width]
+ * ---------------------------------------------------------------------- */
+int botgat_halo_pull(int32_t world, const float* const* peer_shards /* HOST */, int64_t rows_per_rank, int64_t ld_shard,
+                     int64_t col0, int64_t width, float* table, int64_t ld_table, int32_t n_blocks, void* stream);
+int botgat_halo_pull_reduce(int32_t world, int32_t rank, const float* const* peer_tables /* HOST */, int64_t rows_per_rank,
+                            int64_t ld_table, int64_t col0, int64_t width, float* out, int64_t ld_out, int32_t n_blocks,
+                            void* stream);
+
+/* ------------------------------------------------------------------------
  * Neighbour sampling and block construction on the device.  Replaces
  * dgl.dataloading.MultiLayerNeighborSampler + NodeDataLoader and their CPU worker processes
  * (src/ogbn-proteins/gat.py:177-201, src/ogbn-products/gat.py:202-233), per layer:
