@@ -382,8 +382,16 @@ def run_ours(args):
 
     # ---------------- device-resident leg (value) ----------------
     n_own = n_dst_l if layer is not None else n_nodes
-    ft_own = torch.randn(n_own, H, D, device=dev, generator=gen).requires_grad_(True)
-    el_own = torch.randn(n_own, H, device=dev, generator=gen).requires_grad_(True)
+    if layer is not None and layer.exchange == "p2p" and layer.plan == "dense":
+        # the projected rows are produced straight into this rank's slice of the peer-memory exchange table
+        hx = layer.halo_buffers(H, D)
+        with torch.no_grad():
+            hx.own_ft.normal_(generator=gen)
+            hx.own_el.normal_(generator=gen)
+        ft_own, el_own = hx.own_ft.detach().requires_grad_(True), hx.own_el.detach().requires_grad_(True)
+    else:
+        ft_own = torch.randn(n_own, H, D, device=dev, generator=gen).requires_grad_(True)
+        el_own = torch.randn(n_own, H, device=dev, generator=gen).requires_grad_(True)
     er = torch.randn(n_dst_l, H, device=dev, generator=gen).requires_grad_(True) if c["er"] else None
     # edge logits as the layer's own producers emit them: one 32-byte record per edge (E, pad_heads(H)), in the graph's
     # CANONICAL edge order (static edata is stored canonically, bot_b200.graph.EdgeFrame)
@@ -519,8 +527,8 @@ def run_ours(args):
     del ft_own, el_own, er, ee, gout, leaves
     torch.cuda.empty_cache()
 
-    e2e = run_e2e(args, shape, c, graph, layer, world, rank, dev, n_nodes, n_edges, n_own, E_local, cs_l, ds_l, cs_own, barrier,
-                  seeds, replicas)
+    e2e = None if args.no_e2e else run_e2e(args, shape, c, graph, layer, world, rank, dev, n_nodes, n_edges, n_own, E_local, cs_l,
+                                           ds_l, cs_own, barrier, seeds, replicas)
 
     # secondary number: the same layer on a heavy-tailed graph (dst ~ rank^-0.8; the hottest row has ~2 % of all edges)
     skew = None
@@ -571,7 +579,8 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "roofline": roofline, "kernels": kernels, "instrumented_ms_per_step": round(ms_instr / args.steps, 4),
             "graph": {"canonical_edge_order": bool(info.in_eid_identity), "transpose_tiles": [int(info.tiles_src), int(info.tiles_dst)],
-                      "split_row_slots": [int(info.n_slots_in), int(info.n_slots_out)]},
+                      "split_row_slots": [int(info.n_slots_in), int(info.n_slots_out)],
+                      "halo_exchange": None if layer is None else (layer.exchange if layer.plan == "dense" else "sparse all-to-all")},
             "parity": parity, "cpu_baseline": cpu_baseline, "config1_cora_cpu_reference": cora, "e2e": e2e, "skew_variant": skew,
             "gpu_launches": int(launches), "clocks": clocks,
         }
@@ -759,6 +768,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-skew", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="developer runs: skip the end-to-end leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -98,8 +98,7 @@ SIGNATURES = {
     "botgat_partition_extract": (C.c_int, [c_vp, C.c_int64, C.c_int64, c_vp, c_vp, c_vp, c_i64p, c_vp]),
     "botgat_rows_gather": (C.c_int, [c_vp, C.c_int64, C.c_int64, c_vp, C.c_int64, c_vp, c_vp]),
     "botgat_rows_scatter_add": (C.c_int, [c_vp, C.c_int64, C.c_int64, c_vp, C.c_int64, c_vp, c_vp]),
-    "botgat_halo_pull": (C.c_int, [C.c_int32, C.POINTER(c_vp), C.c_int64, C.c_int64, C.c_int64, C.c_int64, c_vp, C.c_int64,
-                                   C.c_int32, c_vp]),
+    "botgat_halo_pull": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(c_vp), C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, c_vp]),
     "botgat_halo_pull_reduce": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(c_vp), C.c_int64, C.c_int64, C.c_int64, C.c_int64, c_vp,
                                           C.c_int64, C.c_int32, c_vp]),
 }

@@ -20,7 +20,9 @@
 namespace botgat {
 
 constexpr int kMaxWorld = 16;
-constexpr int kHaloThreads = 512;
+// Small blocks: the exchange runs BESIDE a gather kernel that owns (nearly) the whole register file; a 128-thread block
+// fits into the space one retiring gather block frees, a 512-thread block would wait for the gather grid to drain.
+constexpr int kHaloThreads = 128;
 constexpr int kUnroll = 8;
 
 struct PeerPtrs {
@@ -29,82 +31,104 @@ struct PeerPtrs {
 
 __device__ __forceinline__ float4 ld_peer(const float4* p) {
   float4 r;
-  // peer memory is written by another GPU in this very step: a plain (coherent at system scope after the
-  // inter-GPU barrier) load, no non-coherent / read-only path, no L1 allocation of stale lines
+  // peer memory is written by another GPU in this very step: a system-scope load (no read-only / L1 path that could
+  // serve a stale line); ordering against the writer comes from the inter-GPU barrier the caller places before the launch
   asm volatile("ld.global.relaxed.sys.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
   return r;
 }
+__device__ __forceinline__ float ld_peer1(const float* p) {
+  float x;
+  asm volatile("ld.global.relaxed.sys.f32 %0, [%1];" : "=f"(x) : "l"(p) : "memory");
+  return x;
+}
 
-// VEC = 4: width, column offset and every leading dimension are multiples of 4 floats and all bases 16-byte aligned
+// table[r * rows + i, c0:c0+w] = peer_r[r * rows + i, c0:c0+w] for every rank r != me.  Every rank's table has the
+// same layout and rank r's OWN slice of its table is the authoritative copy of its rows: nothing is staged.
+// VEC = 4: width, column offset and the leading dimension are multiples of 4 floats and all bases 16-byte aligned.
 template <int VEC>
 __global__ void __launch_bounds__(kHaloThreads)
-k_halo_pull(int world, PeerPtrs peers, int64_t rows, int64_t ld_shard, int64_t c0, int width, float* __restrict__ table,
-            int64_t ld_table) {
+k_halo_pull(int world, int me, PeerPtrs peers, int64_t rows, int64_t ld, int64_t c0, int width, float* __restrict__ table) {
   const int wv = width / VEC;                      // vectors per row piece
   const int64_t per_rank = rows * wv;
-  const int64_t total = per_rank * world;
+  const int64_t total = per_rank * (world - 1);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  auto locate = [&](int64_t j, int& r, int64_t& off) {
+    const int q = (int)(j / per_rank);
+    r = q + (q >= me);                             // skip the own rank
+    const int64_t k = j - q * per_rank, row = k / wv;
+    off = (r * rows + row) * ld + c0 + (k - row * wv) * VEC;
+  };
   if constexpr (VEC == 4) {
     for (; i + (kUnroll - 1) * stride < total; i += kUnroll * stride) {
       float4 v[kUnroll];
-      int64_t dsto[kUnroll];
+      int64_t off[kUnroll];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
-        const int64_t j = i + u * stride;
-        const int r = (int)(j / per_rank);
-        const int64_t k = j - r * per_rank, row = k / wv;
-        const int col = (int)(k - row * wv) * 4;
-        v[u] = ld_peer(reinterpret_cast<const float4*>(peers.p[r] + row * ld_shard + c0 + col));
-        dsto[u] = (r * rows + row) * ld_table + c0 + col;
+        int r;
+        locate(i + u * stride, r, off[u]);
+        v[u] = ld_peer(reinterpret_cast<const float4*>(peers.p[r] + off[u]));
       }
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) *reinterpret_cast<float4*>(table + dsto[u]) = v[u];
+      for (int u = 0; u < kUnroll; ++u) *reinterpret_cast<float4*>(table + off[u]) = v[u];
     }
   }
   for (; i < total; i += stride) {
-    const int r = (int)(i / per_rank);
-    const int64_t k = i - r * per_rank, row = k / wv;
-    const int col = (int)(k - row * wv) * VEC;
-    const float* s = peers.p[r] + row * ld_shard + c0 + col;
-    float* d = table + (r * rows + row) * ld_table + c0 + col;
-    if constexpr (VEC == 4) *reinterpret_cast<float4*>(d) = ld_peer(reinterpret_cast<const float4*>(s));
-    else {
-      float x;
-      asm volatile("ld.global.relaxed.sys.f32 %0, [%1];" : "=f"(x) : "l"(s) : "memory");
-      *d = x;
-    }
+    int r;
+    int64_t off;
+    locate(i, r, off);
+    if constexpr (VEC == 4) *reinterpret_cast<float4*>(table + off) = ld_peer(reinterpret_cast<const float4*>(peers.p[r] + off));
+    else table[off] = ld_peer1(peers.p[r] + off);
   }
 }
 
-template <int VEC>
+// out[i, c0:c0+w] = sum_r table_r[me * rows + i, c0:c0+w], summed in the fixed order r = 0..world-1
+template <int VEC, int WORLD>
 __global__ void __launch_bounds__(kHaloThreads)
-k_halo_pull_reduce(int world, int me, PeerPtrs peers, int64_t rows, int64_t ld_table, int64_t c0, int width,
+k_halo_pull_reduce(int world_rt, int me, PeerPtrs peers, int64_t rows, int64_t ld_table, int64_t c0, int width,
                    float* __restrict__ out, int64_t ld_out) {
+  const int world = WORLD > 0 ? WORLD : world_rt;
+  constexpr int U = VEC == 4 ? (WORLD == 2 ? 4 : (WORLD > 0 && WORLD <= 4) ? 2 : 1) : 1;   // ~8 peer loads in flight per thread
   const int wv = width / VEC;
   const int64_t total = rows * wv;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if constexpr (VEC == 4 && WORLD > 0) {
+    for (; i + (U - 1) * stride < total; i += U * stride) {
+      float4 v[U][WORLD];
+      int64_t oo[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t j = i + u * stride, row = j / wv;
+        const int col = (int)(j - row * wv) * 4;
+        const int64_t off = (me * rows + row) * ld_table + c0 + col;
+        oo[u] = row * ld_out + c0 + col;
+#pragma unroll
+        for (int r = 0; r < WORLD; ++r) v[u][r] = ld_peer(reinterpret_cast<const float4*>(peers.p[r] + off));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float4 a = v[u][0];
+#pragma unroll
+        for (int r = 1; r < WORLD; ++r) { a.x += v[u][r].x; a.y += v[u][r].y; a.z += v[u][r].z; a.w += v[u][r].w; }
+        *reinterpret_cast<float4*>(out + oo[u]) = a;
+      }
+    }
+  }
+  for (; i < total; i += stride) {
     const int64_t row = i / wv;
     const int col = (int)(i - row * wv) * VEC;
     const int64_t off = (me * rows + row) * ld_table + c0 + col;
     if constexpr (VEC == 4) {
-      float4 v[kMaxWorld];
-#pragma unroll
-      for (int r = 0; r < kMaxWorld; ++r)
-        if (r < world) v[r] = ld_peer(reinterpret_cast<const float4*>(peers.p[r] + off));   // all peers in flight together
-      float4 a = v[0];
-#pragma unroll
-      for (int r = 1; r < kMaxWorld; ++r)
-        if (r < world) { a.x += v[r].x; a.y += v[r].y; a.z += v[r].z; a.w += v[r].w; }      // fixed order: deterministic
+      float4 a = ld_peer(reinterpret_cast<const float4*>(peers.p[0] + off));
+      for (int r = 1; r < world; ++r) {
+        const float4 x = ld_peer(reinterpret_cast<const float4*>(peers.p[r] + off));
+        a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+      }
       *reinterpret_cast<float4*>(out + row * ld_out + c0 + col) = a;
     } else {
-      float a = 0.f;
-      for (int r = 0; r < world; ++r) {
-        float x;
-        asm volatile("ld.global.relaxed.sys.f32 %0, [%1];" : "=f"(x) : "l"(peers.p[r] + off) : "memory");
-        a += x;
-      }
+      float a = ld_peer1(peers.p[0] + off);
+      for (int r = 1; r < world; ++r) a += ld_peer1(peers.p[r] + off);
       out[row * ld_out + c0 + col] = a;
     }
   }
@@ -114,31 +138,37 @@ static bool aligned4(const void* p, int64_t a, int64_t b, int64_t c, int64_t d) 
   return ((uintptr_t)p % 16) == 0 && a % 4 == 0 && b % 4 == 0 && c % 4 == 0 && d % 4 == 0;
 }
 
+static int fill_peers(PeerPtrs& pp, int world, const float* const* ptrs, bool& vec) {
+  for (int r = 0; r < kMaxWorld; ++r) {
+    pp.p[r] = r < world ? ptrs[r] : nullptr;
+    if (r < world) {
+      if (!pp.p[r]) { set_error("halo: null peer pointer for rank %d", r); return -1; }
+      vec = vec && ((uintptr_t)pp.p[r] % 16) == 0;
+    }
+  }
+  return 0;
+}
+
 }  // namespace botgat
 
 using namespace botgat;
 
-extern "C" int botgat_halo_pull(int32_t world, const float* const* peer_shards, int64_t rows_per_rank, int64_t ld_shard,
-                                int64_t col0, int64_t width, float* table, int64_t ld_table, int32_t n_blocks, void* stream) {
-  BG_REQUIRE(world >= 1 && world <= kMaxWorld, "halo_pull: world must be in [1, %d]", kMaxWorld);
-  BG_REQUIRE(peer_shards && table, "halo_pull: null pointer");
-  BG_REQUIRE(rows_per_rank >= 0 && width >= 0 && col0 >= 0 && col0 + width <= ld_shard && col0 + width <= ld_table,
+extern "C" int botgat_halo_pull(int32_t world, int32_t rank, const float* const* peer_tables, int64_t rows_per_rank, int64_t ld,
+                                int64_t col0, int64_t width, int32_t n_blocks, void* stream) {
+  BG_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "halo_pull: world must be in [1, %d], rank in [0, world)", kMaxWorld);
+  BG_REQUIRE(peer_tables, "halo_pull: null pointer");
+  BG_REQUIRE(rows_per_rank >= 0 && width >= 0 && col0 >= 0 && col0 + width <= ld,
              "halo_pull: column range [%lld, +%lld) outside the rows", (long long)col0, (long long)width);
-  if (rows_per_rank == 0 || width == 0) return 0;
+  if (rows_per_rank == 0 || width == 0 || world == 1) return 0;
   BG_REQUIRE(width < (1 << 30), "halo_pull: width too large");
   PeerPtrs pp;
-  bool vec = aligned4(table, ld_shard, ld_table, col0, width);
-  for (int r = 0; r < kMaxWorld; ++r) {
-    pp.p[r] = r < world ? peer_shards[r] : nullptr;
-    if (r < world) {
-      BG_REQUIRE(pp.p[r], "halo_pull: null peer pointer for rank %d", r);
-      vec = vec && ((uintptr_t)pp.p[r] % 16) == 0;
-    }
-  }
-  const int grid = n_blocks > 0 ? n_blocks : 64;
+  bool vec = aligned4(peer_tables[rank], ld, ld, col0, width);
+  if (fill_peers(pp, world, peer_tables, vec)) return -1;
+  float* table = const_cast<float*>(peer_tables[rank]);
+  const int grid = n_blocks > 0 ? n_blocks : 592;
   cudaStream_t st = (cudaStream_t)stream;
-  if (vec) k_halo_pull<4><<<grid, kHaloThreads, 0, st>>>(world, pp, rows_per_rank, ld_shard, col0, (int)width, table, ld_table);
-  else k_halo_pull<1><<<grid, kHaloThreads, 0, st>>>(world, pp, rows_per_rank, ld_shard, col0, (int)width, table, ld_table);
+  if (vec) k_halo_pull<4><<<grid, kHaloThreads, 0, st>>>(world, rank, pp, rows_per_rank, ld, col0, (int)width, table);
+  else k_halo_pull<1><<<grid, kHaloThreads, 0, st>>>(world, rank, pp, rows_per_rank, ld, col0, (int)width, table);
   BG_LAUNCHED(1);
   BG_CHECK(cudaGetLastError());
   return 0;
@@ -155,17 +185,16 @@ extern "C" int botgat_halo_pull_reduce(int32_t world, int32_t rank, const float*
   BG_REQUIRE(width < (1 << 30), "halo_pull_reduce: width too large");
   PeerPtrs pp;
   bool vec = aligned4(out, ld_table, ld_out, col0, width);
-  for (int r = 0; r < kMaxWorld; ++r) {
-    pp.p[r] = r < world ? peer_tables[r] : nullptr;
-    if (r < world) {
-      BG_REQUIRE(pp.p[r], "halo_pull_reduce: null peer pointer for rank %d", r);
-      vec = vec && ((uintptr_t)pp.p[r] % 16) == 0;
-    }
-  }
-  const int grid = n_blocks > 0 ? n_blocks : 64;
+  if (fill_peers(pp, world, peer_tables, vec)) return -1;
+  const int grid = n_blocks > 0 ? n_blocks : 592;
   cudaStream_t st = (cudaStream_t)stream;
-  if (vec) k_halo_pull_reduce<4><<<grid, kHaloThreads, 0, st>>>(world, rank, pp, rows_per_rank, ld_table, col0, (int)width, out, ld_out);
-  else k_halo_pull_reduce<1><<<grid, kHaloThreads, 0, st>>>(world, rank, pp, rows_per_rank, ld_table, col0, (int)width, out, ld_out);
+#define BG_PR(VEC, W) k_halo_pull_reduce<VEC, W><<<grid, kHaloThreads, 0, st>>>(world, rank, pp, rows_per_rank, ld_table, col0, (int)width, out, ld_out)
+  if (!vec) BG_PR(1, 0);
+  else if (world == 2) BG_PR(4, 2);
+  else if (world == 4) BG_PR(4, 4);
+  else if (world == 8) BG_PR(4, 8);
+  else BG_PR(4, 0);
+#undef BG_PR
   BG_LAUNCHED(1);
   BG_CHECK(cudaGetLastError());
   return 0;

@@ -153,10 +153,11 @@ class _SparseHalo(torch.autograd.Function):
 
 class P2PHalo:
     """Buffers of the peer-memory halo exchange of one layer shape (``botgat_halo_pull`` / ``botgat_halo_pull_reduce``,
-    csrc/halo.cu): this rank's shard ``[ft | el]`` and its table of partial gradients live in symmetric memory
-    (``torch.distributed._symmetric_memory``: every rank maps every other rank's buffer, NVLink peer loads), the
-    gathered table and the reduced gradient shard are ordinary local tensors.  Row width ``P`` = H*D + H padded to 32
-    floats (128-byte rows)."""
+    csrc/halo.cu).  Every rank holds the gathered source table ``[ft | el]`` (world * max_own rows of ``P`` = H*D + H
+    floats padded to 128-byte rows) and its table of partial gradients in SYMMETRIC memory
+    (``torch.distributed._symmetric_memory``: every rank maps every other rank's buffers; NVLink peer loads).  Rank r's
+    own slice of ITS table is the authoritative copy of its rows: a producer (the projection GEMM, ``own_ft`` /
+    ``own_el`` below) can write there directly and nothing is staged or repacked."""
 
     def __init__(self, pg, H, D):
         import ctypes as C
@@ -168,42 +169,47 @@ class P2PHalo:
         dev = pg.local.device
         group = pg.group if pg.group is not None else dist.group.WORLD
         rows = pg.max_own
-        self.shard = symm_mem.empty((rows, self.P), dtype=torch.float32, device=dev)
+        self.table = symm_mem.empty((pg.world * rows, self.P), dtype=torch.float32, device=dev)
         self.gtable = symm_mem.empty((pg.world * rows, self.P), dtype=torch.float32, device=dev)
-        self.h_shard = symm_mem.rendezvous(self.shard, group)
+        self.h_table = symm_mem.rendezvous(self.table, group)
         self.h_gtable = symm_mem.rendezvous(self.gtable, group)
-        self.shard.zero_()
+        self.table.zero_()
         self.gtable.zero_()
-        self.shard_ptrs = (C.c_void_p * pg.world)(*[int(p) for p in self.h_shard.buffer_ptrs])
+        self.table_ptrs = (C.c_void_p * pg.world)(*[int(p) for p in self.h_table.buffer_ptrs])
         self.gtable_ptrs = (C.c_void_p * pg.world)(*[int(p) for p in self.h_gtable.buffer_ptrs])
-        self.table = torch.zeros((pg.world * rows, self.P), dtype=torch.float32, device=dev)
-        self.gshard = torch.zeros((rows, self.P), dtype=torch.float32, device=dev)
-        self.stream = torch.cuda.Stream(device=dev)
-        self.blocks = int(os.environ.get("BOTGAT_HALO_BLOCKS", "64"))
+        self.own = self.table[pg.rank * rows: pg.rank * rows + pg.n_own]
+        # where a producer writes this rank's rows so that the layer does not copy them (strided views of the table)
+        self.own_ft = self.own[:, :self.HD].unflatten(1, (H, D))
+        self.own_el = self.own[:, self.HD:self.HD + H]
+        # the exchange must find room BESIDE a gather kernel that fills the GPU: small blocks on a high-priority stream
+        self.stream = torch.cuda.Stream(device=dev, priority=-1)
+        self.blocks = int(os.environ.get("BOTGAT_HALO_BLOCKS", "592"))
         self.world, self.rank, self.rows = pg.world, pg.rank, rows
+        torch.cuda.synchronize(dev)
+        self.h_table.barrier(channel=0)
 
     def pull(self, col0, width):
         from . import _lib
         from .graph import _stream
 
-        _lib.check(_lib.load().botgat_halo_pull(self.world, self.shard_ptrs, self.rows, self.P, col0, width, self.table.data_ptr(),
-                                                self.P, self.blocks, _stream()), "botgat_halo_pull")
+        _lib.check(_lib.load().botgat_halo_pull(self.world, self.rank, self.table_ptrs, self.rows, self.P, col0, width, self.blocks,
+                                                _stream()), "botgat_halo_pull")
 
-    def pull_reduce(self, col0, width):
+    def pull_reduce(self, col0, width, out):
         from . import _lib
         from .graph import _stream
 
         _lib.check(_lib.load().botgat_halo_pull_reduce(self.world, self.rank, self.gtable_ptrs, self.rows, self.P, col0, width,
-                                                       self.gshard.data_ptr(), self.P, self.blocks, _stream()),
+                                                       out.data_ptr(), out.stride(0), self.blocks, _stream()),
                    "botgat_halo_pull_reduce")
 
 
 class _P2PGatFn(torch.autograd.Function):
     """The partitioned layer with the halo exchanged by this repo's own peer-memory kernels instead of NCCL collectives,
-    pipelined per head range on a second stream:
+    pipelined per head range on a second (high-priority) stream:
 
-      forward   copy [ft | el] of the owned rows into the symmetric shard -> inter-GPU barrier ->
-                pull(head range k+1)  ||  gather kernel(head range k)
+      forward   [ft | el] of the owned rows sit in this rank's slice of its symmetric table -> inter-GPU barrier ->
+                pull(head range k+1)  ||  gather kernel(head range k)          (edge staging runs beside the first pull)
       backward  src kernel(head range k+1) writes its partial grad_ft into the symmetric gradient table  ||
                 barrier + pull_reduce(head range k) -> owned rows of grad_ft;  grad_el the same after the last range;
                 the edge phase (grad_ee, grad_er) runs beside the tail of the exchange.
@@ -213,15 +219,17 @@ class _P2PGatFn(torch.autograd.Function):
     def forward(ctx, pg, hx, chunks, ft_own, el_own, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed):
         from . import functional as Fn
 
-        H, D, HD, P = hx.H, hx.D, hx.HD, hx.P
+        H, D, HD = hx.H, hx.D, hx.HD
         n_own = pg.n_own
         graph = pg.local
         main = torch.cuda.current_stream()
-        # everybody has finished reading my shard (the pulls of the previous step ended before their kernels did)
-        hx.h_shard.barrier(channel=0)
-        hx.shard[:n_own, :HD].copy_(ft_own.reshape(n_own, HD))
-        hx.shard[:n_own, HD:HD + H].copy_(el_own.reshape(n_own, H))
-        hx.h_shard.barrier(channel=1)        # every shard is written
+        # every peer has finished pulling my rows of the previous step (its kernels waited for its pulls)
+        hx.h_table.barrier(channel=0)
+        if ft_own.data_ptr() != hx.own_ft.data_ptr():
+            hx.own[:, :HD].copy_(ft_own.reshape(n_own, HD))
+        if el_own.data_ptr() != hx.own_el.data_ptr():
+            hx.own_el.copy_(el_own.reshape(n_own, H))
+        hx.h_table.barrier(channel=1)        # every rank's rows are written
         hx.stream.wait_stream(main)
         events = []
         with torch.cuda.stream(hx.stream):
@@ -232,16 +240,19 @@ class _P2PGatFn(torch.autograd.Function):
                 ev = torch.cuda.Event()
                 ev.record(hx.stream)
                 events.append(ev)
-        state = {"el": None}
+        el_all = torch.empty((hx.table.shape[0], H), dtype=torch.float32, device=hx.table.device)
+
+        def pre_kernel():
+            # runs after the edge staging passes (they overlap the first pull): el arrives with head range 0
+            main.wait_event(events[0])
+            el_all.copy_(hx.table[:, HD:HD + H])
 
         def pre_head(i):
-            main.wait_event(events[i])
+            if i > 0:
+                main.wait_event(events[i])
 
         ee, ld_ee, keep, attn_mul, ld_am = Fn._check_edge_operands(graph, H, ee, keep, attn_mul)
-        # el is needed (contiguous) by the very first launch: wait for chunk 0 (which carries it) up front
-        main.wait_event(events[0])
-        el_all = hx.table[:, HD:HD + H].contiguous()
-        hooks = Fn.Hooks(head_chunks=chunks, pre_head=pre_head)
+        hooks = Fn.Hooks(pre_kernel=pre_kernel, head_chunks=chunks, pre_head=pre_head)
         out, row_max, row_sum, pre, attn_p_used = Fn._forward_core(
             graph, hx.table, H, D, el_all, er, ee, ld_ee, keep, attn_mul, ld_am, src_scale, dst_scale, slope, attn_p, seed,
             hooks, True)
@@ -260,26 +271,26 @@ class _P2PGatFn(torch.autograd.Function):
         n_own = pg.n_own
         main = torch.cuda.current_stream()
         gout = gout.contiguous()
-        # everybody has finished reading my gradient table of the previous step
+        gshard = torch.empty((hx.rows, hx.P), dtype=torch.float32, device=gout.device)
+        gshard.record_stream(hx.stream)
+        # every peer has finished reading my gradient table of the previous step
         hx.h_gtable.barrier(channel=0)
 
         def post_src_head(i, grad_ft, grad_el):
-            ev = torch.cuda.Event()
-            ev.record(main)
             hb, hc = chunks[i]
             last = i == len(chunks) - 1
             if last:
                 hx.gtable[:, HD:HD + H].copy_(grad_el)      # complete only after the last head range
-                ev = torch.cuda.Event()
-                ev.record(main)
+            ev = torch.cuda.Event()
+            ev.record(main)
             with torch.cuda.stream(hx.stream):
                 hx.stream.wait_event(ev)
                 hx.h_gtable.barrier(channel=1 + i)          # every rank has written this column range
-                hx.pull_reduce(hb * D, hc * D)
+                hx.pull_reduce(hb * D, hc * D, gshard)
                 if last:
-                    hx.pull_reduce(HD, H)
+                    hx.pull_reduce(HD, H, gshard)
 
-        hooks = Fn.Hooks(head_chunks=chunks if len(chunks) > 1 else [chunks[0], ], post_src_head=post_src_head)
+        hooks = Fn.Hooks(head_chunks=chunks, post_src_head=post_src_head)
         hooks.force_chunked = True
         need_er = er is not None and ctx.needs_input_grad[5]
         need_ee = ee is not None and ctx.needs_input_grad[6]
@@ -287,8 +298,8 @@ class _P2PGatFn(torch.autograd.Function):
             pg.local, ctx.cfg, None, hooks, hx.table, el_all, er, ee, keep, attn_mul, src_scale, dst_scale, out, row_max, row_sum,
             gout, hx.gtable, need_er, need_ee)
         main.wait_stream(hx.stream)
-        grad_ft_own = hx.gshard[:n_own, :HD].reshape(n_own, H, D).clone()
-        grad_el_own = hx.gshard[:n_own, HD:HD + H].clone()
+        grad_ft_own = gshard[:n_own, :HD].unflatten(1, (H, D))
+        grad_el_own = gshard[:n_own, HD:HD + H]
         return (None, None, None, grad_ft_own, grad_el_own, grad_er, grad_ee, None, None, None, None, None, None, None)
 
 
@@ -408,9 +419,7 @@ class PartitionedGraph:
             H, D = ft_own.shape[1], ft_own.shape[2]
             # the exchange buffers hold the gathered table until the layer's backward has run: layers whose forward /
             # backward overlap in time (a multi-layer model) each need their own ``halo_slot``
-            hx = self._p2p.get((H, D, halo_slot))
-            if hx is None:
-                hx = self._p2p[(H, D, halo_slot)] = P2PHalo(self, H, D)
+            hx = self.halo_buffers(H, D, halo_slot)
             n = max(1, min(H, self.halo_chunks if self.halo_chunks > 0 else (H if hx.table.numel() * 4 >= (1 << 30) else 2)))
             if self.local._info.n_slots_in or self.local._info.n_slots_out:
                 n = 1     # split (heavy) rows need the full head range in one launch
@@ -475,6 +484,14 @@ class PartitionedGraph:
         return gat_fused(self.local, ft_all, el_all, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed,
                          hooks=Hooks(head_chunks=chunks, pre_head=pre_head, post_src_head=post_src_head),
                          edge_order="canonical")
+
+    def halo_buffers(self, H, D, halo_slot=0):
+        """The peer-memory exchange buffers of a (H, D) layer (``exchange = "p2p"``): write this rank's projected rows
+        straight into ``.own_ft`` (n_own, H, D) / ``.own_el`` (n_own, H) and pass those views to ``gat`` — no copy."""
+        hx = self._p2p.get((H, D, halo_slot))
+        if hx is None:
+            hx = self._p2p[(H, D, halo_slot)] = P2PHalo(self, H, D)
+        return hx
 
     def owned_slice(self, full_table):
         """Rows of a replicated (N, ...) table this rank owns."""

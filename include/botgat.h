@@ -315,16 +315,19 @@ int botgat_rows_scatter_add(float* table, int64_t ld, int64_t width, const int64
  * a time, by peer loads from buffers every rank has mapped (CUDA VMM / torch symmetric memory) — so that the transfer
  * of head range k+1 overlaps the gather kernel of head range k and nothing is repacked.  The caller provides the
  * inter-GPU barriers (peers' buffers written before a pull, read before they are overwritten).
- *   world <= 16; peer_* : HOST arrays of `world` DEVICE pointers (entry `r` = rank r's buffer, own rank included).
- *   n_blocks : grid size (0 = 64 blocks of 512 threads); the exchange shares the GPU with the kernel it overlaps.
+ *   world <= 16; peer_tables : HOST array of `world` DEVICE pointers (entry `r` = rank r's buffer, own rank included).
+ *   n_blocks : grid size (0 = 592 blocks of 128 threads: small blocks, so that the exchange finds room beside the gather
+ *   kernel it overlaps — launch it on a higher-priority stream).
  *
- * botgat_halo_pull (forward, the all-gather):
- *   table[r * rows_per_rank + i, col0 : col0 + width] = peer_shards[r][i, col0 : col0 + width]   for r = 0..world-1
+ * Every rank holds a table of world * rows_per_rank rows (row stride ld) with the same layout; rank r's OWN slice
+ * [r * rows_per_rank, (r+1) * rows_per_rank) of ITS table is the authoritative copy of its rows (written there directly).
+ * botgat_halo_pull (forward, the all-gather): into this rank's table (= peer_tables[rank])
+ *   table[r * rows_per_rank + i, col0 : col0 + width] = peer_tables[r][r * rows_per_rank + i, same columns]   for r != rank
  * botgat_halo_pull_reduce (backward, the reduce-scatter; summed in the FIXED order r = 0..world-1, deterministic):
  *   out[i, col0 : col0 + width] = sum_r peer_tables[r][rank * rows_per_rank + i, col0 : col0 + width]
  * ---------------------------------------------------------------------- */
-int botgat_halo_pull(int32_t world, const float* const* peer_shards /* HOST */, int64_t rows_per_rank, int64_t ld_shard,
-                     int64_t col0, int64_t width, float* table, int64_t ld_table, int32_t n_blocks, void* stream);
+int botgat_halo_pull(int32_t world, int32_t rank, const float* const* peer_tables /* HOST */, int64_t rows_per_rank, int64_t ld,
+                     int64_t col0, int64_t width, int32_t n_blocks, void* stream);
 int botgat_halo_pull_reduce(int32_t world, int32_t rank, const float* const* peer_tables /* HOST */, int64_t rows_per_rank,
                             int64_t ld_table, int64_t col0, int64_t width, float* out, int64_t ld_out, int32_t n_blocks,
                             void* stream);

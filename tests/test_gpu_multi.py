@@ -15,25 +15,26 @@ pytestmark = pytest.mark.gpu
 
 def test_halo_kernels_with_local_peers(cuda):
     """botgat_halo_pull / botgat_halo_pull_reduce with every "peer" buffer on this GPU: exact copies / fixed-order sums,
-    column ranges, unaligned widths (scalar path)."""
+    column ranges, unaligned widths (scalar path), every specialised world size."""
     from bot_b200 import _lib
     from bot_b200.graph import _stream
 
     lib = _lib.load()
     torch.manual_seed(0)
-    for world, rows, P, col0, width in ((3, 1000, 96, 0, 96), (4, 777, 512, 80, 160), (2, 50, 40, 3, 7), (8, 1200, 512, 480, 6)):
-        shards = [torch.randn(rows, P, device=cuda) for _ in range(world)]
-        ptrs = (C.c_void_p * world)(*[t.data_ptr() for t in shards])
-        table = torch.full((world * rows, P), -7.0, device=cuda)
-        _lib.check(lib.botgat_halo_pull(world, ptrs, rows, P, col0, width, table.data_ptr(), P, 8, _stream()), "pull")
-        want = torch.full_like(table, -7.0)
-        want[:, col0:col0 + width] = torch.cat(shards, 0)[:, col0:col0 + width]
-        assert torch.equal(table, want)
+    for world, rows, P, col0, width in ((3, 1000, 96, 0, 96), (4, 777, 512, 80, 160), (2, 50, 40, 3, 7), (8, 1200, 512, 480, 6),
+                                        (2, 5000, 128, 32, 64), (8, 900, 64, 0, 64), (5, 300, 64, 16, 32)):
         tables = [torch.randn(world * rows, P, device=cuda) for _ in range(world)]
-        tptrs = (C.c_void_p * world)(*[t.data_ptr() for t in tables])
+        ptrs = (C.c_void_p * world)(*[t.data_ptr() for t in tables])
         for me in (0, world - 1):
-            out = torch.full((rows, P), 5.0, device=cuda)
-            _lib.check(lib.botgat_halo_pull_reduce(world, me, tptrs, rows, P, col0, width, out.data_ptr(), P, 8, _stream()), "reduce")
+            before = tables[me].clone()
+            _lib.check(lib.botgat_halo_pull(world, me, ptrs, rows, P, col0, width, 8, _stream()), "pull")
+            want = before.clone()
+            for r in range(world):
+                if r != me:
+                    want[r * rows:(r + 1) * rows, col0:col0 + width] = tables[r][r * rows:(r + 1) * rows, col0:col0 + width]
+            assert torch.equal(tables[me], want)
+            out = torch.full((rows, P + 8), 5.0, device=cuda)
+            _lib.check(lib.botgat_halo_pull_reduce(world, me, ptrs, rows, P, col0, width, out.data_ptr(), P + 8, 8, _stream()), "reduce")
             acc = tables[0][me * rows:(me + 1) * rows, col0:col0 + width].clone()
             for r in range(1, world):
                 acc += tables[r][me * rows:(me + 1) * rows, col0:col0 + width]      # the same fixed order
@@ -41,7 +42,7 @@ def test_halo_kernels_with_local_peers(cuda):
             want[:, col0:col0 + width] = acc
             assert torch.equal(out, want)
     with pytest.raises(RuntimeError, match="world"):
-        _lib.check(lib.botgat_halo_pull(17, ptrs, 1, 8, 0, 8, table.data_ptr(), 8, 0, _stream()), "pull")
+        _lib.check(lib.botgat_halo_pull(17, 0, ptrs, 1, 8, 0, 8, 0, _stream()), "pull")
 
 
 def _free_port():
@@ -89,6 +90,17 @@ def _worker(rank, world, port, ret):
                               (ee_l.grad, ee.grad.index_select(0, pg.edge_gid.cpu()))):
                 assert rel_err(got, want) <= 1e-4, (exchange, chunks)
             results[(exchange, chunks)] = (out.clone(), ft_o.grad.clone(), el_o.grad.clone())
+            if exchange == "p2p" and chunks == 3:
+                # the producer writes its rows straight into the exchange buffers: no copy inside the layer
+                hx = pg.halo_buffers(6, 16)
+                hx.h_table.barrier(channel=0)
+                with torch.no_grad():
+                    hx.own_ft.copy_(ft_o)
+                    hx.own_el.copy_(el_o)
+                f2, e2 = hx.own_ft.detach().requires_grad_(True), hx.own_el.detach().requires_grad_(True)
+                out2 = pg.gat(f2, e2, er_o, ee_l, keep_l)
+                out2.backward(pg.owned_slice(c["gout"].to(dev)))
+                assert torch.equal(out2, out) and torch.equal(f2.grad, ft_o.grad) and torch.equal(e2.grad, el_o.grad)
         # the peer-memory exchange moves the same numbers whatever the chunking; its fixed-order reduction makes the
         # gradients independent of it bit for bit
         a, b = results[("p2p", 1)], results[("p2p", 6)]
