@@ -185,6 +185,7 @@ class P2PHalo:
         self.stream = torch.cuda.Stream(device=dev, priority=-1)
         self.blocks = int(os.environ.get("BOTGAT_HALO_BLOCKS", "592"))
         self.world, self.rank, self.rows = pg.world, pg.rank, rows
+        self.fwd_pending = self.bwd_pending = False   # a forward / backward ran since the last barrier of the other kind
         torch.cuda.synchronize(dev)
         self.h_table.barrier(channel=0)
 
@@ -223,8 +224,12 @@ class _P2PGatFn(torch.autograd.Function):
         n_own = pg.n_own
         graph = pg.local
         main = torch.cuda.current_stream()
-        # every peer has finished pulling my rows of the previous step (its kernels waited for its pulls)
-        hx.h_table.barrier(channel=0)
+        # Before my rows are overwritten every peer must have finished pulling the previous version.  A peer's pulls
+        # end before its forward kernels do, and the barrier at the start of the BACKWARD is passed only after every
+        # rank's forward: in a training loop (forward, backward, forward, ...) that barrier already orders it.
+        if hx.fwd_pending:
+            hx.h_table.barrier(channel=0)
+        hx.fwd_pending, hx.bwd_pending = True, False
         if ft_own.data_ptr() != hx.own_ft.data_ptr():
             hx.own[:, :HD].copy_(ft_own.reshape(n_own, HD))
         if el_own.data_ptr() != hx.own_el.data_ptr():
@@ -273,8 +278,11 @@ class _P2PGatFn(torch.autograd.Function):
         gout = gout.contiguous()
         gshard = torch.empty((hx.rows, hx.P), dtype=torch.float32, device=gout.device)
         gshard.record_stream(hx.stream)
-        # every peer has finished reading my gradient table of the previous step
-        hx.h_gtable.barrier(channel=0)
+        # Before my gradient table is overwritten every peer must have finished reading the previous one; the barrier of
+        # a forward in between (passed only after every rank's previous backward, exchange included) already orders it.
+        if hx.bwd_pending or not hx.fwd_pending:
+            hx.h_gtable.barrier(channel=0)
+        hx.bwd_pending, hx.fwd_pending = True, False
 
         def post_src_head(i, grad_ft, grad_el):
             hb, hc = chunks[i]
