@@ -382,7 +382,7 @@ def run_ours(args):
 
     # ---------------- device-resident leg (value) ----------------
     n_own = n_dst_l if layer is not None else n_nodes
-    if layer is not None and layer.exchange == "p2p" and layer.plan == "dense":
+    if layer is not None and layer.plan == "dense" and layer.exchange in ("p2p", "auto") and layer._p2p_usable(H, D, 0):
         # the projected rows are produced straight into this rank's slice of the peer-memory exchange table
         hx = layer.halo_buffers(H, D)
         with torch.no_grad():

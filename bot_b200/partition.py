@@ -330,9 +330,11 @@ class PartitionedGraph:
         self.pipeline_heads = os.environ.get("BOTGAT_PIPE_HEADS", "0") == "1"
         # halo exchange of the dense plan: "nccl" = all_gather_into_tensor / reduce_scatter_tensor of whole tables;
         # "p2p" = this repo's peer-memory kernels (csrc/halo.cu), pipelined per head range (needs NVLink peer access)
-        self.exchange = os.environ.get("BOTGAT_EXCHANGE", "nccl")
-        self.halo_chunks = int(os.environ.get("BOTGAT_HALO_CHUNKS", "0"))    # head ranges per exchange; 0 = auto
-        self._p2p = {}
+        # (measured on 8 B200s, profiles/r02_multi_gpu.md: p2p 2.98 vs nccl 3.19 ms/step at the proteins shape).  "auto" =
+        # p2p on CUDA when the symmetric-memory rendezvous succeeds, else nccl.
+        self.exchange = os.environ.get("BOTGAT_EXCHANGE", "auto")
+        self.halo_chunks = int(os.environ.get("BOTGAT_HALO_CHUNKS", "0"))    # head ranges per exchange; 0 = auto (2)
+        self._p2p, self._p2p_failed, self._p2p_error = {}, False, None
         self.world = dist.get_world_size(group) if world is None else world
         self.rank = dist.get_rank(group) if rank is None else rank
         self.n_nodes = n_nodes
@@ -423,12 +425,13 @@ class PartitionedGraph:
             ee, keep, attn_mul = (to_canonical(self.local, t) for t in (ee, keep, attn_mul))
         edge_order = "canonical"
 
-        if self.world > 1 and self.plan == "dense" and self.exchange == "p2p" and ft_own.is_cuda and ft_own.dim() == 3:
+        if self.world > 1 and self.plan == "dense" and self.exchange in ("p2p", "auto") and ft_own.is_cuda and ft_own.dim() == 3 \
+                and isinstance(self.local, Graph) and self._p2p_usable(ft_own.shape[1], ft_own.shape[2], halo_slot):
             H, D = ft_own.shape[1], ft_own.shape[2]
             # the exchange buffers hold the gathered table until the layer's backward has run: layers whose forward /
             # backward overlap in time (a multi-layer model) each need their own ``halo_slot``
             hx = self.halo_buffers(H, D, halo_slot)
-            n = max(1, min(H, self.halo_chunks if self.halo_chunks > 0 else (H if hx.table.numel() * 4 >= (1 << 30) else 2)))
+            n = max(1, min(H, self.halo_chunks if self.halo_chunks > 0 else 2))
             if self.local._info.n_slots_in or self.local._info.n_slots_out:
                 n = 1     # split (heavy) rows need the full head range in one launch
             bounds = [round(i * H / n) for i in range(n + 1)]
@@ -492,6 +495,29 @@ class PartitionedGraph:
         return gat_fused(self.local, ft_all, el_all, er, ee, keep, attn_mul, src_scale, dst_scale, slope, attn_p, seed,
                          hooks=Hooks(head_chunks=chunks, pre_head=pre_head, post_src_head=post_src_head),
                          edge_order="canonical")
+
+    def _p2p_usable(self, H, D, halo_slot):
+        """Create (once) the peer-memory exchange buffers; with ``exchange = "auto"`` a failing symmetric-memory
+        rendezvous (no peer access, an older torch) falls back to the NCCL collectives on EVERY rank."""
+        if self.exchange == "p2p" or (H, D, halo_slot) in self._p2p:
+            return True
+        if self._p2p_failed:
+            return False
+        ok = 1
+        try:
+            self.halo_buffers(H, D, halo_slot)
+        except Exception as ex:  # noqa: BLE001 - any failure means "use NCCL"
+            ok = 0
+            self._p2p_error = repr(ex)
+        flag = torch.tensor([ok], device=self.local.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)     # the ranks must agree
+        if int(flag.item()) == 0:
+            self._p2p_failed = True
+            self._p2p.pop((H, D, halo_slot), None)
+            self.exchange = "nccl"
+            return False
+        self.exchange = "p2p"
+        return True
 
     def halo_buffers(self, H, D, halo_slot=0):
         """The peer-memory exchange buffers of a (H, D) layer (``exchange = "p2p"``): write this rank's projected rows
