@@ -17,10 +17,6 @@
 // Attention weights are recomputed from (el, er, eb, row_max, row_sum); nothing
 // E-sized is saved by the forward.  No atomics: every output element is produced
 // by exactly one warp in a fixed order, so results are run-to-run deterministic.
-#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
-
-#include <cstdlib>
-
 #include "common.cuh"
 #include "params.cuh"
 
@@ -293,293 +289,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB_BWD) gat_bwd_src_
   if (lane == 0) p.grad_el[(int64_t)row * p.H + h] = gel;
 }
 
-// ---------------------------------------------------------------------------
-// src phase, TMA variant: the g'[v] rows of a warp's neighbours are fetched by the tensor-memory accelerator —
-// `cp.async.bulk.tensor.2d ... tile::gather4` (SASS UTMALDG.2D.GATHER4), FOUR table rows per request — into a
-// 3-stage shared-memory ring per warp (16 rows per stage, completion on an mbarrier), and consumed from there with
-// LDS.128.  Against the LDG variant above: no load-address arithmetic, no registers holding rows in flight (the
-// ring holds 32 rows = 10 KB per warp where 48 registers per lane held 16), so the next 32 rows travel while the
-// FFMA chains of the current 16 run.  Same math, same operand conventions; float4 lanes, 8 lanes per neighbour.
-// Requires D % 8 == 0 (128-byte-aligned gather4 destinations), D <= 256 (TMA box), rows 16-byte aligned.
-// ---------------------------------------------------------------------------
-#ifndef BG_TMA_STAGES
-#define BG_TMA_STAGES 3
-#endif
-#ifndef BG_TMA_MINB
-#define BG_TMA_MINB 3
-#endif
-constexpr int kTmaRows = 16, kTmaStages = BG_TMA_STAGES;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-template <int VPL>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_TMA_MINB)
-gat_bwd_src_tma_kernel(const BwdParams p, const __grid_constant__ CUtensorMap tmap) {
-  constexpr int VW = 4, GSH = 3, G = 8, EPS = 4, NS = 4, GSTRIDE = G * VW;
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row_bytes = p.D * 4;
-  unsigned char* ring = smem + (size_t)warp * kTmaStages * kTmaRows * row_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kWarpsPerBlock * kTmaStages * kTmaRows * row_bytes) + warp * kTmaStages;
-  if (lane == 0)
-    for (int s = 0; s < kTmaStages; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + s)));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncwarp();
-
-  const int hl = blockIdx.x / p.blocks_per_slab;
-  const int h = hl + p.h_begin;
-  const int item = (blockIdx.x - hl * p.blocks_per_slab) * kWarpsPerBlock + warp;
-  if (item >= p.n_items) return;
-  const int row = item;
-  const int grp = lane >> GSH, l8 = lane & (G - 1);
-  const int nv = p.D / VW;
-  bool act[VPL];
-  int voff[VPL];  // byte offset of this lane's vector inside a staged row (clamped onto the row for idle slots)
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int v = l8 + i * G;
-    act[i] = v < nv;
-    voff[i] = min(v, nv - 1) * 16;
-  }
-  const int beg = p.indptr[row], end = p.indptr[row + 1];
-  const float slope = p.slope;
-  const float csu = p.cs ? p.cs[row] : 1.f;
-  const float el_u = p.el[(int64_t)row * p.H + h];
-  Vec<VW> fu[VPL], acc[VPL];
-  {
-    const float* f = p.ft + (int64_t)row * p.ld_ft + h * p.D + l8 * VW;
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      if (act[i]) { fu[i].load(f + i * GSTRIDE); fu[i].scale(csu); } else fu[i].zero();
-      acc[i].zero();
-    }
-  }
-  const float4* __restrict__ drec_h = p.drec + (int64_t)h * p.n_dst;
-  const float* __restrict__ eb_h = p.eb ? p.eb + (int64_t)(p.Hb == 1 ? 0 : h) * p.n_edges : nullptr;
-  const float* __restrict__ am_h = p.am ? p.am + (int64_t)h * p.n_edges : nullptr;
-  float* __restrict__ gz_h = p.gz ? p.gz + (int64_t)h * p.n_edges : nullptr;
-  const float* __restrict__ ee_h = p.ee ? p.ee + h : nullptr;
-  const float* __restrict__ amul_h = p.amul_e ? p.amul_e + h : nullptr;
-  const uint8_t* __restrict__ keep = p.keep;
-  float* __restrict__ gze_h = p.gz_e ? p.gz_e + h : nullptr;
-  const int H = p.H;
-  const bool philox = (p.am == nullptr) && (p.amul_e == nullptr) && p.attn_p > 0.f;
-  const bool need_eid = ee_h || amul_h || keep || philox || gze_h;
-  float gel_lane = 0.f;
-  const int col0 = h * p.D;
-
-  auto load_index = [&](int base, int& v, int& k) {
-    const int pos = base + lane;
-    v = k = 0;
-    if (pos < end) {
-      v = __ldg(p.indices + pos);
-      if (need_eid) k = __ldg(p.eid + pos);
-    }
-  };
-  auto load_operands = [&](int base, int v, int k, SrcOps& o) {
-    const int pos = base + lane;
-    o.rec = make_float4(0.f, 0.f, 0.f, 0.f);
-    o.eb = -INFINITY;
-    o.amul = 1.f; o.ame = 1.f; o.amp = 1.f;
-    o.ee = 0.f;
-    o.kp = 1;
-    if (pos < end) {
-      o.rec = __ldg(drec_h + v);
-      o.eb = eb_h ? __ldg(eb_h + pos) : 0.f;
-      if (ee_h) o.ee = __ldg(ee_h + (int64_t)k * H);
-      if (keep) o.kp = __ldg(keep + k);
-      if (am_h) o.amul = __ldg(am_h + pos);
-      if (amul_h) o.ame = __ldg(amul_h + (int64_t)k * H);
-      if (philox) o.amp = philox_dropout_mul(p.seed, (uint32_t)k, (uint32_t)h, p.attn_p, p.inv_keep);
-    }
-  };
-
-  // ---- the ring: halves (16 neighbours) of the 32-neighbour chunks, issued and consumed in the same order ----
-  int sq = 0, sc = 0;          // stage of the next half to issue / to consume
-  uint32_t pc = 0;             // parity bits of the stages on the consumer side
-  auto issue_half = [&](int vtx, int half) {  // vtx: lane-held neighbour ids of the chunk (0 past the row end: a valid row)
-    const uint32_t bar = smem_u32(bars + sq);
-    if (lane == 0)
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kTmaRows * row_bytes) : "memory");
-    const int b = half * 16 + (lane & 3) * 4;
-    const int r0 = __shfl_sync(kFull, vtx, b), r1 = __shfl_sync(kFull, vtx, b + 1);
-    const int r2 = __shfl_sync(kFull, vtx, b + 2), r3 = __shfl_sync(kFull, vtx, b + 3);
-    __syncwarp();
-    if (lane < 4)
-      asm volatile(
-          "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::
-              "r"(smem_u32(ring + ((size_t)sq * kTmaRows + lane * 4) * row_bytes)), "l"(&tmap), "r"(col0), "r"(r0), "r"(r1), "r"(r2), "r"(r3),
-          "r"(bar)
-          : "memory");
-    sq = sq + 1 == kTmaStages ? 0 : sq + 1;
-  };
-
-  int vtx0, vtx1, vtx2 = 0, k0, k1, k2 = 0;
-  load_index(beg, vtx0, k0);
-  load_index(beg + 32, vtx1, k1);
-  SrcOps o0, o1;
-  load_operands(beg, vtx0, k0, o0);
-  // the next half to issue: chunk `qc` relative to the one being consumed (0 = current, 1 = next; the ids of later
-  // chunks are not here yet), half `qh`; `nf` halves are issued and not yet consumed (at most one per stage)
-  int qc = 0, qh = 0, nf = 0;
-  auto fill = [&](int base) {
-#pragma unroll 1
-    while (nf < kTmaStages && qc <= 1) {
-      const int left = end - (base + qc * 32) - qh * 16;   // neighbours from this half on
-      if (left <= 0) { qc = 2; break; }                    // past the row end: nothing more to issue
-      issue_half(qc == 0 ? vtx0 : vtx1, qh);
-      ++nf;
-      if (qh == 0 && left > 16) qh = 1; else { qh = 0; ++qc; }
-    }
-  };
-  fill(beg);
-
-  for (int base = beg; base < end; base += 32) {
-    const int cnt = min(32, end - base);
-    load_index(base + 64, vtx2, k2);
-    load_operands(base + 32, vtx1, k1, o1);
-
-    const float z = el_u + o0.rec.x + o0.logit_term();
-    const float s = leaky_relu(z, slope);
-    const float alpha = (s == -INFINITY) ? 0.f : __expf(s - o0.rec.y) * o0.rec.z;
-    const float dz = z > 0.f ? 1.f : slope;
-    const float am0 = o0.multiplier();
-    const float w_lane = alpha * am0;
-    float d_lane = 0.f;
-
-    const int nh = cnt > 16 ? 2 : 1;
-    for (int half = 0; half < nh; ++half) {
-      fill(base);   // keep every free stage in flight: the next chunk's ids are already here
-      {
-        const uint32_t bar = smem_u32(bars + sc);
-        const uint32_t parity = (pc >> sc) & 1u;
-        uint32_t done = 0;
-        while (!done)
-          asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}"
-                       : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-      }
-      const unsigned char* stage = ring + (size_t)sc * kTmaRows * row_bytes + (size_t)grp * row_bytes;
-      const int e = half * 16;
-      float part[NS];
-#pragma unroll
-      for (int s2 = 0; s2 < NS; s2 += 2) {   // two steps (8 neighbours) of rows in registers at a time
-        Vec<VW> x[2][VPL];
-        float w[2];
-#pragma unroll
-        for (int s_ = 0; s_ < 2; ++s_) {
-          const unsigned char* r = stage + (size_t)(s2 + s_) * EPS * row_bytes;
-          w[s_] = __shfl_sync(kFull, w_lane, e + (s2 + s_) * EPS + grp);
-#pragma unroll
-          for (int i = 0; i < VPL; ++i) x[s_][i].v = *reinterpret_cast<const float4*>(r + voff[i]);
-        }
-#pragma unroll
-        for (int s_ = 0; s_ < 2; ++s_) {
-          float pt = 0.f;
-#pragma unroll
-          for (int i = 0; i < VPL; ++i) {
-            acc[i].fma(w[s_], x[s_][i]);
-            pt = x[s_][i].dot(fu[i], pt);  // fu is 0 on slots this lane does not own
-          }
-          part[s2 + s_] = pt;
-        }
-      }
-      __syncwarp();  // every lane is done with the stage before a later issue refills it
-      --nf;
-      pc ^= 1u << sc;
-      sc = sc + 1 == kTmaStages ? 0 : sc + 1;
-      // packed butterfly over the 8 lanes of a group (see gat_bwd_src_kernel), then one indexed shuffle
-      int k = NS;
-#pragma unroll
-      for (int o = G >> 1; o > 0; o >>= 1) {
-        if (k > 1) {
-          const bool upper = (lane & o) != 0;
-#pragma unroll
-          for (int i = 0; i < NS / 2; ++i) {
-            if (i < k / 2) {
-              const float send = upper ? part[i] : part[i + k / 2];
-              const float keepv = upper ? part[i + k / 2] : part[i];
-              part[i] = keepv + __shfl_xor_sync(kFull, send, o);
-            }
-          }
-          k >>= 1;
-        } else {
-          part[0] += __shfl_xor_sync(kFull, part[0], o);
-        }
-      }
-      const int t = lane - e;
-      const int from = ((t & (EPS - 1)) << GSH) + (t / EPS) * (G / NS);
-      const float got = __shfl_sync(kFull, part[0], from & 31);
-      if (t >= 0 && t < NS * EPS) d_lane = got;
-    }
-    const float gz = alpha * (d_lane * am0 - o0.rec.w) * dz;
-    if (gz_h && lane < cnt) gz_h[base + lane] = gz;
-    if (gze_h && lane < cnt) gze_h[(int64_t)k0 * H] = gz;
-    gel_lane += gz;
-    vtx0 = vtx1; vtx1 = vtx2; k0 = k1; k1 = k2; o0 = o1;
-    --qc;   // the next chunk becomes the current one (every half of the finished chunk had been issued: qc >= 1)
-  }
-
-#pragma unroll
-  for (int o = G; o < 32; o <<= 1) {
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) acc[i].add_shfl_xor(o);
-  }
-  const float gel = warp_sum(gel_lane);
-  if (grp == 0) {
-    float* o = p.grad_ft + (int64_t)row * p.ld_gft + h * p.D + l8 * VW;
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      if (act[i]) {
-        acc[i].scale(csu);
-        acc[i].store(o + i * GSTRIDE);
-      }
-    }
-  }
-  if (lane == 0) p.grad_el[(int64_t)row * p.H + h] = gel;
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-// 1 = not applicable (caller uses the LDG kernel), 0 = launched, < 0 = error
-static int launch_src_tma(const BwdParams& p, const Tiling& t, dim3 grid, cudaStream_t st) {
-  const char* env = getenv("BOTGAT_BWD_TMA");
-  if (!(env && *env == '1')) return 1;
-  if (t.vw != 4 || t.gshift != 3 || p.D % 8 != 0 || p.D > 256 || p.ld_g % 4 != 0 || ((uintptr_t)p.g % 16) != 0 || p.seg_row) return 1;
-  static EncodeTiledFn encode = nullptr;
-  if (!encode) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return 1;
-    encode = (EncodeTiledFn)fn;
-  }
-  CUtensorMap tmap;
-  cuuint64_t gdim[2] = {(cuuint64_t)p.ld_g, (cuuint64_t)p.n_dst};
-  cuuint64_t gstride[1] = {(cuuint64_t)p.ld_g * 4};
-  cuuint32_t box[2] = {(cuuint32_t)p.D, 1};   // tile::gather4: a box of ONE row, four row coordinates per request
-  cuuint32_t estr[2] = {1, 1};
-  if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)p.g, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-    return 1;
-  const size_t bytes = (size_t)kWarpsPerBlock * kTmaStages * kTmaRows * p.D * 4 + kWarpsPerBlock * kTmaStages * 8;
-  dim3 block(kWarpsPerBlock * 32);
-#define BG_T(VPL)                                                                                                     \
-  if (t.vpl == VPL) {                                                                                                 \
-    static bool attr_set = false;                                                                                     \
-    if (!attr_set) {                                                                                                  \
-      if (cudaFuncSetAttribute(gat_bwd_src_tma_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return 1; \
-      attr_set = true;                                                                                                \
-    }                                                                                                                 \
-    gat_bwd_src_tma_kernel<VPL><<<grid, block, bytes, st>>>(p, tmap);                                                 \
-    BG_LAUNCHED(1);                                                                                                   \
-    return 0;                                                                                                         \
-  }
-  BG_T(1) BG_T(2) BG_T(3) BG_T(4) BG_T(5) BG_T(6) BG_T(7) BG_T(8)
-#undef BG_T
-  return 1;
-}
-
 static int launch_src(const BwdParams& p, const Tiling& t, dim3 grid, cudaStream_t st) {
   dim3 block(kWarpsPerBlock * 32);
 #define BG_X(VW, GSH, VPL)                                            \
@@ -676,7 +385,7 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
     const int64_t nblocks = (int64_t)p.blocks_per_slab * p.h_count;
     BG_REQUIRE(nblocks < (1ll << 31), "backward: grid too large");
     int rc = 1;
-    if (!lowdeg && !split) rc = launch_src_tma(p, t, dim3((unsigned)nblocks), st);   // opt-in (BOTGAT_BWD_TMA=1)
+    if (!lowdeg && !split) rc = launch_src_tma(p, t, st);   // 1 = shape not covered by the TMA kernel
     if (rc == 1) rc = lowdeg ? launch_src_lowdeg(p, t, st) : launch_src(p, t, dim3((unsigned)nblocks), st);
     if (rc) return rc;
     if (split) {

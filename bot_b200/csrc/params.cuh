@@ -73,6 +73,9 @@ struct SrcOps {
 bool use_lowdeg_kernels(int64_t n_edges, int64_t n_rows, bool backward);
 int launch_fwd_lowdeg(const FwdParams& p, const Tiling& t, cudaStream_t st);
 int launch_src_lowdeg(const BwdParams& p, const Tiling& t, cudaStream_t st);
+// gat_bwd_tma.cu: the warp-per-row src pass with TMA-staged rows; returns 1 when the shape is not covered (caller
+// falls back to gat_bwd_src_kernel), 0 when launched, < 0 on error
+int launch_src_tma(const BwdParams& p, const Tiling& t, cudaStream_t st);
 int segment_length();
 // floats per scratch slot (rounded to 4 so that float4 stores into a slot stay aligned)
 __host__ __device__ inline int64_t fwd_slot_floats(int H, int D) { return ((int64_t)H * (D + 2) + 3) / 4 * 4; }
