@@ -46,8 +46,11 @@ __device__ __forceinline__ void lds128(uint32_t addr, uint64_t& a, uint64_t& b) 
   asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
 }
 
-// DV = D / 4 (float4 vectors per head row), G = 1 << GSH lanes per neighbour (4 or 8)
-template <int DV, int GSH>
+// DV = D / 4 (float4 vectors per head row), G = 1 << GSH lanes per neighbour (4 or 8).
+// kStaged: the common operand set of a staged backward — the per-edge logit term `eb` in out-CSR order, gz written in
+// out-CSR order, nothing addressed by edge id, no attention-dropout multiplier: every optional-operand test and the
+// edge-id stream fold away at compile time (~50 of the ~420 instructions per 32-edge chunk).
+template <int DV, int GSH, bool kStaged>
 __global__ void __launch_bounds__(32, BG_TMA_MINB) gat_bwd_src_tma_kernel(const BwdParams p, const __grid_constant__ CUtensorMap tmap) {
   constexpr int G = 1 << GSH;           // lanes per neighbour = steps per 32-neighbour chunk
   constexpr int RPS = 32 >> GSH;        // neighbour rows per step (a multiple of the 4 rows of one request)
@@ -60,7 +63,9 @@ __global__ void __launch_bounds__(32, BG_TMA_MINB) gat_bwd_src_tma_kernel(const 
   __shared__ __align__(128) unsigned char ring[kTmaStages * STAGEB];
   __shared__ __align__(8) uint64_t bars[kTmaStages];
   const int lane = threadIdx.x;
-  const uint32_t ring0 = smem_u32(ring), bar0 = smem_u32(bars);
+  uint32_t ring0 = smem_u32(ring), bar0 = smem_u32(bars);
+  // opaque from here on: otherwise every use re-derives the window address (S2UR CgaCtaId + ULEA) on the uniform path
+  asm volatile("" : "+r"(ring0), "+r"(bar0));
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < kTmaStages; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * s));
@@ -95,16 +100,16 @@ __global__ void __launch_bounds__(32, BG_TMA_MINB) gat_bwd_src_tma_kernel(const 
     }
   }
   const float4* __restrict__ drec_h = p.drec + (int64_t)h * p.n_dst;
-  const float* __restrict__ eb_h = p.eb ? p.eb + (int64_t)(p.Hb == 1 ? 0 : h) * p.n_edges : nullptr;
-  const float* __restrict__ am_h = p.am ? p.am + (int64_t)h * p.n_edges : nullptr;
-  float* __restrict__ gz_h = p.gz ? p.gz + (int64_t)h * p.n_edges : nullptr;
-  const float* __restrict__ ee_h = p.ee ? p.ee + h : nullptr;
-  const float* __restrict__ amul_h = p.amul_e ? p.amul_e + h : nullptr;
-  const uint8_t* __restrict__ keep = p.keep;
-  float* __restrict__ gze_h = p.gz_e ? p.gz_e + h : nullptr;
+  const float* __restrict__ eb_h = (kStaged || p.eb) ? p.eb + (int64_t)(p.Hb == 1 ? 0 : h) * p.n_edges : nullptr;
+  const float* __restrict__ am_h = (!kStaged && p.am) ? p.am + (int64_t)h * p.n_edges : nullptr;
+  float* __restrict__ gz_h = (kStaged || p.gz) ? p.gz + (int64_t)h * p.n_edges : nullptr;
+  const float* __restrict__ ee_h = (!kStaged && p.ee) ? p.ee + h : nullptr;
+  const float* __restrict__ amul_h = (!kStaged && p.amul_e) ? p.amul_e + h : nullptr;
+  const uint8_t* __restrict__ keep = kStaged ? nullptr : p.keep;
+  float* __restrict__ gze_h = (!kStaged && p.gz_e) ? p.gz_e + h : nullptr;
   const int H = p.H;
-  const bool philox = (p.am == nullptr) && (p.amul_e == nullptr) && p.attn_p > 0.f;
-  const bool need_eid = ee_h || amul_h || keep || philox || gze_h;
+  const bool philox = !kStaged && (p.am == nullptr) && (p.amul_e == nullptr) && p.attn_p > 0.f;
+  const bool need_eid = !kStaged && (ee_h || amul_h || keep || philox || gze_h);
   float gel_lane = 0.f;
   const int col0 = h * D;
 
@@ -127,6 +132,10 @@ __global__ void __launch_bounds__(32, BG_TMA_MINB) gat_bwd_src_tma_kernel(const 
     o.kp = 1;
     if (pos < end) {
       o.rec = __ldg(drec_h + v);
+      if constexpr (kStaged) {
+        o.eb = __ldg(eb_h + pos);
+        return;
+      }
       o.eb = eb_h ? __ldg(eb_h + pos) : 0.f;
       if (ee_h) o.ee = __ldg(ee_h + (int64_t)k * H);
       if (keep) o.kp = __ldg(keep + k);
@@ -240,8 +249,8 @@ __global__ void __launch_bounds__(32, BG_TMA_MINB) gat_bwd_src_tma_kernel(const 
     const float d_lane = __shfl_sync(kFull, part[0], (lane & (RPS - 1)) * G + lane / RPS);
     // d_lane = <src_scale*ft[u], g'[v]>; softmax + leaky_relu adjoint (App. A.3)
     const float gz = alpha * (d_lane * am0 - o0.rec.w) * dz;
-    if (gz_h && lane < cnt) gz_h[base + lane] = gz;
-    if (gze_h && lane < cnt) gze_h[(int64_t)k0 * H] = gz;
+    if ((kStaged || gz_h) && lane < cnt) gz_h[base + lane] = gz;
+    if (!kStaged && gze_h && lane < cnt) gze_h[(int64_t)k0 * H] = gz;
     gel_lane += gz;
     vtx0 = vtx1; vtx1 = vtx2; vtx2 = vtx3; k0 = k1; k1 = k2; o0 = o1;
   }
@@ -275,7 +284,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 #define BG_TMA_COMBOS(X) X(4, 2) X(8, 2) X(12, 2) X(16, 2) X(20, 2) X(24, 2) X(32, 2) X(10, 3) X(30, 3) X(40, 3)
 
 int launch_src_tma(const BwdParams& p, const Tiling& t, cudaStream_t st) {
-  const char* env = getenv("BOTGAT_BWD_TMA");  // read per call: the tests run both kernels in one process
+  const char* env = getenv("BOTGAT_BWD_TMA");  // read per call: the tests run every variant in one process
   if (env && *env == '0') return 1;
   // float4 access to ft / grad_ft (t.vw == 4), a 16-byte aligned table with rows a multiple of 16 bytes, whole rows
   if (t.vw != 4 || p.D % 8 != 0 || p.ld_g % 4 != 0 || ((uintptr_t)p.g % 16) != 0 || p.seg_row) return 1;
@@ -286,6 +295,7 @@ int launch_src_tma(const BwdParams& p, const Tiling& t, cudaStream_t st) {
   BG_TMA_COMBOS(BG_T)
 #undef BG_T
   if (!have) return 1;
+  const bool staged = p.eb && p.gz && !p.am && !p.ee && !p.amul_e && !p.keep && !p.gz_e && !(p.attn_p > 0.f);
   const int64_t nblocks = (int64_t)p.n_items * p.h_count;
   if (nblocks <= 0 || nblocks >= (1ll << 31)) return 1;
 
@@ -309,7 +319,10 @@ int launch_src_tma(const BwdParams& p, const Tiling& t, cudaStream_t st) {
     return 1;
 #define BG_T(DV, GSH)                                                                   \
   if (dv == DV && gsh == GSH) {                                                         \
-    gat_bwd_src_tma_kernel<DV, GSH><<<dim3((unsigned)nblocks), dim3(32), 0, st>>>(p, tmap); \
+    if (staged)                                                                         \
+      gat_bwd_src_tma_kernel<DV, GSH, true><<<dim3((unsigned)nblocks), dim3(32), 0, st>>>(p, tmap);  \
+    else                                                                                \
+      gat_bwd_src_tma_kernel<DV, GSH, false><<<dim3((unsigned)nblocks), dim3(32), 0, st>>>(p, tmap); \
     BG_LAUNCHED(1);                                                                     \
     return 0;                                                                           \
   }

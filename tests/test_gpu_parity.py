@@ -797,7 +797,7 @@ def test_v1_folded_logits_match_unfolded(cuda, kind):
         assert rel_err(gp1[k], gp2[k]) <= 1e-4, k
 
 
-@pytest.mark.parametrize("tma", ["0", "1"])
+@pytest.mark.parametrize("tma", ["0", "1", "2"])
 @pytest.mark.parametrize("H,D,kw", [
     (6, 80, dict(ee=True, keep_p=0.1)),              # proteins: G = 4, five slots, no idle lanes
     (4, 64, dict(er=False, symm=True, attn_p=0.1)),  # Reddit
@@ -808,7 +808,7 @@ def test_v1_folded_logits_match_unfolded(cuda, kind):
 ])
 def test_src_pass_tma_and_ldg(cuda, monkeypatch, tma, H, D, kw):
     """The warp-per-row backward src pass in both data-movement variants (TMA gather4 ring / LDG registers) on every
-    head width the TMA kernel is instantiated for: rows of 0, 1, < 32, exactly 32/64 and several hundred out-edges."""
+    head width the TMA kernels (1 = a block per row, 2 = persistent warps) are instantiated for: rows of 0, 1, < 32, exactly 32/64 and several hundred out-edges."""
     monkeypatch.setenv("BOTGAT_LOWDEG", "0")
     monkeypatch.setenv("BOTGAT_BWD_TMA", tma)
     n = 260
@@ -825,13 +825,14 @@ def test_src_pass_tma_and_ldg(cuda, monkeypatch, tma, H, D, kw):
     check_case(c, cuda)
 
 
+@pytest.mark.parametrize("tma", ["1", "2"])
 @pytest.mark.parametrize("H", [2, 6])
-def test_src_pass_tma_philox(cuda, monkeypatch, H):
-    """In-kernel attention dropout through the TMA src pass (warp-per-row forced)."""
+def test_src_pass_tma_philox(cuda, monkeypatch, H, tma):
+    """In-kernel attention dropout through the TMA src pass (warp-per-row forced; 2 = the persistent form)."""
     from util import philox_attn_mul
 
     monkeypatch.setenv("BOTGAT_LOWDEG", "0")
-    monkeypatch.setenv("BOTGAT_BWD_TMA", "1")
+    monkeypatch.setenv("BOTGAT_BWD_TMA", tma)
     p, seed = 0.25, 0x0BAD_5EED_1234_5678
     c = make_case(200, 200, 20000, H, 80, ee=True, keep_p=0.1, seed=90 + H)
     c["attn_mul"] = philox_attn_mul(seed, 20000, H, p, eids=graph_ref.canonical_edge_ids(c["src"].numpy(), c["dst"].numpy()))
