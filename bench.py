@@ -290,7 +290,7 @@ def cora_cpu_reference(steps=20, warmup=3):
 
 def common_config(shape, n_nodes, n_edges, world):
     """`config` of the JSON line — identical for both arms (the driver compares them)."""
-    par = "single GPU" if world == 1 else (f"1-D dst-row partition x{world}, halo all-gather + gradient reduce-scatter (NCCL)"
+    par = "single GPU" if world == 1 else (f"1-D dst-row partition x{world}, halo all-gather + gradient reduce-scatter over NVLink (peer-memory pulls or NCCL: `graph.halo_exchange`)"
                                            if shape != "arxiv" else f"{world} independent replicas (too small to shard)")
     return {"workload": workload_name(shape, n_nodes, n_edges), "shape": shape,
             "l2": "inputs_exceed_l2 (no flush between iterations: the per-step working set is >= 20x the 126 MB L2)",

@@ -47,10 +47,12 @@ __device__ __forceinline__ void lds128(uint32_t addr, uint64_t& a, uint64_t& b) 
 }
 
 // DV = D / 4 (float4 vectors per head row), G = 1 << GSH lanes per neighbour (4 or 8).
-// kStaged: the common operand set of a staged backward — the per-edge logit term `eb` in out-CSR order, gz written in
-// out-CSR order, nothing addressed by edge id, no attention-dropout multiplier: every optional-operand test and the
-// edge-id stream fold away at compile time (~50 of the ~420 instructions per 32-edge chunk).
-template <int DV, int GSH, bool kStaged>
+// MODE selects the operand set at compile time, so that the optional-operand tests (and, in mode 1, the edge-id stream)
+// fold away — ~50 of the ~420 instructions per 32-edge chunk:
+//   1  the common staged backward: logit term `eb` and `gz` in out-CSR order, nothing else
+//   2  nothing addressed by edge id: optional `eb` / `am` / `gz` in out-CSR order, optional in-kernel Philox dropout
+//   0  everything (operands by edge id: ee, keep, attn_mul, gz_e)
+template <int DV, int GSH, int MODE>
 __global__ void __launch_bounds__(32, BG_TMA_MINB) gat_bwd_src_tma_kernel(const BwdParams p, const __grid_constant__ CUtensorMap tmap) {
   constexpr int G = 1 << GSH;           // lanes per neighbour = steps per 32-neighbour chunk
   constexpr int RPS = 32 >> GSH;        // neighbour rows per step (a multiple of the 4 rows of one request)
@@ -59,6 +61,7 @@ __global__ void __launch_bounds__(32, BG_TMA_MINB) gat_bwd_src_tma_kernel(const 
   constexpr int STAGEB = 32 * ROWB;
   constexpr int D = DV * 4;
   constexpr bool kRagged = VPL * G != DV;  // the last slot is owned by only some lanes of a group
+  constexpr bool kStaged = MODE == 1, kNoEid = MODE != 0;
   static_assert(RPS >= 4 && G >= 2, "a step must cover whole gather4 requests");
   __shared__ __align__(128) unsigned char ring[kTmaStages * STAGEB];
   __shared__ __align__(8) uint64_t bars[kTmaStages];
@@ -103,12 +106,12 @@ __global__ void __launch_bounds__(32, BG_TMA_MINB) gat_bwd_src_tma_kernel(const 
   const float* __restrict__ eb_h = (kStaged || p.eb) ? p.eb + (int64_t)(p.Hb == 1 ? 0 : h) * p.n_edges : nullptr;
   const float* __restrict__ am_h = (!kStaged && p.am) ? p.am + (int64_t)h * p.n_edges : nullptr;
   float* __restrict__ gz_h = (kStaged || p.gz) ? p.gz + (int64_t)h * p.n_edges : nullptr;
-  const float* __restrict__ ee_h = (!kStaged && p.ee) ? p.ee + h : nullptr;
-  const float* __restrict__ amul_h = (!kStaged && p.amul_e) ? p.amul_e + h : nullptr;
-  const uint8_t* __restrict__ keep = kStaged ? nullptr : p.keep;
-  float* __restrict__ gze_h = (!kStaged && p.gz_e) ? p.gz_e + h : nullptr;
+  const float* __restrict__ ee_h = (!kNoEid && p.ee) ? p.ee + h : nullptr;
+  const float* __restrict__ amul_h = (!kNoEid && p.amul_e) ? p.amul_e + h : nullptr;
+  const uint8_t* __restrict__ keep = kNoEid ? nullptr : p.keep;
+  float* __restrict__ gze_h = (!kNoEid && p.gz_e) ? p.gz_e + h : nullptr;
   const int H = p.H;
-  const bool philox = !kStaged && (p.am == nullptr) && (p.amul_e == nullptr) && p.attn_p > 0.f;
+  const bool philox = !kStaged && (p.am == nullptr) && (kNoEid || p.amul_e == nullptr) && p.attn_p > 0.f;
   const bool need_eid = !kStaged && (ee_h || amul_h || keep || philox || gze_h);
   float gel_lane = 0.f;
   const int col0 = h * D;
@@ -137,10 +140,12 @@ __global__ void __launch_bounds__(32, BG_TMA_MINB) gat_bwd_src_tma_kernel(const 
         return;
       }
       o.eb = eb_h ? __ldg(eb_h + pos) : 0.f;
-      if (ee_h) o.ee = __ldg(ee_h + (int64_t)k * H);
-      if (keep) o.kp = __ldg(keep + k);
       if (am_h) o.amul = __ldg(am_h + pos);
-      if (amul_h) o.ame = __ldg(amul_h + (int64_t)k * H);
+      if constexpr (!kNoEid) {
+        if (ee_h) o.ee = __ldg(ee_h + (int64_t)k * H);
+        if (keep) o.kp = __ldg(keep + k);
+        if (amul_h) o.ame = __ldg(amul_h + (int64_t)k * H);
+      }
       if (philox) o.amp = philox_dropout_mul(p.seed, (uint32_t)k, (uint32_t)h, p.attn_p, p.inv_keep);
     }
   };
@@ -250,7 +255,7 @@ __global__ void __launch_bounds__(32, BG_TMA_MINB) gat_bwd_src_tma_kernel(const 
     // d_lane = <src_scale*ft[u], g'[v]>; softmax + leaky_relu adjoint (App. A.3)
     const float gz = alpha * (d_lane * am0 - o0.rec.w) * dz;
     if ((kStaged || gz_h) && lane < cnt) gz_h[base + lane] = gz;
-    if (!kStaged && gze_h && lane < cnt) gze_h[(int64_t)k0 * H] = gz;
+    if (!kNoEid && gze_h && lane < cnt) gze_h[(int64_t)k0 * H] = gz;
     gel_lane += gz;
     vtx0 = vtx1; vtx1 = vtx2; vtx2 = vtx3; k0 = k1; k1 = k2; o0 = o1;
   }
@@ -295,7 +300,8 @@ int launch_src_tma(const BwdParams& p, const Tiling& t, cudaStream_t st) {
   BG_TMA_COMBOS(BG_T)
 #undef BG_T
   if (!have) return 1;
-  const bool staged = p.eb && p.gz && !p.am && !p.ee && !p.amul_e && !p.keep && !p.gz_e && !(p.attn_p > 0.f);
+  const bool no_eid = !p.ee && !p.amul_e && !p.keep && !p.gz_e;
+  const int mode = !no_eid ? 0 : (p.eb && p.gz && !p.am && !(p.attn_p > 0.f)) ? 1 : 2;
   const int64_t nblocks = (int64_t)p.n_items * p.h_count;
   if (nblocks <= 0 || nblocks >= (1ll << 31)) return 1;
 
@@ -319,10 +325,12 @@ int launch_src_tma(const BwdParams& p, const Tiling& t, cudaStream_t st) {
     return 1;
 #define BG_T(DV, GSH)                                                                   \
   if (dv == DV && gsh == GSH) {                                                         \
-    if (staged)                                                                         \
-      gat_bwd_src_tma_kernel<DV, GSH, true><<<dim3((unsigned)nblocks), dim3(32), 0, st>>>(p, tmap);  \
+    if (mode == 1)                                                                      \
+      gat_bwd_src_tma_kernel<DV, GSH, 1><<<dim3((unsigned)nblocks), dim3(32), 0, st>>>(p, tmap); \
+    else if (mode == 2)                                                                 \
+      gat_bwd_src_tma_kernel<DV, GSH, 2><<<dim3((unsigned)nblocks), dim3(32), 0, st>>>(p, tmap); \
     else                                                                                \
-      gat_bwd_src_tma_kernel<DV, GSH, false><<<dim3((unsigned)nblocks), dim3(32), 0, st>>>(p, tmap); \
+      gat_bwd_src_tma_kernel<DV, GSH, 0><<<dim3((unsigned)nblocks), dim3(32), 0, st>>>(p, tmap); \
     BG_LAUNCHED(1);                                                                     \
     return 0;                                                                           \
   }
