@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BOTGAT_LIB") or os.path.join(_HERE, "libbotgat.so")  # BOTGAT_LIB: developer A/B builds
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_i64p = C.POINTER(C.c_int64)
 c_vp = C.c_void_p
@@ -40,6 +40,9 @@ class FwdArgs(C.Structure):
         ("slope", C.c_float), ("attn_p", C.c_float), ("seed", C.c_uint64),
         ("out", c_vp), ("row_max", c_vp), ("row_sum", c_vp), ("scratch", c_vp),
         ("h_begin", C.c_int32), ("h_count", C.c_int32),
+        ("res", c_vp), ("ld_res", C.c_int64), ("res2", c_vp), ("ld_res2", C.c_int64),
+        ("ep_scale", c_vp), ("ep_shift", c_vp), ("y", c_vp), ("ld_y", C.c_int64),
+        ("ep_relu", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 

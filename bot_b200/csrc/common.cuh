@@ -159,6 +159,9 @@ template <> struct Vec<4> {
     return acc;
   }
   __device__ __forceinline__ void scale(float s) { v.x *= s; v.y *= s; v.z *= s; v.w *= s; }
+  __device__ __forceinline__ void add(const Vec& o) { v.x += o.v.x; v.y += o.v.y; v.z += o.v.z; v.w += o.v.w; }
+  __device__ __forceinline__ void mul(const Vec& o) { v.x *= o.v.x; v.y *= o.v.y; v.z *= o.v.z; v.w *= o.v.w; }
+  __device__ __forceinline__ void relu() { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
   __device__ __forceinline__ void add_shfl_xor(int o) {
     v.x += __shfl_xor_sync(kFull, v.x, o); v.y += __shfl_xor_sync(kFull, v.y, o);
     v.z += __shfl_xor_sync(kFull, v.z, o); v.w += __shfl_xor_sync(kFull, v.w, o);
@@ -179,6 +182,9 @@ template <> struct Vec<2> {
     return acc;
   }
   __device__ __forceinline__ void scale(float s) { v.x *= s; v.y *= s; }
+  __device__ __forceinline__ void add(const Vec& o) { v.x += o.v.x; v.y += o.v.y; }
+  __device__ __forceinline__ void mul(const Vec& o) { v.x *= o.v.x; v.y *= o.v.y; }
+  __device__ __forceinline__ void relu() { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
   __device__ __forceinline__ void add_shfl_xor(int o) {
     v.x += __shfl_xor_sync(kFull, v.x, o); v.y += __shfl_xor_sync(kFull, v.y, o);
   }
@@ -195,6 +201,9 @@ template <> struct Vec<1> {
   __device__ __forceinline__ void fma(float w, const Vec& o) { v = fmaf(w, o.v, v); }
   __device__ __forceinline__ float dot(const Vec& o, float acc) const { return fmaf(v, o.v, acc); }
   __device__ __forceinline__ void scale(float s) { v *= s; }
+  __device__ __forceinline__ void add(const Vec& o) { v += o.v; }
+  __device__ __forceinline__ void mul(const Vec& o) { v *= o.v; }
+  __device__ __forceinline__ void relu() { v = fmaxf(v, 0.f); }
   __device__ __forceinline__ void add_shfl_xor(int o) { v += __shfl_xor_sync(kFull, v, o); }
 };
 
@@ -239,6 +248,20 @@ __host__ __device__ constexpr int steps_in_flight(int vpl) { return BG_NS; }
 #else
 __host__ __device__ constexpr int steps_in_flight(int vpl) { return vpl <= 1 ? 4 : vpl <= 2 ? 3 : vpl <= 4 ? 2 : 1; }
 #endif
+
+// Resident blocks per SM the gather kernels are compiled for (= their register cap: 65536 / (128 threads x blocks)).
+// The narrow instantiations run at the occupancy the sweeps chose (profiles/r01_sweeps.md: forward 6 blocks, backward
+// src pass 4); the wide ones (>= 4 / 5 vector slots per lane: D >= 128 at 8 lanes per neighbour, the arxiv D = 250
+// path) get the registers their accumulators need instead of spilling them (round 1: up to 628 bytes of local loads
+// per thread in gat_fwd_kernel<4,5,8>).  -DBG_MINB / -DBG_MINB_BWD override the narrow figure for sweeps.
+#ifndef BG_MINB
+#define BG_MINB 6
+#endif
+#ifndef BG_MINB_BWD
+#define BG_MINB_BWD 4
+#endif
+__host__ __device__ constexpr int fwd_min_blocks(int vpl) { return vpl <= 3 ? BG_MINB : vpl == 4 ? (BG_MINB < 5 ? BG_MINB : 5) : vpl <= 6 ? 4 : 3; }
+__host__ __device__ constexpr int bwd_min_blocks(int vpl) { return vpl <= 3 ? BG_MINB_BWD : vpl <= 5 ? (BG_MINB_BWD < 3 ? BG_MINB_BWD : 3) : 2; }
 
 // (vector width, log2 lanes per neighbour, slots per lane) combinations the gather kernels are instantiated
 // for; choose_tiling() only returns members of this set.

@@ -59,9 +59,6 @@ gat_bwd_node_kernel(int n_dst, int H, int D, int64_t ld, const float* __restrict
 
 // 4 blocks x 4 warps (16 warps, <= 128 registers) per SM with 4 steps in flight: the src pass carries ft[u] and the
 // dot product besides the accumulators, and prefers registers over occupancy (profiles/r01_sweeps.md)
-#ifndef BG_MINB_BWD
-#define BG_MINB_BWD 4
-#endif
 #ifdef BG_NS_BWD
 __host__ __device__ constexpr int steps_in_flight_bwd(int) { return BG_NS_BWD; }
 #else
@@ -69,7 +66,7 @@ __host__ __device__ constexpr int steps_in_flight_bwd(int vpl) { return vpl <= 3
 #endif
 
 template <int VW, int GSH, int VPL>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB_BWD) gat_bwd_src_kernel(const BwdParams p) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, bwd_min_blocks(VPL)) gat_bwd_src_kernel(const BwdParams p) {
   constexpr int NS = steps_in_flight_bwd(VPL);
   constexpr int G = 1 << GSH;
   constexpr int EPS = 32 >> GSH;
@@ -373,7 +370,7 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
     p.n_rows = (int)g->n_src; p.eb = a->eb_out; p.am = a->am_out; p.omask = t.omask;
     const botgat_graph::SegTable& seg = g->seg_out;
     const bool lowdeg = use_lowdeg_kernels(g->n_edges, g->n_src, true);
-    const bool split = seg.n_items > 0 && !lowdeg;
+    const bool split = seg.n_items > 0;   // both kernel families work on (row | segment) items
     BG_REQUIRE(!split || seg.n_slots == 0 || a->scratch, "backward: this graph has split rows; scratch is required");
     p.seg_row = split ? seg.row : nullptr; p.seg_beg = seg.beg; p.seg_end = seg.end; p.seg_slot = seg.slot;
     p.n_items = split ? seg.n_items : p.n_rows; p.scratch = a->scratch;
@@ -385,7 +382,7 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
     const int64_t nblocks = (int64_t)p.blocks_per_slab * p.h_count;
     BG_REQUIRE(nblocks < (1ll << 31), "backward: grid too large");
     int rc = 1;
-    if (!lowdeg && !split) rc = launch_src_tma(p, t, st);   // 1 = shape not covered by the TMA kernel
+    if (!lowdeg) rc = launch_src_tma(p, t, st);   // 1 = shape not covered by the TMA kernel
     if (rc == 1) rc = lowdeg ? launch_src_lowdeg(p, t, st) : launch_src(p, t, dim3((unsigned)nblocks), st);
     if (rc) return rc;
     if (split) {

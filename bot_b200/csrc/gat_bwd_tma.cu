@@ -77,8 +77,11 @@ __global__ void __launch_bounds__(32, BG_TMA_MINB) gat_bwd_src_tma_kernel(const 
   __syncwarp();
 
   const int hl = blockIdx.x / p.n_items;
-  const int row = blockIdx.x - hl * p.n_items;
+  const int item = blockIdx.x - hl * p.n_items;
   const int h = hl + p.h_begin;
+  // heavy rows are split into segments (segments.cu): a work item is then a segment whose partial result goes to a slot
+  const int row = p.seg_row ? p.seg_row[item] : item;
+  const int slot = p.seg_row ? p.seg_slot[item] : -1;
   const int grp = lane >> GSH, l = lane & (G - 1);
   const bool act_last = l + (VPL - 1) * G < DV;
   // byte offset of this lane's slot 0 inside a stage; the last slot of a lane that does not own it re-reads slot 0
@@ -86,7 +89,8 @@ __global__ void __launch_bounds__(32, BG_TMA_MINB) gat_bwd_src_tma_kernel(const 
   const uint32_t lane_off = (uint32_t)(grp * ROWB + l * 16);
   const uint32_t last_off = lane_off + ((!kRagged || act_last) ? (uint32_t)((VPL - 1) * G * 16) : 0u);
 
-  const int beg = p.indptr[row], end = p.indptr[row + 1];
+  const int beg = p.seg_row ? p.seg_beg[item] : p.indptr[row];
+  const int end = p.seg_row ? p.seg_end[item] : p.indptr[row + 1];
   const float slope = p.slope;
   const float csu = p.cs ? p.cs[row] : 1.f;
   const float el_u = p.el[(int64_t)row * p.H + h];
@@ -272,6 +276,18 @@ __global__ void __launch_bounds__(32, BG_TMA_MINB) gat_bwd_src_tma_kernel(const 
     }
   }
   const float gel = warp_sum(gel_lane);
+  if (slot >= 0) {
+    // segment of a split row: partial grad_el and (unscaled) partial grad_ft go to this segment's scratch slot
+    float* sl = p.scratch + (int64_t)slot * bwd_slot_floats(p.H, D);
+    if (grp == 0) {
+      float4* o = reinterpret_cast<float4*>(sl + (int64_t)h * D) + l;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+        if (i < VPL - 1 || act_last) o[i * G] = r[i];
+    }
+    if (lane == 0) sl[p.H * D + h] = gel;
+    return;
+  }
   if (grp == 0) {
     float4* o = reinterpret_cast<float4*>(p.grad_ft + (int64_t)row * p.ld_gft + h * D) + l;
 #pragma unroll
@@ -291,8 +307,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 int launch_src_tma(const BwdParams& p, const Tiling& t, cudaStream_t st) {
   const char* env = getenv("BOTGAT_BWD_TMA");  // read per call: the tests run every variant in one process
   if (env && *env == '0') return 1;
-  // float4 access to ft / grad_ft (t.vw == 4), a 16-byte aligned table with rows a multiple of 16 bytes, whole rows
-  if (t.vw != 4 || p.D % 8 != 0 || p.ld_g % 4 != 0 || ((uintptr_t)p.g % 16) != 0 || p.seg_row) return 1;
+  // float4 access to ft / grad_ft (t.vw == 4), a 16-byte aligned table with rows a multiple of 16 bytes
+  if (t.vw != 4 || p.D % 8 != 0 || p.ld_g % 4 != 0 || ((uintptr_t)p.g % 16) != 0) return 1;
   const int dv = p.D / 4;
   const int gsh = (dv % 4 == 0 && dv <= 32) ? 2 : 3;
   bool have = false;

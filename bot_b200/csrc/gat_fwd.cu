@@ -27,12 +27,9 @@ namespace botgat {
 
 // 6 blocks x 4 warps (24 warps, <= 80 registers) per SM with 2 steps in flight: the best of the occupancy /
 // loads-in-flight sweep on B200 (profiles/r01_sweeps.md)
-#ifndef BG_MINB
-#define BG_MINB 6
-#endif
 
 template <int VW, int GSH, int VPL>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB) gat_fwd_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, fwd_min_blocks(VPL)) gat_fwd_kernel(const FwdParams p) {
   constexpr int NS = steps_in_flight(VPL);
   constexpr int G = 1 << GSH;     // lanes per neighbour
   constexpr int EPS = 32 >> GSH;  // neighbours per warp step
@@ -209,6 +206,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB) gat_fwd_kernel(c
     for (int i = 0; i < VPL; ++i) {
       if (act[i]) {
         acc[i].scale(scale);
+        p.ep.apply(acc[i], row, (int64_t)h * p.D + c0 + (v0 + i * G) * VW);
         acc[i].store(o + i * G * VW);
       }
     }
@@ -251,7 +249,16 @@ extern "C" int botgat_gat_forward(const botgat_graph* g, const botgat_fwd_args* 
   DeviceGuard guard(g->device);
   cudaStream_t st = (cudaStream_t)stream;
 
-  Tiling t = choose_tiling(a->H, a->D, a->ld_ft, a->ft, a->ld_out, a->out, a->col_parts, g->n_src);
+  const int64_t HDf = (int64_t)a->H * a->D;
+  BG_REQUIRE(!a->res || a->ld_res >= HDf, "forward: ld_res < H*D");
+  BG_REQUIRE(!a->res2 || a->ld_res2 >= HDf, "forward: ld_res2 < H*D");
+  BG_REQUIRE(!a->y || a->ld_y >= HDf, "forward: ld_y < H*D");
+  BG_REQUIRE(a->y || (!a->ep_scale && !a->ep_shift && !a->ep_relu), "forward: the epilogue's scale / shift / relu need y");
+  // the row-local arrays (out, residuals, y, the per-column scale / shift) constrain the vector width together
+  const int64_t ld_o = a->ld_out | (a->res ? a->ld_res : 0) | (a->res2 ? a->ld_res2 : 0) | (a->y ? a->ld_y : 0);
+  const uintptr_t p_o = (uintptr_t)a->out | (uintptr_t)a->res | (uintptr_t)a->res2 | (uintptr_t)a->y | (uintptr_t)a->ep_scale |
+                        (uintptr_t)a->ep_shift;
+  Tiling t = choose_tiling(a->H, a->D, a->ld_ft, a->ft, ld_o, (const void*)p_o, a->col_parts, g->n_src);
   FwdParams p;
   p.indptr = g->in_indptr; p.indices = g->in_indices; p.eid = g->in_eid;
   p.n_rows = (int)g->n_dst; p.n_edges = g->n_edges;
@@ -261,10 +268,12 @@ extern "C" int botgat_gat_forward(const botgat_graph* g, const botgat_fwd_args* 
   p.ee = a->ee; p.keep = a->keep; p.amul_e = a->attn_mul;
   p.slope = a->slope; p.attn_p = a->attn_p; p.inv_keep = 1.f / (1.f - a->attn_p); p.seed = a->seed;
   p.out = a->out; p.row_max = a->row_max; p.row_sum = a->row_sum;
+  p.ep.res = a->res; p.ep.ld_res = a->ld_res; p.ep.res2 = a->res2; p.ep.ld_res2 = a->ld_res2;
+  p.ep.scale = a->ep_scale; p.ep.shift = a->ep_shift; p.ep.relu = a->ep_relu; p.ep.y = a->y; p.ep.ld_y = a->ld_y;
   p.col_parts = t.col_parts; p.part_cols = t.part_cols; p.omask = t.omask;
   const botgat_graph::SegTable& seg = g->seg_in;
   const bool lowdeg = use_lowdeg_kernels(g->n_edges, g->n_dst, false);
-  const bool split = seg.n_items > 0 && !lowdeg;
+  const bool split = seg.n_items > 0;   // both kernel families work on (row | segment) items
   BG_REQUIRE(!split || seg.n_slots == 0 || a->scratch, "forward: this graph has split rows; scratch is required");
   p.seg_row = split ? seg.row : nullptr; p.seg_beg = seg.beg; p.seg_end = seg.end; p.seg_slot = seg.slot;
   p.n_items = split ? seg.n_items : p.n_rows; p.scratch = a->scratch;
@@ -282,7 +291,7 @@ extern "C" int botgat_gat_forward(const botgat_graph* g, const botgat_fwd_args* 
     rc = launch_fwd(p, t, dim3((unsigned)nblocks), st);
   if (rc) return rc;
   if (split) {
-    rc = launch_fwd_combine(seg, a->H, a->D, a->ld_out, a->scratch, a->dst_scale, a->out, a->row_max, a->row_sum, st);
+    rc = launch_fwd_combine(seg, a->H, a->D, a->ld_out, a->scratch, a->dst_scale, a->out, a->row_max, a->row_sum, p.ep, st);
     if (rc) return rc;
   }
   BG_CHECK(cudaGetLastError());

@@ -16,12 +16,6 @@
 
 namespace botgat {
 
-#ifndef BG_MINB
-#define BG_MINB 6
-#endif
-#ifndef BG_MINB_BWD
-#define BG_MINB_BWD 4
-#endif
 
 bool use_lowdeg_kernels(int64_t n_edges, int64_t n_rows, bool backward) {
   // average neighbours per row below which a group owns a row (swept on B200, profiles/r01_sweeps.md): the
@@ -48,7 +42,7 @@ template <int G> __device__ __forceinline__ float group_sum(float v) {
 // forward
 // ---------------------------------------------------------------------------
 template <int VW, int GSH, int VPL>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB) gat_fwd_lowdeg_kernel(const FwdParams p, int warps_per_slab) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, fwd_min_blocks(VPL)) gat_fwd_lowdeg_kernel(const FwdParams p, int warps_per_slab) {
   constexpr int NS = steps_in_flight(VPL);
   constexpr int G = 1 << GSH;     // lanes per row
   constexpr int RPW = 32 >> GSH;  // rows per warp
@@ -58,8 +52,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB) gat_fwd_lowdeg_k
   const int wrow = gw - slab * warps_per_slab;
   if (slab >= p.h_count * p.col_parts) return;
   const int j = lane & (G - 1), gbase = lane & ~(G - 1);
-  const int row = wrow * RPW + (lane >> GSH);
-  const bool valid = row < p.n_rows;
+  // a work item is a CSR row or, for a row that exceeds the segment length (segments.cu), one segment of it whose
+  // partial result goes to a scratch slot: a heavy row of a sparse graph is shared by many groups instead of one
+  const int item = wrow * RPW + (lane >> GSH);
+  const bool valid = item < p.n_items;
+  const int row = (valid && p.seg_row) ? p.seg_row[item] : item;
+  const int slot = (valid && p.seg_row) ? p.seg_slot[item] : -1;
   const int hl = slab / p.col_parts;  // head within this launch's range
   const int h = hl + p.h_begin;
   const int cp = slab - hl * p.col_parts;
@@ -77,7 +75,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB) gat_fwd_lowdeg_k
   }
   const unsigned ldb = (unsigned)(p.ld_ft * 4);
 
-  const int beg = valid ? p.indptr[row] : 0, end = valid ? p.indptr[row + 1] : 0;
+  const int beg = !valid ? 0 : p.seg_row ? p.seg_beg[item] : p.indptr[row];
+  const int end = !valid ? 0 : p.seg_row ? p.seg_end[item] : p.indptr[row + 1];
   const float slope = p.slope;
   const int H = p.H;
   const float er_v = (p.er && valid) ? p.er[(int64_t)row * H + h] : 0.f;
@@ -170,7 +169,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB) gat_fwd_lowdeg_k
   }
 
   const float l = group_sum<G>(l_lane);
-  if (valid) {
+  if (valid && slot >= 0) {
+    // segment of a split row: park (max, sum, unnormalised accumulator) in this segment's scratch slot (k_fwd_combine)
+    float* sl = p.scratch + (int64_t)slot * fwd_slot_floats(H, p.D);
+    float* o = sl + (int64_t)h * p.D + c0 + v0 * VW;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+      if (act[i]) acc[i].store(o + i * G * VW);
+    if (cp == 0 && j == 0) { sl[H * p.D + h * 2] = m; sl[H * p.D + h * 2 + 1] = l; }
+  } else if (valid) {
     float scale = l > 0.f ? 1.f / l : 0.f;
     if (p.ds) scale *= p.ds[row];
     float* o = p.out + (int64_t)row * p.ld_out + h * p.D + c0 + v0 * VW;
@@ -178,6 +185,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB) gat_fwd_lowdeg_k
     for (int i = 0; i < VPL; ++i) {
       if (act[i]) {
         acc[i].scale(scale);
+        p.ep.apply(acc[i], row, (int64_t)h * p.D + c0 + (v0 + i * G) * VW);
         acc[i].store(o + i * G * VW);
       }
     }
@@ -190,7 +198,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB) gat_fwd_lowdeg_k
 
 int launch_fwd_lowdeg(const FwdParams& p, const Tiling& t, cudaStream_t st) {
   const int rpw = 32 >> t.gshift;
-  const int warps_per_slab = (p.n_rows + rpw - 1) / rpw;
+  const int warps_per_slab = (p.n_items + rpw - 1) / rpw;
   const int64_t warps = (int64_t)warps_per_slab * p.h_count * p.col_parts;
   const int64_t nblocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
   if (nblocks >= (1ll << 31)) { set_error("forward: grid too large"); return -1; }
@@ -213,7 +221,7 @@ int launch_fwd_lowdeg(const FwdParams& p, const Tiling& t, cudaStream_t st) {
 __host__ __device__ constexpr int lowdeg_steps_bwd(int vpl) { return vpl <= 3 ? 4 : vpl <= 6 ? 2 : 1; }
 
 template <int VW, int GSH, int VPL>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, BG_MINB_BWD)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, bwd_min_blocks(VPL))
 gat_bwd_src_lowdeg_kernel(const BwdParams p, int warps_per_slab) {
   constexpr int NS = lowdeg_steps_bwd(VPL);
   constexpr int G = 1 << GSH;
@@ -226,8 +234,10 @@ gat_bwd_src_lowdeg_kernel(const BwdParams p, int warps_per_slab) {
   if (hl >= p.h_count) return;
   const int h = hl + p.h_begin;
   const int j = lane & (G - 1), gbase = lane & ~(G - 1);
-  const int row = wrow * RPW + (lane >> GSH);
-  const bool valid = row < p.n_rows;
+  const int item = wrow * RPW + (lane >> GSH);   // a row, or a segment of a split row (see the forward)
+  const bool valid = item < p.n_items;
+  const int row = (valid && p.seg_row) ? p.seg_row[item] : item;
+  const int slot = (valid && p.seg_row) ? p.seg_slot[item] : -1;
   const int v0 = j - (((h * p.D) / VW) & p.omask);
 
   const int nv = p.D / VW;
@@ -241,7 +251,8 @@ gat_bwd_src_lowdeg_kernel(const BwdParams p, int warps_per_slab) {
   }
   const unsigned ldb = (unsigned)(p.ld_g * 4);
 
-  const int beg = valid ? p.indptr[row] : 0, end = valid ? p.indptr[row + 1] : 0;
+  const int beg = !valid ? 0 : p.seg_row ? p.seg_beg[item] : p.indptr[row];
+  const int end = !valid ? 0 : p.seg_row ? p.seg_end[item] : p.indptr[row + 1];
   const float slope = p.slope;
   const int H = p.H;
   const float csu = (p.cs && valid) ? p.cs[row] : 1.f;
@@ -370,7 +381,15 @@ gat_bwd_src_lowdeg_kernel(const BwdParams p, int warps_per_slab) {
   }
 
   const float gel = group_sum<G>(gel_lane);
-  if (valid) {
+  if (valid && slot >= 0) {
+    // segment of a split row: partial grad_el and (unscaled) partial grad_ft go to the segment's slot (k_bwd_combine)
+    float* sl = p.scratch + (int64_t)slot * bwd_slot_floats(H, p.D);
+    float* o = sl + (int64_t)h * p.D + v0 * VW;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+      if (act[i]) acc[i].store(o + i * G * VW);
+    if (j == 0) sl[H * p.D + h] = gel;
+  } else if (valid) {
     float* o = p.grad_ft + (int64_t)row * p.ld_gft + h * p.D + v0 * VW;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
@@ -385,7 +404,7 @@ gat_bwd_src_lowdeg_kernel(const BwdParams p, int warps_per_slab) {
 
 int launch_src_lowdeg(const BwdParams& p, const Tiling& t, cudaStream_t st) {
   const int rpw = 32 >> t.gshift;
-  const int warps_per_slab = (p.n_rows + rpw - 1) / rpw;
+  const int warps_per_slab = (p.n_items + rpw - 1) / rpw;
   const int64_t warps = (int64_t)warps_per_slab * p.h_count;
   const int64_t nblocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
   if (nblocks >= (1ll << 31)) { set_error("backward: grid too large"); return -1; }

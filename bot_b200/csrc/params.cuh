@@ -4,6 +4,33 @@
 
 namespace botgat {
 
+// Fused layer epilogue of the forward (the elementwise tail of a reference layer in inference: residual adds, the
+// eval-mode norm as a per-column scale / shift, ReLU; src/no-sampling/models.py:720-731,
+// src/ogbn-proteins/models.py:159-160,253-260), applied where an output vector is still in registers:
+//   out[v, c] = dst_scale[v] * agg[v, c] + res[v, c] + res2[v, c]       y[v, c] = act(out[v, c] * scale[c] + shift[c])
+struct Epilogue {
+  const float *res, *res2;
+  int64_t ld_res, ld_res2;
+  const float *scale, *shift;  // (H*D) or null (= 1 / 0)
+  int relu;
+  float* y;
+  int64_t ld_y;
+  // `a` holds dst_scale * agg of columns [col, col + VW) of row `row`; on return it holds `out`
+  template <int VW>
+  __device__ __forceinline__ void apply(Vec<VW>& a, int64_t row, int64_t col) const {
+    Vec<VW> t;
+    if (res) { t.load(res + row * ld_res + col); a.add(t); }
+    if (res2) { t.load(res2 + row * ld_res2 + col); a.add(t); }
+    if (y) {
+      Vec<VW> r = a;
+      if (scale) { t.load(scale + col); r.mul(t); }
+      if (shift) { t.load(shift + col); r.add(t); }
+      if (relu) r.relu();
+      r.store(y + row * ld_y + col);
+    }
+  }
+};
+
 struct FwdParams {
   const int32_t* indptr;
   const int32_t* indices;
@@ -19,6 +46,7 @@ struct FwdParams {
   float slope, attn_p, inv_keep;
   uint64_t seed;
   float *out, *row_max, *row_sum;
+  Epilogue ep;
   int col_parts, part_cols, omask;
   int blocks_per_slab;
   int h_begin, h_count;  // head range of this launch
@@ -81,7 +109,7 @@ int segment_length();
 __host__ __device__ inline int64_t fwd_slot_floats(int H, int D) { return ((int64_t)H * (D + 2) + 3) / 4 * 4; }
 __host__ __device__ inline int64_t bwd_slot_floats(int H, int D) { return ((int64_t)H * (D + 1) + 3) / 4 * 4; }
 int launch_fwd_combine(const botgat_graph::SegTable& t, int H, int D, int64_t ld_out, const float* scratch,
-                       const float* ds, float* out, float* row_max, float* row_sum, cudaStream_t st);
+                       const float* ds, float* out, float* row_max, float* row_sum, const Epilogue& ep, cudaStream_t st);
 int launch_bwd_combine(const botgat_graph::SegTable& t, int H, int D, int64_t ld_gft, const float* scratch,
                        const float* cs, float* grad_ft, float* grad_el, cudaStream_t st);
 

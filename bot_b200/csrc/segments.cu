@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256)
 k_fwd_combine(int n_split, int H, int D, int64_t ld_out, const int32_t* __restrict__ split_rows,
               const int32_t* __restrict__ split_first, const float* __restrict__ scratch,
               const float* __restrict__ ds, float* __restrict__ out, float* __restrict__ row_max,
-              float* __restrict__ row_sum) {
+              float* __restrict__ row_sum, const Epilogue ep) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= n_split * H) return;
   const int i = w / H, h = w - i * H;
@@ -135,7 +135,10 @@ k_fwd_combine(int n_split, int H, int D, int64_t ld_out, const int32_t* __restri
       const float m = scratch[s * stride + ml];
       if (m != -INFINITY) a = fmaf(scratch[s * stride + (int64_t)h * D + d], __expf(m - M), a);
     }
-    out[(int64_t)row * ld_out + h * D + d] = a * scale;
+    Vec<1> o;
+    o.v = a * scale;
+    ep.apply(o, row, (int64_t)h * D + d);
+    out[(int64_t)row * ld_out + h * D + d] = o.v;
   }
   if (lane == 0) {
     row_max[(int64_t)row * H + h] = M;
@@ -167,11 +170,11 @@ k_bwd_combine(int n_split, int H, int D, int64_t ld_gft, const int32_t* __restri
 }
 
 int launch_fwd_combine(const botgat_graph::SegTable& t, int H, int D, int64_t ld_out, const float* scratch,
-                       const float* ds, float* out, float* row_max, float* row_sum, cudaStream_t st) {
+                       const float* ds, float* out, float* row_max, float* row_sum, const Epilogue& ep, cudaStream_t st) {
   if (t.n_split == 0) return 0;
   const int64_t warps = (int64_t)t.n_split * H;
   k_fwd_combine<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(t.n_split, H, D, ld_out, t.split_rows, t.split_first,
-                                                           scratch, ds, out, row_max, row_sum);
+                                                           scratch, ds, out, row_max, row_sum, ep);
   BG_LAUNCHED(1);
   BG_CHECK(cudaGetLastError());
   return 0;

@@ -153,10 +153,13 @@ def _check_edge_operands(graph, H, ee, keep, attn_mul):
 
 
 def _forward_core(graph, ft2d, H, D, el, er, ee, ld_ee, keep, attn_mul, ld_am, src_scale, dst_scale, slope, attn_p, seed,
-                  hooks, will_backward):
+                  hooks, will_backward, ep=None):
     """Edge staging + the fused forward kernel.  ``ft2d``: 2-D tensor whose first H*D columns are the projected source
     features (any 16-byte-aligned row stride: a column slice of a wider GEMM output works).  Returns
-    (out (N_d,H,D), row_max, row_sum, prestaged backward operands | None, attn_p actually used)."""
+    (out (N_d,H,D), row_max, row_sum, prestaged backward operands | None, attn_p actually used).
+    ``ep``: fused layer epilogue of an inference forward (``botgat_fwd_args.res`` ...): a dict with optional 2-D
+    ``res`` / ``res2`` (N_d, >= H*D), ``scale`` / ``shift`` (H*D), ``relu``, ``want_y``; the ``y`` tensor is stored
+    back into it."""
     lib = _lib.load()
     h = graph._ensure()
     dev = ft2d.device
@@ -195,6 +198,28 @@ def _forward_core(graph, ft2d, H, D, el, er, ee, ld_ee, keep, attn_mul, ld_am, s
     a.dst_scale = dst_scale.data_ptr() if dst_scale is not None else None
     a.slope, a.attn_p, a.seed = float(slope), float(attn_p if attn_mul is None else 0.0), int(seed)
     a.out, a.row_max, a.row_sum = out.data_ptr(), row_max.data_ptr(), row_sum.data_ptr()
+    if ep is not None:
+        if will_backward:
+            raise RuntimeError("the fused layer epilogue is forward-only (the backward expects the plain aggregate)")
+        for key, ld in (("res", "ld_res"), ("res2", "ld_res2")):
+            t = ep.get(key)
+            if t is not None:
+                if t.dim() != 2 or t.shape[0] < N_d or t.shape[1] < H * D or t.stride(1) != 1 or t.dtype != torch.float32:
+                    raise ValueError(f"epilogue {key} must be a float32 (>= N_dst, >= H*D) matrix with unit column stride")
+                setattr(a, key, t.data_ptr())
+                setattr(a, ld, t.stride(0))
+        if ep.get("want_y", True):
+            y = torch.empty((N_d, H * D), dtype=torch.float32, device=dev)
+            ep["y"] = y
+            a.y, a.ld_y = y.data_ptr(), H * D
+            for key, field in (("scale", "ep_scale"), ("shift", "ep_shift")):
+                t = ep.get(key)
+                if t is not None:
+                    t = ep[key] = _f32c(t, key)
+                    if t.numel() != H * D:
+                        raise ValueError(f"epilogue {key} must have H*D entries")
+                    setattr(a, field, t.data_ptr())
+            a.ep_relu = 1 if ep.get("relu") else 0
     scratch = None
     if graph._info.n_slots_in:  # heavy rows are split over several warps (segments.cu)
         scratch = torch.empty(graph._info.n_slots_in * _r4(H * (D + 2)), dtype=torch.float32, device=dev)
@@ -444,6 +469,98 @@ class GATConvSampledFn(torch.autograd.Function):
                 gx_s = gYs @ ws if need[1] else None
                 gx_d = gYd @ wd if need[2] else None
         return (None, gx_s, gx_d, gw_s, gw_d, gb, grad_ee, None, None, None, None, None, None, None, None, None)
+
+
+class LayerTail:
+    """What a reference model does to a layer's output before the next layer (src/no-sampling/models.py:720-731,
+    src/ogbn-proteins/models.py:253-260): ``h = conv(...) [+ h_last]; h_last = h; h = act(norm(h))`` — handed to the layer
+    so that, in inference (no gradient, eval-mode norm), the fused forward kernel applies it while the output vectors are
+    still in registers instead of four more passes over (N, H*D).
+
+    ``h_last``: (>= N_dst, H*D) or None; ``norm``: ``nn.BatchNorm1d`` in eval mode with running statistics, an
+    ``ElementWiseLinear``-like module (``weight`` / ``bias`` vectors or None) or None; ``relu``: apply ReLU."""
+
+    def __init__(self, h_last=None, norm=None, relu=False):
+        self.h_last, self.norm, self.relu = h_last, norm, relu
+
+    def usable(self):
+        if os.environ.get("BOTGAT_FUSE_TAIL", "1") == "0":   # developer A/B switch (tools/tail_bench.py)
+            return False
+        n = self.norm
+        if isinstance(n, torch.nn.BatchNorm1d):
+            return not n.training and n.running_mean is not None
+        return n is None or (hasattr(n, "weight") and hasattr(n, "bias"))
+
+    def scale_shift(self):
+        n = self.norm
+        if n is None:
+            return None, None
+        if isinstance(n, torch.nn.BatchNorm1d):   # y = (x - mean) / sqrt(var + eps) * gamma + beta
+            scale = torch.rsqrt(n.running_var + n.eps)
+            if n.weight is not None:
+                scale = scale * n.weight
+            shift = -n.running_mean * scale
+            if n.bias is not None:
+                shift = shift + n.bias
+            return scale.detach(), shift.detach()
+        return (None if n.weight is None else n.weight.detach()), (None if n.bias is None else n.bias.detach())
+
+
+def gat_fused_inference(graph, ft, el, er, ee, keep, attn_mul, src_scale, dst_scale, slope, tail, res=None):
+    """Forward of :func:`gat_fused` (operands in canonical edge order) without autograd and with the layer tail fused into
+    the gather kernel's epilogue.  ``res``: the layer's own residual projection (N_dst, H*D) or None.  Returns ``(h, y)``:
+    ``h = rst [+ res] [+ tail.h_last]`` (N_dst, H*D) and ``y = act(norm(h))``."""
+    with torch.no_grad():
+        ft = _f32c(ft, "ft")
+        N_s, H, D = ft.shape
+        N_d = graph.number_of_dst_nodes()
+        el = _f32c(el, "el").view(N_s, H)
+        er = None if er is None else _f32c(er, "er").view(N_d, H)
+        ee, ld_ee, keep, attn_mul, ld_am = _check_edge_operands(graph, H, ee, keep, attn_mul)
+        src_scale, dst_scale = _f32c(src_scale, "src_scale"), _f32c(dst_scale, "dst_scale")
+        scale, shift = tail.scale_shift()
+        h_last = tail.h_last
+        if h_last is not None:
+            h_last = _f32c(h_last, "h_last").view(h_last.shape[0], -1)
+        if res is not None:
+            res = _f32c(res, "res").view(res.shape[0], -1)
+        ep = {"res": res, "res2": h_last, "scale": scale, "shift": shift, "relu": tail.relu, "want_y": True}
+        with torch.cuda.device(ft.device):
+            out, _, _, _, _ = _forward_core(graph, ft.view(N_s, H * D), H, D, el, er, ee, ld_ee, keep, attn_mul, ld_am, src_scale,
+                                            dst_scale, slope, 0.0, 0, None, False, ep=ep)
+        return out.view(N_d, H * D), ep["y"]
+
+
+def gat_conv_inference(graph, x_src, x_dst, w_src, w_dst, b_dst, ee, keep, attn_mul, dst_scale, H, D, slope, tail,
+                       src_scale=None):
+    """Forward of :class:`GATConvSampledFn` without autograd and with the layer tail fused into the gather kernel's
+    epilogue.  Returns ``(h, y)``: ``h = rst + dst_fc(x_dst) [+ tail.h_last]`` (N_dst, H*D) — the next layer's ``h_last``
+    — and ``y = act(norm(h))``."""
+    with torch.no_grad():
+        x_src, x_dst = _f32c(x_src, "feat_src"), _f32c(x_dst, "feat_dst")
+        N_s, N_d, HD = graph.number_of_src_nodes(), graph.number_of_dst_nodes(), H * D
+        if x_src.shape[0] != N_s or x_dst.shape[0] != N_d:
+            raise ValueError("feat_src / feat_dst rows do not match the graph")
+        has_er = w_dst.shape[0] == HD + H
+        P = (HD + H + 31) // 32 * 32
+        ws, wd = _pad_rows(w_src, P), _pad_rows(w_dst, P)
+        bd = torch.cat([b_dst, b_dst.new_zeros(P - HD)])
+        ee, ld_ee, keep, attn_mul, ld_am = _check_edge_operands(graph, H, ee, keep, attn_mul)
+        dst_scale, src_scale = _f32c(dst_scale, "dst_scale"), _f32c(src_scale, "src_scale")
+        scale, shift = tail.scale_shift()
+        h_last = tail.h_last
+        if h_last is not None:
+            h_last = _f32c(h_last, "h_last").view(h_last.shape[0], -1)
+        ep = {"res2": h_last, "scale": scale, "shift": shift, "relu": tail.relu, "want_y": True}
+        with torch.cuda.device(x_src.device):
+            Ys = x_src @ ws.t()
+            Yd = torch.addmm(bd, x_dst, wd.t())
+            ep["res"] = Yd                                                    # models.py:159-160, read in place
+            el = Ys[:, HD:HD + H].contiguous() if src_scale is None else Ys[:, HD:HD + H] * src_scale.unsqueeze(-1)
+            er = Yd[:, HD:HD + H].contiguous() if has_er else None
+            out, _, _, _, _ = _forward_core(graph, Ys, H, D, el, er, ee, ld_ee, keep, attn_mul, ld_am, src_scale, dst_scale,
+                                            slope, 0.0, 0, None, False, ep=ep)
+        return out.view(N_d, HD), ep["y"]
 
 
 class EdgeLogitProj(torch.autograd.Function):

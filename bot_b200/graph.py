@@ -47,8 +47,35 @@ class EdgeFrame(dict):
         super().__init__()
         self._graph = graph
         self._canon = {}
+        self._lazy = {}     # key -> tensor given in canonical order whose edge-id view has not been asked for
+
+    def put_canonical(self, key, t):
+        """Assign ``key`` from a tensor that is ALREADY in canonical order (static features kept canonically on the host
+        and fed every step, ``bot_b200.HostFeed``): no permutation pass; the edge-id-order view ``self[key]`` is
+        materialised only if somebody reads it."""
+        if dict.__contains__(self, key):
+            dict.__delitem__(self, key)
+        self._canon.pop(key, None)
+        self._lazy[key] = t
+
+    def __setitem__(self, key, t):
+        self._lazy.pop(key, None)
+        dict.__setitem__(self, key, t)
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self._lazy
+
+    def __getitem__(self, key):
+        if not dict.__contains__(self, key) and key in self._lazy:
+            t = self._lazy[key]
+            inv = self._graph.canonical_edge_ids() if t.is_cuda else None
+            dict.__setitem__(self, key, t if inv is None else t.index_select(0, inv))
+            self._canon[key] = (dict.__getitem__(self, key), t)
+        return dict.__getitem__(self, key)
 
     def canonical(self, key):
+        if key in self._lazy:
+            return self._lazy[key]
         t = self[key]
         hit = self._canon.get(key)
         if hit is None or hit[0] is not t:

@@ -15,7 +15,9 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .functional import gat_fused, to_canonical
+import torch.nn.functional as F
+
+from .functional import LayerTail, gat_fused, to_canonical
 
 
 edge_drop_mode = "select"   # "randperm": torch.randperm exactly as the reference calls it (replays its generator)
@@ -165,7 +167,9 @@ class GATConv(nn.Module):
     def set_allow_zero_in_degree(self, set_value):
         self._allow_zero_in_degree = set_value
 
-    def forward(self, graph, feat):
+    def forward(self, graph, feat, tail=None):
+        # ``tail`` (functional.LayerTail, an extension of the reference signature): the model's elementwise layer tail,
+        # fused into the forward kernel in inference; the layer then returns (h, act(norm(h))), both (N, H*D)
         H, D = self._num_heads, self._out_feats
         with graph.local_scope():
             if not self._allow_zero_in_degree and graph.has_zero_in_degree:  # models.py:477-479
@@ -174,7 +178,7 @@ class GATConv(nn.Module):
             fold = (self.fold_logits and not isinstance(feat, tuple) and hasattr(self, "fc") and self.res_fc is not None
                     and feat.is_cuda and feat.dim() == 2 and self._activation is None)
             if fold:
-                return self._forward_folded(graph, feat, n_dst)
+                return self._forward_folded(graph, feat, n_dst, tail)
             if isinstance(feat, tuple):                                      # models.py:481-488
                 h_src, h_dst = self.feat_drop(feat[0]), self.feat_drop(feat[1])
                 if not hasattr(self, "fc_src"):
@@ -202,6 +206,12 @@ class GATConv(nn.Module):
             if self.attn_r is not None:
                 er = torch.einsum("nhd,hd->nh", ft_dst, self.attn_r[0])       # models.py:521
 
+            if (tail is not None and tail.usable() and not torch.is_grad_enabled() and not self.training
+                    and self._activation is None and ft.is_cuda):
+                from .functional import gat_fused_inference
+                res = self.res_fc(h_dst) if self.res_fc is not None else None   # models.py:557-560
+                return gat_fused_inference(graph, ft, el, er, None, None, None, src_scale, dst_scale, self._negative_slope,
+                                           tail, res)
             keep, attn_mul, attn_p, seed = self._draw(graph, graph.number_of_edges(), H, ft.device)   # models.py:528-537
             rst = gat_fused(graph, ft, el, er, None, keep, attn_mul, src_scale, dst_scale,
                             self._negative_slope, attn_p, seed, edge_order="canonical")   # models.py:523-555
@@ -229,7 +239,7 @@ class GATConv(nn.Module):
             keep, attn_mul = to_canonical(graph, keep), to_canonical(graph, attn_mul)
         return keep, attn_mul, attn_p, seed
 
-    def _forward_folded(self, graph, feat, n_dst):
+    def _forward_folded(self, graph, feat, n_dst, tail=None):
         """models.py:490-560 with the logits folded into the projections: ONE wide GEMM per side,
         ``[ft | el] = h_src @ [W ; W_el]^T`` and ``[res | er] = h_dst @ [W_res ; W_er]^T``, read in place by the kernels."""
         from .functional import GATConvSampledFn
@@ -247,6 +257,10 @@ class GATConv(nn.Module):
             src_scale, dst_scale = graph.deg_scale("out", -0.5), graph.deg_scale("in", 0.5)
         keep, attn_mul, attn_p, seed = self._draw(graph, graph.number_of_edges(), H, feat.device)
         zero_bias = torch.zeros(H * D, dtype=feat.dtype, device=feat.device)   # res_fc has no bias (models.py:453)
+        if tail is not None and tail.usable() and not torch.is_grad_enabled() and not self.training:
+            from .functional import gat_conv_inference
+            return gat_conv_inference(graph, h_src, h_dst, w_src, w_dst, zero_bias, None, None, None, dst_scale, H, D,
+                                      self._negative_slope, tail, src_scale)
         return GATConvSampledFn.apply(graph, h_src, h_dst, w_src, w_dst, zero_bias, None, keep, attn_mul, dst_scale, H, D,
                                       self._negative_slope, attn_p, seed, src_scale)
 
@@ -292,7 +306,16 @@ class GAT(nn.Module):
         h = self.input_drop(feat)
         h_last = None
         for i in range(self.n_layers):
-            h = self.convs[i](graph, h)
+            tail = None
+            if (i < self.n_layers - 1 and not torch.is_grad_enabled() and not self.training
+                    and self.activation in (F.relu, torch.relu)):
+                # inference: `h += h_last`, the eval-mode norm / bias and ReLU (models.py:720-731) ride in the kernel epilogue
+                tail = LayerTail(h_last if self.residual else None, self.norms[i] if self.norms else self.biases[i], relu=True)
+            h = self.convs[i](graph, h, tail=tail) if tail is not None else self.convs[i](graph, h)
+            if isinstance(h, tuple):
+                hn, h = h
+                h_last = hn.view(hn.shape[0], self.convs[i]._num_heads, -1)   # dropout is the identity in eval mode
+                continue
             if i < self.n_layers - 1:
                 if self.residual and h_last is not None:
                     h = h + h_last

@@ -19,7 +19,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .functional import Deferred, EdgeEmbedding, GATConvSampledFn, edge_logits, gat_fused, to_canonical
+from .functional import (Deferred, EdgeEmbedding, GATConvSampledFn, LayerTail, edge_logits, gat_conv_inference, gat_fused,
+                         to_canonical)
 from .no_sampling import KeptEdges, draw_attn_mul, draw_edge_keep
 
 
@@ -73,7 +74,9 @@ class GATConv(nn.Module):
     def set_allow_zero_in_degree(self, set_value):
         self._allow_zero_in_degree = set_value
 
-    def forward(self, graph, feat_src, feat_edge=None):
+    def forward(self, graph, feat_src, feat_edge=None, tail=None):
+        # ``tail`` (functional.LayerTail, an extension of the reference signature): the model's elementwise layer tail,
+        # fused into the forward kernel in inference; the layer then returns (h, act(norm(h))) instead of rst
         H, D = self._n_heads, self._out_feats
         with graph.local_scope():
             if not self._allow_zero_in_degree and graph.has_zero_in_degree:   # models.py:89-91
@@ -131,6 +134,10 @@ class GATConv(nn.Module):
                 w_src = torch.cat([self.src_fc.weight, self.attn_src_fc.weight], 0)
                 w_dst = self.dst_fc.weight if self.attn_dst_fc is None else \
                     torch.cat([self.dst_fc.weight, self.attn_dst_fc.weight], 0)
+                if (tail is not None and tail.usable() and not torch.is_grad_enabled() and not self.training
+                        and self.activation is None):
+                    return gat_conv_inference(graph, feat_src, feat_dst, w_src, w_dst, self.dst_fc.bias, ee, None, None,
+                                              dst_scale, H, D, self._negative_slope, tail)
                 rst = GATConvSampledFn.apply(graph, feat_src, feat_dst, w_src, w_dst, self.dst_fc.bias, ee, keep, attn_mul,
                                              dst_scale, H, D, self._negative_slope, attn_p, seed)
             else:
@@ -167,7 +174,15 @@ class _SampledGAT(nn.Module):
                 # relu(edge_encoder[i](efeat)) (models.py:245-247), left to the layer to fuse with attn_edge_fc
                 # static edge features are kept in the graph's canonical order (permuted once, EdgeFrame.canonical)
                 efeat_emb = EdgeEmbedding(subgraphs[i].edata.canonical("feat"), self.edge_encoder[i], canonical=True)
-            h = self.convs[i](subgraphs[i], h, efeat_emb).flatten(1, -1)
+            # inference: residual + eval-mode BatchNorm + ReLU (models.py:253-260) ride in the gather kernel's epilogue
+            tail = None
+            if not torch.is_grad_enabled() and not self.training and self.activation in (F.relu, torch.relu):
+                tail = LayerTail(h_last if (always_residual or self.residual) else None, self.norms[i], relu=True)
+            h = self.convs[i](subgraphs[i], h, efeat_emb, tail=tail)
+            if isinstance(h, tuple):
+                h_last, h = h            # dropout is the identity in eval mode
+                continue
+            h = h.flatten(1, -1)
             if h_last is not None and (always_residual or self.residual):
                 h = h + h_last[: h.shape[0], :]
             h_last = h

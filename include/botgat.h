@@ -31,7 +31,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define BOTGAT_ABI_VERSION 3
+#define BOTGAT_ABI_VERSION 4
 
 typedef struct botgat_graph botgat_graph;
 
@@ -235,6 +235,24 @@ typedef struct {
    * arguments keep their full-H meaning.  Lets a caller overlap per-head transfers with per-head launches (the
    * kernels work head-major anyway).  Graphs with split rows (n_slots_in > 0) need the full range. */
   int32_t h_begin, h_count;
+  /* Fused layer epilogue (ABI v4; all NULL / 0 = off).  The elementwise tail of a reference layer where it needs no
+   * batch statistics and no gradient, i.e. inference: the residual adds `rst + dst_fc(feat_dst)`
+   * (src/ogbn-proteins/models.py:159-160) and `h += h_last` (:253-254, src/no-sampling/models.py:722-723), the
+   * eval-mode norm / bias as a per-column scale and shift (:257, no-sampling :727) and ReLU (:258 / :728), applied
+   * while an output vector is still in registers instead of as four more passes over (n_dst, H*D):
+   *   out[v,c] = dst_scale[v] * agg[v,c] + res[v,c] + res2[v,c]      y[v,c] = act(out[v,c] * ep_scale[c] + ep_shift[c])
+   * `out` then carries the residual sum (the next layer's h_last).  The backward expects the plain aggregate in
+   * `out`: training keeps these fields NULL. */
+  const float* res;       /* (n_dst, ld_res) or NULL */
+  int64_t ld_res;
+  const float* res2;      /* (n_dst, ld_res2) or NULL */
+  int64_t ld_res2;
+  const float* ep_scale;  /* (H*D) or NULL = 1; needs y */
+  const float* ep_shift;  /* (H*D) or NULL = 0; needs y */
+  float* y;               /* (n_dst, ld_y) or NULL */
+  int64_t ld_y;
+  int32_t ep_relu;        /* 1: y = max(., 0); needs y */
+  int32_t reserved_;
 } botgat_fwd_args;
 int botgat_gat_forward(const botgat_graph* g, const botgat_fwd_args* a /* HOST */, void* stream);
 

@@ -198,11 +198,13 @@ def test_both_kernel_families(cuda, monkeypatch, name, lowdeg):
     check_case(c, cuda)
 
 
+@pytest.mark.parametrize("lowdeg", ["0", "1000000"])
 @pytest.mark.parametrize("seg", ["32", "64", "100"])
-def test_row_splitting(cuda, monkeypatch, seg):
-    """Heavy rows split into segments (segment length forced small): same results, still deterministic."""
+def test_row_splitting(cuda, monkeypatch, seg, lowdeg):
+    """Heavy rows split into segments (segment length forced small), in the warp-per-row kernels (LDG and TMA src pass)
+    and in the group-per-row family: same results, still deterministic."""
     monkeypatch.setenv("BOTGAT_SEG", seg)
-    monkeypatch.setenv("BOTGAT_LOWDEG", "0")
+    monkeypatch.setenv("BOTGAT_LOWDEG", lowdeg)
     c = make_case(600, 600, 60000, 3, 40, ee=True, keep_p=0.1, power_law=1.2, symm=True, seed=31)
     errs = check_case(c, cuda)
     o1, g1, g = engine_run(c, cuda)
@@ -211,10 +213,11 @@ def test_row_splitting(cuda, monkeypatch, seg):
     assert torch.equal(o1, o2) and all(torch.equal(g1[k], g2[k]) for k in g1)
 
 
-def test_row_splitting_all_dropped_segment(cuda, monkeypatch):
+@pytest.mark.parametrize("lowdeg", ["0", "1000000"])
+def test_row_splitting_all_dropped_segment(cuda, monkeypatch, lowdeg):
     """A whole segment of a split row dropped by edge-drop (max = -inf in that slot)."""
     monkeypatch.setenv("BOTGAT_SEG", "32")
-    monkeypatch.setenv("BOTGAT_LOWDEG", "0")
+    monkeypatch.setenv("BOTGAT_LOWDEG", lowdeg)
     c = make_case(100, 100, 3000, 2, 16, ee=True, power_law=1.5, seed=32)
     # drop the first 40 in-edges (edge-id order = CSR order inside a row) of the heaviest row
     keep = torch.ones(3000, dtype=torch.bool)
@@ -841,3 +844,74 @@ def test_src_pass_tma_philox(cuda, monkeypatch, H, tma):
     assert rel_err(out, ref_out) <= FWD_TOL
     for k in ("ft", "el", "er", "ee"):
         assert rel_err(g[k], ref_g[k]) <= 1e-4, k
+
+
+@pytest.mark.parametrize("family", ["warp", "group", "split"])
+@pytest.mark.parametrize("model_kind", ["proteins", "products_res", "products_nores", "v1_bn", "v1_bias", "v1_bn_linear"])
+def test_fused_layer_tail_inference(cuda, monkeypatch, family, model_kind):
+    """Inference with the layer tail (residual adds, eval-mode BatchNorm / bias, ReLU) fused into the forward kernel's
+    epilogue — in the warp-per-row kernel, the group-per-row kernel and the split-row combine — against the same model run
+    op by op (gradients enabled selects the unfused path)."""
+    import torch.nn.functional as F
+
+    import bot_b200
+    from bot_b200 import functional
+    from bot_b200.no_sampling import GAT as V1GAT
+    from bot_b200.ogbn_products import GAT as ProductsGAT
+    from bot_b200.ogbn_proteins import GAT as ProteinsGAT
+
+    monkeypatch.setenv("BOTGAT_LOWDEG", "1000000" if family == "group" else "0")
+    if family == "split":
+        monkeypatch.setenv("BOTGAT_SEG", "32")
+    torch.manual_seed(5)
+    n, e = 500, 30000
+    c = make_case(n, n, e, 1, 8, power_law=0.8 if family == "split" else 0.0, self_loops=True, seed=77)
+    g = bot_b200.Graph(c["src"].to(cuda), c["dst"].to(cuda), n)
+    E = g.number_of_edges()
+    if model_kind == "proteins":
+        model = ProteinsGAT(8, 8, 5, 3, 3, 16, 16, F.relu, 0.1, 0.1, 0.0, 0.1)
+        g.srcdata["feat"] = torch.randn(n, 8, device=cuda)
+        g.edata["feat"] = torch.rand(E, 8, device=cuda)
+        call = lambda m: m(g)
+    elif model_kind.startswith("products"):
+        model = ProductsGAT(12, 0, 5, 3, 2, 20, 0, F.relu, 0.1, 0.1, 0.0, 0.1, residual=model_kind == "products_res")
+        g.srcdata["feat"] = torch.randn(n, 12, device=cuda)
+        call = lambda m: m(g)
+    else:
+        model = V1GAT(12, 0, 5, 16, 3, 2, F.relu, norm="none" if model_kind == "v1_bias" else "batch", dropout=0.1,
+                      use_symmetric_norm=True, residual=True, linear=model_kind == "v1_bn_linear",
+                      non_interactive_attn=model_kind == "v1_bn_linear")
+        x = torch.randn(n, 12, device=cuda)
+        call = lambda m: m(g, x)
+    model = model.to(cuda)
+    for m in model.modules():   # non-trivial running statistics / biases
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.running_mean.normal_(); m.running_var.uniform_(0.5, 2.0); m.weight.data.normal_(1.0, 0.2); m.bias.data.normal_()
+    for name, p_ in model.named_parameters():
+        if "biases" in name:
+            p_.data.normal_()
+    model.eval()
+    from bot_b200 import sampled
+    calls = []
+    real = functional.gat_conv_inference
+
+    def counted(*a, **k):
+        calls.append(1)
+        return real(*a, **k)
+
+    real2 = functional.gat_fused_inference
+
+    def counted2(*a, **k):
+        calls.append(1)
+        return real2(*a, **k)
+
+    monkeypatch.setattr(functional, "gat_conv_inference", counted)
+    monkeypatch.setattr(functional, "gat_fused_inference", counted2)
+    monkeypatch.setattr(sampled, "gat_conv_inference", counted)
+    with torch.no_grad():
+        y_fused = call(model)
+    n_fused = len(calls)
+    y_plain = call(model).detach()    # gradients enabled: the op-by-op path
+    assert n_fused >= 2 and len(calls) == n_fused, "the fused tail must run in inference and only there"
+    assert y_fused.shape == y_plain.shape
+    assert rel_err(y_fused, y_plain) <= 2e-6
