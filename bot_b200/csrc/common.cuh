@@ -260,7 +260,10 @@ __host__ __device__ constexpr int steps_in_flight(int vpl) { return vpl <= 1 ? 4
 #ifndef BG_MINB_BWD
 #define BG_MINB_BWD 4
 #endif
-__host__ __device__ constexpr int fwd_min_blocks(int vpl) { return vpl <= 3 ? BG_MINB : vpl == 4 ? (BG_MINB < 5 ? BG_MINB : 5) : vpl <= 6 ? 4 : 3; }
+#ifndef BG_MINB4
+#define BG_MINB4 5
+#endif
+__host__ __device__ constexpr int fwd_min_blocks(int vpl) { return vpl <= 3 ? BG_MINB : vpl == 4 ? (BG_MINB < BG_MINB4 ? BG_MINB : BG_MINB4) : vpl <= 6 ? 4 : 3; }
 __host__ __device__ constexpr int bwd_min_blocks(int vpl) { return vpl <= 3 ? BG_MINB_BWD : vpl <= 5 ? (BG_MINB_BWD < 3 ? BG_MINB_BWD : 3) : 2; }
 
 // (vector width, log2 lanes per neighbour, slots per lane) combinations the gather kernels are instantiated

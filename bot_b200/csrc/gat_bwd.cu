@@ -381,8 +381,8 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
     BG_REQUIRE(!split || p.h_count == a->H, "backward: a graph with split rows needs the full head range");
     const int64_t nblocks = (int64_t)p.blocks_per_slab * p.h_count;
     BG_REQUIRE(nblocks < (1ll << 31), "backward: grid too large");
-    int rc = 1;
-    if (!lowdeg) rc = launch_src_tma(p, t, st);   // 1 = shape not covered by the TMA kernel
+    int rc = launch_src_rowwise(p, t, st);        // 1 = not wanted for this table size / shape not covered
+    if (rc == 1 && !lowdeg) rc = launch_src_tma(p, t, st);   // 1 = shape not covered by the TMA kernel
     if (rc == 1) rc = lowdeg ? launch_src_lowdeg(p, t, st) : launch_src(p, t, dim3((unsigned)nblocks), st);
     if (rc) return rc;
     if (split) {

@@ -261,7 +261,7 @@ extern "C" int botgat_gat_forward(const botgat_graph* g, const botgat_fwd_args* 
   Tiling t = choose_tiling(a->H, a->D, a->ld_ft, a->ft, ld_o, (const void*)p_o, a->col_parts, g->n_src);
   FwdParams p;
   p.indptr = g->in_indptr; p.indices = g->in_indices; p.eid = g->in_eid;
-  p.n_rows = (int)g->n_dst; p.n_edges = g->n_edges;
+  p.n_rows = (int)g->n_dst; p.n_src_table = g->n_src; p.n_edges = g->n_edges;
   p.H = a->H; p.D = a->D; p.ld_ft = a->ld_ft; p.ld_out = a->ld_out;
   p.ft = a->ft; p.el = a->el; p.er = a->er; p.eb = a->eb; p.am = a->am;
   p.cs = a->src_scale; p.ds = a->dst_scale; p.Hb = a->Hb;
@@ -284,11 +284,8 @@ extern "C" int botgat_gat_forward(const botgat_graph* g, const botgat_fwd_args* 
   BG_REQUIRE(!split || p.h_count == a->H, "forward: a graph with split rows needs the full head range");
   const int64_t nblocks = (int64_t)p.blocks_per_slab * p.h_count * t.col_parts;
   BG_REQUIRE(nblocks < (1ll << 31), "forward: grid too large");
-  int rc;
-  if (lowdeg)
-    rc = launch_fwd_lowdeg(p, t, st);
-  else
-    rc = launch_fwd(p, t, dim3((unsigned)nblocks), st);
+  int rc = launch_fwd_rowwise(p, t, st);  // 1 = not wanted for this table size / shape not covered
+  if (rc == 1) rc = lowdeg ? launch_fwd_lowdeg(p, t, st) : launch_fwd(p, t, dim3((unsigned)nblocks), st);
   if (rc) return rc;
   if (split) {
     rc = launch_fwd_combine(seg, a->H, a->D, a->ld_out, a->scratch, a->dst_scale, a->out, a->row_max, a->row_sum, p.ep, st);

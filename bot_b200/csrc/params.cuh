@@ -36,6 +36,7 @@ struct FwdParams {
   const int32_t* indices;
   const int32_t* eid;
   int n_rows;
+  int64_t n_src_table;  // rows of the gathered table ft
   int64_t n_edges;
   int H, D;
   int64_t ld_ft, ld_out;
@@ -104,6 +105,10 @@ int launch_src_lowdeg(const BwdParams& p, const Tiling& t, cudaStream_t st);
 // gat_bwd_tma.cu: the warp-per-row src pass with TMA-staged rows; returns 1 when the shape is not covered (caller
 // falls back to gat_bwd_src_kernel), 0 when launched, < 0 on error
 int launch_src_tma(const BwdParams& p, const Tiling& t, cudaStream_t st);
+// gat_rowwise.cu: one warp per row for ALL heads, for gathered tables far beyond the L2 (no head slab can be resident);
+// same return convention as launch_src_tma
+int launch_fwd_rowwise(const FwdParams& p, const Tiling& t, cudaStream_t st);
+int launch_src_rowwise(const BwdParams& p, const Tiling& t, cudaStream_t st);
 int segment_length();
 // floats per scratch slot (rounded to 4 so that float4 stores into a slot stay aligned)
 __host__ __device__ inline int64_t fwd_slot_floats(int H, int D) { return ((int64_t)H * (D + 2) + 3) / 4 * 4; }

@@ -846,7 +846,7 @@ def test_src_pass_tma_philox(cuda, monkeypatch, H, tma):
         assert rel_err(g[k], ref_g[k]) <= 1e-4, k
 
 
-@pytest.mark.parametrize("family", ["warp", "group", "split"])
+@pytest.mark.parametrize("family", ["warp", "group", "split", "rowwise"])
 @pytest.mark.parametrize("model_kind", ["proteins", "products_res", "products_nores", "v1_bn", "v1_bias", "v1_bn_linear"])
 def test_fused_layer_tail_inference(cuda, monkeypatch, family, model_kind):
     """Inference with the layer tail (residual adds, eval-mode BatchNorm / bias, ReLU) fused into the forward kernel's
@@ -861,6 +861,7 @@ def test_fused_layer_tail_inference(cuda, monkeypatch, family, model_kind):
     from bot_b200.ogbn_proteins import GAT as ProteinsGAT
 
     monkeypatch.setenv("BOTGAT_LOWDEG", "1000000" if family == "group" else "0")
+    monkeypatch.setenv("BOTGAT_ROWWISE", "1" if family == "rowwise" else "0")
     if family == "split":
         monkeypatch.setenv("BOTGAT_SEG", "32")
     torch.manual_seed(5)
@@ -915,3 +916,107 @@ def test_fused_layer_tail_inference(cuda, monkeypatch, family, model_kind):
     assert n_fused >= 2 and len(calls) == n_fused, "the fused tail must run in inference and only there"
     assert y_fused.shape == y_plain.shape
     assert rel_err(y_fused, y_plain) <= 2e-6
+
+
+# ---------------------------------------------------------------------------
+# all-heads-per-row kernels (gat_rowwise.cu): selected automatically only for tables far beyond the L2, forced here
+# ---------------------------------------------------------------------------
+ROWWISE_CASES = dict(CASES)
+ROWWISE_CASES.update({
+    "rw_H2_D48": (300, 300, 9000, 2, 48, dict(ee=True)),                      # 16 lanes per head, one slot
+    "rw_H1_D512": (100, 100, 3000, 1, 512, dict(keep_p=0.2)),                 # 32 lanes per head, four slots
+    "rw_H3_D32_symm": (400, 400, 12000, 3, 32, dict(er=False, symm=True, attn_p=0.2)),   # an idle head group
+    "rw_H5_D20": (200, 200, 8000, 5, 20, dict(ee=True, keep_p=0.1)),          # 4 lanes per head, three idle groups
+    "rw_H8_D128": (150, 150, 5000, 8, 128, dict(ee=True)),                    # 4 lanes per head, eight slots
+    "rw_H4_D256": (120, 120, 4000, 4, 256, dict()),                           # 8 lanes per head, eight slots
+    "rw_long_rows": (64, 64, 40000, 4, 120, dict(ee=True, keep_p=0.1)),       # ~20 chunks per row: the online rescale
+})
+
+
+@pytest.mark.parametrize("name", list(ROWWISE_CASES))
+def test_rowwise_kernels(cuda, monkeypatch, name):
+    """One warp per row for all heads (forward and backward src pass) against the fp64 oracle on every parity case;
+    shapes the family does not cover (vector width < 4) silently take the head-major kernels."""
+    monkeypatch.setenv("BOTGAT_ROWWISE", "1")
+    n_src, n_dst, e, H, D, kw = ROWWISE_CASES[name]
+    c = make_case(n_src, n_dst, e, H, D, seed=zlib.crc32(name.encode()) % 1000 + 2, **kw)
+    check_case(c, cuda)
+    o1, g1, _ = engine_run(c, cuda)
+    o2, g2, _ = engine_run(c, cuda)
+    assert torch.equal(o1, o2) and all(g1[k] is None or torch.equal(g1[k], g2[k]) for k in g1)
+
+
+def test_rowwise_is_selected(cuda, monkeypatch):
+    """The family really runs when forced (launch names differ only in the profiler, so compare against the head-major
+    result: close, but not bit-identical — the summation order differs) and is not selected for small tables."""
+    c = make_case(500, 500, 20000, 4, 120, keep_p=0.1, seed=5)
+    monkeypatch.setenv("BOTGAT_ROWWISE", "0")
+    o0, g0, _ = engine_run(c, cuda)
+    monkeypatch.delenv("BOTGAT_ROWWISE")
+    oa, ga, _ = engine_run(c, cuda)          # auto: a 240 KB slab is L2-resident -> head-major
+    assert torch.equal(o0, oa) and torch.equal(g0["ft"], ga["ft"])
+    monkeypatch.setenv("BOTGAT_ROWWISE", "1")
+    o1, g1, _ = engine_run(c, cuda)
+    assert rel_err(o1, o0) <= 1e-6 and rel_err(g1["ft"], g0["ft"]) <= 1e-6
+    assert not torch.equal(g1["ft"], g0["ft"])
+    monkeypatch.setenv("BOTGAT_ROWWISE_MB", "0")   # auto with a zero threshold: selected by table size
+    monkeypatch.delenv("BOTGAT_ROWWISE")
+    o2, g2, _ = engine_run(c, cuda)
+    assert torch.equal(o2, o1) and torch.equal(g2["ft"], g1["ft"])
+
+
+@pytest.mark.parametrize("seg", ["32", "100"])
+def test_rowwise_row_splitting(cuda, monkeypatch, seg):
+    """Heavy rows split into segments through the all-heads-per-row kernels (same scratch slots and combine kernels)."""
+    monkeypatch.setenv("BOTGAT_SEG", seg)
+    monkeypatch.setenv("BOTGAT_ROWWISE", "1")
+    c = make_case(600, 600, 60000, 3, 40, ee=True, keep_p=0.1, power_law=1.2, symm=True, seed=31)
+    check_case(c, cuda)
+    o1, g1, g = engine_run(c, cuda)
+    o2, g2, _ = engine_run(c, cuda)
+    assert g._info.n_slots_in > 0
+    assert torch.equal(o1, o2) and all(torch.equal(g1[k], g2[k]) for k in g1)
+
+
+@pytest.mark.parametrize("H", [1, 4, 6])
+def test_rowwise_philox(cuda, monkeypatch, H):
+    """In-kernel attention dropout through the all-heads-per-row kernels."""
+    from util import philox_attn_mul
+
+    monkeypatch.setenv("BOTGAT_ROWWISE", "1")
+    p, seed = 0.25, 0x0BAD_5EED_1234_5678
+    c = make_case(200, 200, 20000, H, 80, ee=True, keep_p=0.1, seed=190 + H)
+    c["attn_mul"] = philox_attn_mul(seed, 20000, H, p, eids=graph_ref.canonical_edge_ids(c["src"].numpy(), c["dst"].numpy()))
+    ref_out, ref_g = oracle_run(c)
+    out, g, _ = engine_run(dict(c, attn_mul=None), cuda, attn_p=p, seed=seed)
+    assert rel_err(out, ref_out) <= FWD_TOL
+    for k in ("ft", "el", "er", "ee"):
+        assert rel_err(g[k], ref_g[k]) <= 1e-4, k
+
+
+@pytest.mark.parametrize("name", ["proteins_like_edge_drop", "products_like_H4_D120", "reddit_like_H4_D64_symm"])
+def test_rowwise_head_range_launches(cuda, monkeypatch, name):
+    """Head-range launches (the head-pipelined halo exchange's protocol) through the all-heads-per-row kernels: a range
+    of heads is a narrower row; results are bit-identical to the single launch when the lane geometry is the same and
+    within rounding otherwise (fewer heads per launch -> more lanes per head -> another summation order)."""
+    import bot_b200
+    from bot_b200.functional import Hooks, gat_fused
+
+    monkeypatch.setenv("BOTGAT_ROWWISE", "1")
+    n_src, n_dst, e, H, D, kw = CASES[name]
+    c = make_case(n_src, n_dst, e, H, D, seed=3, **kw)
+    g = bot_b200.Graph(c["src"].to(cuda), c["dst"].to(cuda), n_src, n_dst)
+    names = ["ft", "el"] + (["er"] if c.get("er") is not None else []) + (["ee"] if c.get("ee") is not None else [])
+    keep = c["keep"].to(cuda) if c.get("keep") is not None else None
+    cs = c["src_scale"].to(cuda) if c.get("src_scale") is not None else None
+    ds = c["dst_scale"].to(cuda) if c.get("dst_scale") is not None else None
+    hooks = Hooks(head_chunks=[(0, 1), (1, H - 1)], pre_head=lambda i: None, post_src_head=lambda i, gft, gel: None)
+    res = []
+    for hk in (None, hooks):
+        t = {k: c[k].to(cuda).clone().requires_grad_(True) for k in names}
+        am = c["attn_mul"].to(cuda) if c.get("attn_mul") is not None else None
+        out = gat_fused(g, t["ft"], t["el"], t.get("er"), t.get("ee"), keep, am, cs, ds, 0.2, 0.0, 0, hooks=hk)
+        out.backward(c["gout"].to(cuda))
+        res.append([out.detach()] + [t[k].grad for k in names])
+    for a, b in zip(*res):
+        assert rel_err(b, a) <= 2e-6
