@@ -467,6 +467,265 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, rw_bwd_blocks(VPL)) gat_b
   if (hval && j == 0) p.grad_el[(int64_t)row * H + h] = gel;
 }
 
+
+// ---------------------------------------------------------------------------
+// backward src pass, rows staged by bulk copies
+//
+// Same pass with the g'[v] rows fetched by the copy engine instead of LDG: one `cp.async.bulk` (UBLKCP) per
+// neighbour row — the whole 4*H*D contiguous bytes in ONE request — into a per-warp shared-memory ring of R slots,
+// completion on one mbarrier per slot, rows consumed with LDS.128.  The register ring above keeps U = 4 neighbours
+// (7.7 KB at the products shape) per warp in flight at 168 registers / 12 warps per SM (92 KB per SM) and leaves DRAM
+// at 57 % (profiles/r02_s_rw_summary.txt); here the ring is R = 8 rows per warp in shared memory, no register holds
+// a row in flight, and the resident warps are bounded by shared memory instead (13 one-warp blocks x 15 KB).
+// One warp per block, as in gat_bwd_tma.cu.  Each lane issues the copy of ITS OWN neighbour (lane = edge), so no
+// index shuffles are needed on the issue side.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rw_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 rw_lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void rw_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tRW_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%0], %1;\n\t@q bra RW_DONE;\n\tbra RW_WAIT;\n\tRW_DONE:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
+constexpr int kBulkRingLog2 = 3;  // R = 8 slots
+constexpr int kBulkRing = 1 << kBulkRingLog2;
+
+template <int GSH, int VPL>
+__global__ void __launch_bounds__(32, 10) gat_bwd_src_rowbulk_kernel(const BwdParams p, int slotB) {
+  constexpr int G = 1 << GSH;
+  constexpr int HG = 32 >> GSH;
+  constexpr int U = 4;         // neighbours per packed dot reduction (G >= 4 in every instantiation)
+  constexpr int LPU = G / U;
+  constexpr int R = kBulkRing;
+  extern __shared__ __align__(128) unsigned char ring[];  // R slots of slotB bytes
+  __shared__ __align__(8) uint64_t bars[R];
+  __shared__ __align__(16) float wsm[32 * HG];
+  __shared__ __align__(16) float dsm[32 * HG];
+  const int lane = threadIdx.x;
+  uint32_t ring0 = rw_smem_u32(ring), bar0 = rw_smem_u32(bars);
+  asm volatile("" : "+r"(ring0), "+r"(bar0));
+  if (lane < R) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * lane));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+
+  const int item = blockIdx.x;
+  const int row = p.seg_row ? p.seg_row[item] : item;
+  const int slot = p.seg_row ? p.seg_slot[item] : -1;
+  const int grp = lane >> GSH, j = lane & (G - 1);
+  const int hc = p.h_count;
+  const bool hval = grp < hc;
+  const int hl = hval ? grp : hc - 1;  // idle groups shadow the last head (reads stay inside the staged row)
+  const int h = p.h_begin + hl;
+  const int H = p.H, D = p.D;
+  const int nv = D >> 2;
+  const uint32_t rowB = (uint32_t)(hc * D * 4);  // staged bytes of one neighbour: the heads of this launch
+
+  bool act[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) act[i] = hval && (j + i * G) < nv;
+  const uint32_t lane_off = (uint32_t)((hl * D + j * 4) * 4);
+  const uint32_t last_off = lane_off + (uint32_t)((min(j + (VPL - 1) * G, nv - 1) - j) * 16);
+  const char* gbase = reinterpret_cast<const char*>(p.g + p.h_begin * D);
+  const size_t ldb = (size_t)p.ld_g * 4;
+
+  const int beg = p.seg_row ? p.seg_beg[item] : p.indptr[row];
+  const int end = p.seg_row ? p.seg_end[item] : p.indptr[row + 1];
+  const float slope = p.slope;
+  const float csu = p.cs ? p.cs[row] : 1.f;
+  Vec<4> fu[VPL], acc[VPL];
+  {
+    const float* f = p.ft + (int64_t)row * p.ld_ft + h * D;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      if (act[i]) { fu[i].load(f + (j + i * G) * 4); fu[i].scale(csu); } else fu[i].zero();
+      acc[i].zero();
+    }
+  }
+  float gel_lane[HG];
+#pragma unroll
+  for (int hh = 0; hh < HG; ++hh) gel_lane[hh] = 0.f;
+  const float* __restrict__ el_u = p.el + (int64_t)row * H + p.h_begin;
+  const float4* __restrict__ drec = p.drec + (int64_t)p.h_begin * p.n_dst;
+  const float* __restrict__ eb = p.eb ? p.eb + (int64_t)(p.Hb == 1 ? 0 : p.h_begin) * p.n_edges : nullptr;
+  const int64_t eb_hs = p.Hb == 1 ? 0 : p.n_edges;
+  const float* __restrict__ am = p.am ? p.am + (int64_t)p.h_begin * p.n_edges : nullptr;
+  float* __restrict__ gz = p.gz ? p.gz + (int64_t)p.h_begin * p.n_edges : nullptr;
+  const bool philox = (p.am == nullptr) && p.attn_p > 0.f;
+
+  auto load_index = [&](int base, int& v, int& k) {
+    const int pos = base + lane;
+    v = k = 0;
+    if (pos < end) {
+      v = __ldg(p.indices + pos);
+      if (philox) k = __ldg(p.eid + pos);
+    }
+  };
+  // neighbours [lo, hi) of the current chunk (lane = neighbour) go to the ring slots q0 + (lane - lo), ...
+  auto issue = [&](int lo, int hi, uint32_t q0, int v) {
+    if (lane >= lo && lane < hi) {
+      const uint32_t s = (q0 + (uint32_t)(lane - lo)) & (R - 1);
+      const uint32_t bar = bar0 + 8 * s;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(rowB) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ring0 + s * slotB),
+                   "l"(gbase + (size_t)(unsigned)v * ldb), "r"(rowB), "r"(bar)
+                   : "memory");
+    }
+  };
+  int v0, v1, k0, k1;
+  load_index(beg, v0, k0);
+  load_index(beg + 32, v1, k1);
+  uint32_t q = 0;  // neighbours issued so far (ring write position); consumed: c (read position, phase = c / R)
+  uint32_t c = 0;
+
+  for (int base = beg; base < end; base += 32) {
+    const int cnt = min(32, end - base);
+    const int pos = base + lane;
+    const bool valid = pos < end;
+    int v2, k2;
+    load_index(base + 64, v2, k2);
+
+    // the ring is empty at a chunk boundary: fill it before the logit operands are even requested
+    int issued = min(cnt, R);
+    issue(0, issued, q, v0);
+    q += (uint32_t)issued;
+
+    // ---- lane = edge: recompute the attention weight of this edge for every head ----
+    float ca[HG], cb[HG];  // gz = ca * <src_scale * ft[u], g'[v]> - cb   (softmax + leaky_relu adjoint, App. A.3)
+    {
+      float4 rec[HG];
+      float ebv[HG], amv[HG];
+#pragma unroll
+      for (int hh = 0; hh < HG; ++hh) {
+        const bool hv = valid && hh < hc;
+        rec[hh] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ebv[hh] = -INFINITY;  // lanes past the row end / idle heads behave like dropped edges: alpha = 0
+        amv[hh] = 1.f;
+        if (hv) {
+          rec[hh] = __ldg(drec + (int64_t)hh * p.n_dst + v0);
+          ebv[hh] = eb ? __ldg(eb + hh * eb_hs + pos) : 0.f;
+          if (am) amv[hh] = __ldg(am + (int64_t)hh * p.n_edges + pos);
+        }
+      }
+      if (philox) {
+        float pm[HG];
+        philox_heads<HG>(p.seed, (uint32_t)k0, p.h_begin, hc, p.attn_p, p.inv_keep, pm);
+#pragma unroll
+        for (int hh = 0; hh < HG; ++hh) amv[hh] *= pm[hh];
+      }
+      float wv[HG];
+#pragma unroll
+      for (int hh = 0; hh < HG; ++hh) {
+        const float z = (hh < hc ? __ldg(el_u + hh) : 0.f) + rec[hh].x + ebv[hh];
+        const float s = leaky_relu(z, slope);
+        const float alpha = (s == -INFINITY) ? 0.f : __expf(s - rec[hh].y) * rec[hh].z;
+        const float dz = z > 0.f ? 1.f : slope;
+        wv[hh] = alpha * amv[hh];
+        ca[hh] = wv[hh] * dz;
+        cb[hh] = alpha * rec[hh].w * dz;
+      }
+      if constexpr (HG % 4 == 0) {
+#pragma unroll
+        for (int qd = 0; qd < HG / 4; ++qd)
+          reinterpret_cast<float4*>(wsm + lane * HG)[qd] = make_float4(wv[4 * qd], wv[4 * qd + 1], wv[4 * qd + 2], wv[4 * qd + 3]);
+      } else {
+#pragma unroll
+        for (int hh = 0; hh < HG; ++hh) wsm[lane * HG + hh] = wv[hh];
+      }
+    }
+    __syncwarp();
+
+    // ---- group = head: acc += w * g'[v], dot <g'[v], ft[u]> back to the edge's lane through shared memory ----
+    for (int e = 0; e < cnt; e += U) {
+      float part[U];
+#pragma unroll
+      for (int s = 0; s < U; ++s) {
+        part[s] = 0.f;
+        if (e + s < cnt) {  // warp-uniform
+          const uint32_t sl = c & (R - 1);
+          rw_wait(bar0 + 8 * sl, (c >> kBulkRingLog2) & 1u);
+          ++c;
+          const uint32_t a = ring0 + sl * slotB;
+          const float w = wsm[(e + s) * HG + grp];
+#pragma unroll
+          for (int i = 0; i < VPL; ++i) {
+            Vec<4> x;
+            x.v = rw_lds128(a + (i < VPL - 1 ? lane_off + i * G * 16 : last_off));
+            acc[i].fma(w, x);
+            part[s] = x.dot(fu[i], part[s]);  // fu is 0 on slots this lane does not own
+          }
+        }
+      }
+      __syncwarp();  // every lane is done with these U slots before they are refilled
+      {
+        const int more = min(U, cnt - issued);
+        if (more > 0) {
+          issue(issued, issued + more, q, v0);
+          q += (uint32_t)more;
+          issued += more;
+        }
+      }
+      int k = U;
+#pragma unroll
+      for (int o = G >> 1; o > 0; o >>= 1) {
+        if (k > 1) {
+          const bool upper = (lane & o) != 0;
+#pragma unroll
+          for (int i = 0; i < U / 2; ++i) {
+            if (i < k / 2) {
+              const float send = upper ? part[i] : part[i + k / 2];
+              const float keep = upper ? part[i + k / 2] : part[i];
+              part[i] = keep + __shfl_xor_sync(kFull, send, o);
+            }
+          }
+          k >>= 1;
+        } else {
+          part[0] += __shfl_xor_sync(kFull, part[0], o);
+        }
+      }
+      if ((j & (LPU - 1)) == 0) dsm[(e + j / LPU) * HG + grp] = part[0];  // e + s <= 31
+    }
+    __syncwarp();
+
+    if (valid) {
+#pragma unroll
+      for (int hh = 0; hh < HG; ++hh) {
+        if (hh < hc) {
+          const float gzv = fmaf(ca[hh], dsm[lane * HG + hh], -cb[hh]);
+          if (gz) gz[(int64_t)hh * p.n_edges + pos] = gzv;
+          gel_lane[hh] += gzv;
+        }
+      }
+    }
+    __syncwarp();
+    v0 = v1; v1 = v2; k0 = k1; k1 = k2;
+  }
+
+  const float gel = packed_reduce<GSH, false>(gel_lane, lane);
+  if (slot >= 0) {
+    float* sl = p.scratch + (int64_t)slot * bwd_slot_floats(H, D);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+      if (act[i]) acc[i].store(sl + (int64_t)h * D + (j + i * G) * 4);
+    if (hval && j == 0) sl[H * D + h] = gel;
+    return;
+  }
+  float* o = p.grad_ft + (int64_t)row * p.ld_gft + h * D;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    if (act[i]) {
+      acc[i].scale(csu);
+      acc[i].store(o + (j + i * G) * 4);
+    }
+  }
+  if (hval && j == 0) p.grad_el[(int64_t)row * H + h] = gel;
+}
+
 // ---------------------------------------------------------------------------
 // selection and launch
 // ---------------------------------------------------------------------------
@@ -521,7 +780,34 @@ int launch_src_rowwise(const BwdParams& p, const Tiling& t, cudaStream_t st) {
   if (t.vw != 4 || p.ee || p.keep || p.amul_e || p.gz_e || !rowwise_wanted(p.D, p.n_dst) || !rowwise_geometry(p.h_count, p.D, &gsh, &vpl))
     return 1;
   const int64_t nblocks = ((int64_t)p.n_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  if (nblocks <= 0 || nblocks >= (1ll << 31)) return 1;
+  if (nblocks <= 0 || nblocks >= (1ll << 31) || p.n_items <= 0) return 1;
+  // rows staged by bulk copies (one-warp blocks, shared-memory ring) unless BOTGAT_RW_BULK=0 or a staged row is too
+  // large for a ring of kBulkRing slots; the register-ring kernel otherwise
+  const char* eb = getenv("BOTGAT_RW_BULK");
+  const int slotB = (int)(((int64_t)p.h_count * p.D * 4 + 127) / 128 * 128);
+  const size_t ringB = (size_t)kBulkRing * slotB;
+  const bool bulk = !(eb && *eb == '0') && ringB <= 96 * 1024 && ((uintptr_t)p.g % 16) == 0 && p.ld_g % 4 == 0;
+  if (bulk) {
+#define BG_X(GSH, VPL)                                                                                                \
+  if (gsh == GSH && vpl == VPL) {                                                                                     \
+    static bool attr_set = false;                                                                                     \
+    if (!attr_set) {                                                                                                  \
+      if (cudaFuncSetAttribute(gat_bwd_src_rowbulk_kernel<GSH, VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                               96 * 1024) != cudaSuccess) {                                                           \
+        cudaGetLastError();                                                                                           \
+        return 1;                                                                                                     \
+      }                                                                                                               \
+      cudaFuncSetAttribute(gat_bwd_src_rowbulk_kernel<GSH, VPL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
+      attr_set = true;                                                                                                \
+    }                                                                                                                 \
+    gat_bwd_src_rowbulk_kernel<GSH, VPL><<<dim3((unsigned)p.n_items), dim3(32), ringB, st>>>(p, slotB);               \
+    BG_LAUNCHED(1);                                                                                                   \
+    return 0;                                                                                                         \
+  }
+    BG_RW_COMBOS(BG_X)
+#undef BG_X
+    return 1;
+  }
 #define BG_X(GSH, VPL)                                                                                       \
   if (gsh == GSH && vpl == VPL) {                                                                            \
     gat_bwd_src_rowwise_kernel<GSH, VPL><<<dim3((unsigned)nblocks), dim3(kWarpsPerBlock * 32), 0, st>>>(p);  \

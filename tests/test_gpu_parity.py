@@ -933,11 +933,14 @@ ROWWISE_CASES.update({
 })
 
 
+@pytest.mark.parametrize("bulk", ["1", "0"])
 @pytest.mark.parametrize("name", list(ROWWISE_CASES))
-def test_rowwise_kernels(cuda, monkeypatch, name):
-    """One warp per row for all heads (forward and backward src pass) against the fp64 oracle on every parity case;
-    shapes the family does not cover (vector width < 4) silently take the head-major kernels."""
+def test_rowwise_kernels(cuda, monkeypatch, name, bulk):
+    """One warp per row for all heads (forward and backward src pass; the latter with its rows staged by bulk copies
+    into a shared-memory ring, or through the register ring) against the fp64 oracle on every parity case; shapes the
+    family does not cover (vector width < 4) silently take the head-major kernels."""
     monkeypatch.setenv("BOTGAT_ROWWISE", "1")
+    monkeypatch.setenv("BOTGAT_RW_BULK", bulk)
     n_src, n_dst, e, H, D, kw = ROWWISE_CASES[name]
     c = make_case(n_src, n_dst, e, H, D, seed=zlib.crc32(name.encode()) % 1000 + 2, **kw)
     check_case(c, cuda)
@@ -965,11 +968,13 @@ def test_rowwise_is_selected(cuda, monkeypatch):
     assert torch.equal(o2, o1) and torch.equal(g2["ft"], g1["ft"])
 
 
+@pytest.mark.parametrize("bulk", ["1", "0"])
 @pytest.mark.parametrize("seg", ["32", "100"])
-def test_rowwise_row_splitting(cuda, monkeypatch, seg):
+def test_rowwise_row_splitting(cuda, monkeypatch, seg, bulk):
     """Heavy rows split into segments through the all-heads-per-row kernels (same scratch slots and combine kernels)."""
     monkeypatch.setenv("BOTGAT_SEG", seg)
     monkeypatch.setenv("BOTGAT_ROWWISE", "1")
+    monkeypatch.setenv("BOTGAT_RW_BULK", bulk)
     c = make_case(600, 600, 60000, 3, 40, ee=True, keep_p=0.1, power_law=1.2, symm=True, seed=31)
     check_case(c, cuda)
     o1, g1, g = engine_run(c, cuda)
@@ -978,12 +983,14 @@ def test_rowwise_row_splitting(cuda, monkeypatch, seg):
     assert torch.equal(o1, o2) and all(torch.equal(g1[k], g2[k]) for k in g1)
 
 
+@pytest.mark.parametrize("bulk", ["1", "0"])
 @pytest.mark.parametrize("H", [1, 4, 6])
-def test_rowwise_philox(cuda, monkeypatch, H):
+def test_rowwise_philox(cuda, monkeypatch, H, bulk):
     """In-kernel attention dropout through the all-heads-per-row kernels."""
     from util import philox_attn_mul
 
     monkeypatch.setenv("BOTGAT_ROWWISE", "1")
+    monkeypatch.setenv("BOTGAT_RW_BULK", bulk)
     p, seed = 0.25, 0x0BAD_5EED_1234_5678
     c = make_case(200, 200, 20000, H, 80, ee=True, keep_p=0.1, seed=190 + H)
     c["attn_mul"] = philox_attn_mul(seed, 20000, H, p, eids=graph_ref.canonical_edge_ids(c["src"].numpy(), c["dst"].numpy()))
