@@ -30,7 +30,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 gat_bwd_node_kernel(int n_dst, int H, int D, int64_t ld, const float* __restrict__ out,
                     const float* __restrict__ gout, const float* __restrict__ er,
                     const float* __restrict__ row_max, const float* __restrict__ row_sum,
-                    const float* __restrict__ ds, float4* __restrict__ drec, float* __restrict__ gprime) {
+                    const float* __restrict__ ds, float4* __restrict__ drec, int drec_hs, int drec_vs,
+                    float* __restrict__ gprime) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int v = blockIdx.x * kWarpsPerBlock + warp;
   if (v >= n_dst) return;
@@ -47,7 +48,7 @@ gat_bwd_node_kernel(int n_dst, int H, int D, int64_t ld, const float* __restrict
     t = warp_sum(t);
     if (lane == 0) {
       const float l = row_sum[(int64_t)v * H + h];
-      drec[(int64_t)h * n_dst + v] =
+      drec[(unsigned)(h * drec_hs + v * drec_vs)] =
           make_float4(er ? er[(int64_t)v * H + h] : 0.f, row_max[(int64_t)v * H + h], l > 0.f ? 1.f / l : 0.f, t);
     }
   }
@@ -109,7 +110,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, bwd_min_blocks(VPL)) gat_
       acc[i].zero();
     }
   }
-  const float4* __restrict__ drec_h = p.drec + (int64_t)h * p.n_dst;
+  const float4* __restrict__ drec_h = p.drec + (unsigned)(h * p.drec_hs);
+  const int drec_vs = p.drec_vs;
   const float* __restrict__ eb_h = p.eb ? p.eb + (int64_t)(p.Hb == 1 ? 0 : h) * p.n_edges : nullptr;
   const float* __restrict__ am_h = p.am ? p.am + (int64_t)h * p.n_edges : nullptr;
   float* __restrict__ gz_h = p.gz ? p.gz + (int64_t)h * p.n_edges : nullptr;
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, bwd_min_blocks(VPL)) gat_
     o.ee = 0.f;
     o.kp = 1;
     if (pos < end) {
-      o.rec = __ldg(drec_h + v);
+      o.rec = __ldg(drec_h + (unsigned)(v * drec_vs));
       o.eb = eb_h ? __ldg(eb_h + pos) : 0.f;
       if (ee_h) o.ee = __ldg(ee_h + (int64_t)k * H);
       if (keep) o.kp = __ldg(keep + k);
@@ -340,10 +342,13 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
   const int64_t ld_gee = a->ld_gee > 0 ? a->ld_gee : a->H;
   BG_REQUIRE(a->gz || ld_gee == a->H, "backward: a padded grad_ee needs the staged path (gz workspace)");
 
+  const bool node_major = drec_node_major(a->H, a->D, g->n_dst);
+  BG_REQUIRE(g->n_dst * (int64_t)a->H < (1ll << 31), "backward: n_dst * H must be < 2^31");
+  const int drec_hs = node_major ? 1 : (int)g->n_dst, drec_vs = node_major ? a->H : 1;
   if (phases & 1) {
     dim3 grid((unsigned)((g->n_dst + kWarpsPerBlock - 1) / kWarpsPerBlock));
     gat_bwd_node_kernel<<<grid, block, 0, st>>>((int)g->n_dst, a->H, a->D, a->ld_out, a->out, a->gout, a->er,
-                                                a->row_max, a->row_sum, a->dst_scale, (float4*)a->drec,
+                                                a->row_max, a->row_sum, a->dst_scale, (float4*)a->drec, drec_hs, drec_vs,
                                                 a->dst_scale ? a->gprime : nullptr);
     BG_LAUNCHED(1);
     BG_CHECK(cudaGetLastError());
@@ -355,6 +360,7 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
     p.n_dst = (int)g->n_dst; p.n_edges = g->n_edges;
     p.H = a->H; p.D = a->D; p.ld_ft = a->ld_ft; p.ld_g = a->ld_out; p.ld_gft = a->ld_gft;
     p.ft = a->ft; p.el = a->el; p.cs = a->src_scale; p.g = gp; p.drec = (const float4*)a->drec;
+    p.drec_hs = drec_hs; p.drec_vs = drec_vs;
     p.Hb = a->Hb; p.slope = a->slope; p.attn_p = a->attn_p; p.inv_keep = 1.f / (1.f - a->attn_p); p.seed = a->seed;
     p.grad_ft = a->grad_ft; p.grad_el = a->grad_el;
     p.ee = a->ee; p.keep = a->keep; p.amul_e = a->attn_mul;

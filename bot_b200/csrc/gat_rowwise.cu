@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, rw_bwd_blocks(VPL)) gat_b
     el_u[hh] = hh < hc ? p.el[(int64_t)row * H + p.h_begin + hh] : 0.f;
     gel_lane[hh] = 0.f;
   }
-  const float4* __restrict__ drec = p.drec + (int64_t)p.h_begin * p.n_dst;
+  const float4* __restrict__ drec = p.drec + (unsigned)(p.h_begin * p.drec_hs);
   const float* __restrict__ eb = p.eb ? p.eb + (int64_t)(p.Hb == 1 ? 0 : p.h_begin) * p.n_edges : nullptr;
   const int64_t eb_hs = p.Hb == 1 ? 0 : p.n_edges;
   const float* __restrict__ am = p.am ? p.am + (int64_t)p.h_begin * p.n_edges : nullptr;
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, rw_bwd_blocks(VPL)) gat_b
         ebv[hh] = -INFINITY;  // lanes past the row end / idle heads behave like dropped edges: alpha = 0
         amv[hh] = 1.f;
         if (hv) {
-          rec[hh] = __ldg(drec + (int64_t)hh * p.n_dst + v0);
+          rec[hh] = __ldg(drec + (unsigned)(hh * p.drec_hs + v0 * p.drec_vs));
           ebv[hh] = eb ? __ldg(eb + hh * eb_hs + pos) : 0.f;
           if (am) amv[hh] = __ldg(am + (int64_t)hh * p.n_edges + pos);
         }
@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(32, 10) gat_bwd_src_rowbulk_kernel(const BwdPa
 #pragma unroll
   for (int hh = 0; hh < HG; ++hh) gel_lane[hh] = 0.f;
   const float* __restrict__ el_u = p.el + (int64_t)row * H + p.h_begin;
-  const float4* __restrict__ drec = p.drec + (int64_t)p.h_begin * p.n_dst;
+  const float4* __restrict__ drec = p.drec + (unsigned)(p.h_begin * p.drec_hs);
   const float* __restrict__ eb = p.eb ? p.eb + (int64_t)(p.Hb == 1 ? 0 : p.h_begin) * p.n_edges : nullptr;
   const int64_t eb_hs = p.Hb == 1 ? 0 : p.n_edges;
   const float* __restrict__ am = p.am ? p.am + (int64_t)p.h_begin * p.n_edges : nullptr;
@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(32, 10) gat_bwd_src_rowbulk_kernel(const BwdPa
         ebv[hh] = -INFINITY;  // lanes past the row end / idle heads behave like dropped edges: alpha = 0
         amv[hh] = 1.f;
         if (hv) {
-          rec[hh] = __ldg(drec + (int64_t)hh * p.n_dst + v0);
+          rec[hh] = __ldg(drec + (unsigned)(hh * p.drec_hs + v0 * p.drec_vs));
           ebv[hh] = eb ? __ldg(eb + hh * eb_hs + pos) : 0.f;
           if (am) amv[hh] = __ldg(am + (int64_t)hh * p.n_edges + pos);
         }
@@ -756,6 +756,11 @@ static bool rowwise_wanted(int D, int64_t n_rows_table) {
   const int64_t thr = ((mb && *mb) ? atoll(mb) : 256) << 20;
   const int max_parts = D / 64 > 0 ? D / 64 : 1;  // choose_tiling keeps column parts >= 16 vectors wide
   return n_rows_table * (int64_t)D * 4 / max_parts > thr;
+}
+
+bool drec_node_major(int H, int D, int64_t n_dst) {
+  int gsh, vpl;
+  return rowwise_wanted(D, n_dst) && rowwise_geometry(H, D, &gsh, &vpl);
 }
 
 int launch_fwd_rowwise(const FwdParams& p, const Tiling& t, cudaStream_t st) {

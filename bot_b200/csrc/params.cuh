@@ -71,7 +71,10 @@ struct BwdParams {
   const uint8_t* keep;
   float* gz_e;         // (n_edges, H) edge-id order (direct mode), written by the src pass
   const float* g;      // g' (n_dst, ld_g)
-  const float4* drec;  // (H, n_dst)
+  const float4* drec;  // record of (head h, destination v) at drec[h * drec_hs + v * drec_vs]: head-major (hs = n_dst,
+                       // vs = 1) for the head-major kernels, node-major (hs = 1, vs = H: one contiguous 16*H-byte read per
+                       // edge) when the all-heads-per-row kernels are in charge (drec_node_major())
+  int drec_hs, drec_vs;  // 32-bit: n_dst * H < 2^31 is checked at launch
   int Hb;
   float slope, attn_p, inv_keep;
   uint64_t seed;
@@ -107,6 +110,9 @@ int launch_src_lowdeg(const BwdParams& p, const Tiling& t, cudaStream_t st);
 int launch_src_tma(const BwdParams& p, const Tiling& t, cudaStream_t st);
 // gat_rowwise.cu: one warp per row for ALL heads, for gathered tables far beyond the L2 (no head slab can be resident);
 // same return convention as launch_src_tma
+// layout of the per-destination records: a function of the shape alone, so that the node phase (writer) and every src
+// kernel (readers) agree even when the phases are launched by separate calls
+bool drec_node_major(int H, int D, int64_t n_dst);
 int launch_fwd_rowwise(const FwdParams& p, const Tiling& t, cudaStream_t st);
 int launch_src_rowwise(const BwdParams& p, const Tiling& t, cudaStream_t st);
 int segment_length();
