@@ -110,8 +110,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, bwd_min_blocks(VPL)) gat_
       acc[i].zero();
     }
   }
-  const float4* __restrict__ drec_h = p.drec + (unsigned)(h * p.drec_hs);
-  const int drec_vs = p.drec_vs;
+  const float4* __restrict__ drec_h = p.drec + (int64_t)h * p.n_dst;  // head-major records (BwdParams::drec)
   const float* __restrict__ eb_h = p.eb ? p.eb + (int64_t)(p.Hb == 1 ? 0 : h) * p.n_edges : nullptr;
   const float* __restrict__ am_h = p.am ? p.am + (int64_t)h * p.n_edges : nullptr;
   float* __restrict__ gz_h = p.gz ? p.gz + (int64_t)h * p.n_edges : nullptr;
@@ -141,7 +140,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, bwd_min_blocks(VPL)) gat_
     o.ee = 0.f;
     o.kp = 1;
     if (pos < end) {
-      o.rec = __ldg(drec_h + (unsigned)(v * drec_vs));
+      o.rec = __ldg(drec_h + v);
       o.eb = eb_h ? __ldg(eb_h + pos) : 0.f;
       if (ee_h) o.ee = __ldg(ee_h + (int64_t)k * H);
       if (keep) o.kp = __ldg(keep + k);
@@ -388,6 +387,17 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
     const int64_t nblocks = (int64_t)p.blocks_per_slab * p.h_count;
     BG_REQUIRE(nblocks < (1ll << 31), "backward: grid too large");
     int rc = launch_src_rowwise(p, t, st);        // 1 = not wanted for this table size / shape not covered
+    if (rc == 1 && node_major) {
+      // The node phase laid the records out for the all-heads-per-row kernel, which does not cover this call after all
+      // (operands by edge id, an unaligned table): redo the cheap node phase head-major.  gprime is rewritten with
+      // the same values.
+      dim3 ngrid((unsigned)((g->n_dst + kWarpsPerBlock - 1) / kWarpsPerBlock));
+      gat_bwd_node_kernel<<<ngrid, block, 0, st>>>((int)g->n_dst, a->H, a->D, a->ld_out, a->out, a->gout, a->er, a->row_max,
+                                                   a->row_sum, a->dst_scale, (float4*)a->drec, (int)g->n_dst, 1,
+                                                   a->dst_scale ? a->gprime : nullptr);
+      BG_LAUNCHED(1);
+      BG_CHECK(cudaGetLastError());
+    }
     if (rc == 1 && !lowdeg) rc = launch_src_tma(p, t, st);   // 1 = shape not covered by the TMA kernel
     if (rc == 1) rc = lowdeg ? launch_src_lowdeg(p, t, st) : launch_src(p, t, dim3((unsigned)nblocks), st);
     if (rc) return rc;

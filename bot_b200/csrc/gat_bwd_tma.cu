@@ -106,8 +106,7 @@ __global__ void __launch_bounds__(32, BG_TMA_MINB) gat_bwd_src_tma_kernel(const 
       acc[i][0] = acc[i][1] = 0ull;  // the bit pattern of (0.f, 0.f)
     }
   }
-  const float4* __restrict__ drec_h = p.drec + (unsigned)(h * p.drec_hs);
-  const int drec_vs = p.drec_vs;
+  const float4* __restrict__ drec_h = p.drec + (int64_t)h * p.n_dst;  // head-major records (BwdParams::drec)
   const float* __restrict__ eb_h = (kStaged || p.eb) ? p.eb + (int64_t)(p.Hb == 1 ? 0 : h) * p.n_edges : nullptr;
   const float* __restrict__ am_h = (!kStaged && p.am) ? p.am + (int64_t)h * p.n_edges : nullptr;
   float* __restrict__ gz_h = (kStaged || p.gz) ? p.gz + (int64_t)h * p.n_edges : nullptr;
@@ -139,7 +138,7 @@ __global__ void __launch_bounds__(32, BG_TMA_MINB) gat_bwd_src_tma_kernel(const 
     o.ee = 0.f;
     o.kp = 1;
     if (pos < end) {
-      o.rec = __ldg(drec_h + (unsigned)(v * drec_vs));
+      o.rec = __ldg(drec_h + v);
       if constexpr (kStaged) {
         o.eb = __ldg(eb_h + pos);
         return;

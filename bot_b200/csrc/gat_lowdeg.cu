@@ -266,8 +266,7 @@ gat_bwd_src_lowdeg_kernel(const BwdParams p, int warps_per_slab) {
       acc[i].zero();
     }
   }
-  const float4* __restrict__ drec_h = p.drec + (unsigned)(h * p.drec_hs);
-  const int drec_vs = p.drec_vs;
+  const float4* __restrict__ drec_h = p.drec + (int64_t)h * p.n_dst;  // head-major records (BwdParams::drec)
   const float* __restrict__ eb_h = p.eb ? p.eb + (int64_t)(p.Hb == 1 ? 0 : h) * p.n_edges : nullptr;
   const float* __restrict__ am_h = p.am ? p.am + (int64_t)h * p.n_edges : nullptr;
   float* __restrict__ gz_h = p.gz ? p.gz + (int64_t)h * p.n_edges : nullptr;
@@ -293,7 +292,7 @@ gat_bwd_src_lowdeg_kernel(const BwdParams p, int warps_per_slab) {
     o.eb = -INFINITY;
     o.amul = 1.f;
     if (pos < end) {
-      o.rec = __ldg(drec_h + (unsigned)(v * drec_vs));
+      o.rec = __ldg(drec_h + v);
       o.eb = eb_h ? __ldg(eb_h + pos) : 0.f;
       if (ee_h) o.eb += __ldg(ee_h + (int64_t)k * H);
       if (keep && !__ldg(keep + k)) o.eb = -INFINITY;

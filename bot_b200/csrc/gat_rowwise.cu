@@ -749,8 +749,9 @@ static bool rowwise_geometry(int heads, int D, int* gsh, int* vpl) {
 // The all-heads-per-row kernels pay when even one column part of one head's slab cannot stay in L2 (the head-major
 // order then has nothing to offer).  BOTGAT_ROWWISE=0 / 1 forces the choice (tests, sweeps); BOTGAT_ROWWISE_MB moves
 // the slab size (per column part, MB) from which they are used.
-static bool rowwise_wanted(int D, int64_t n_rows_table) {
-  const char* s = getenv("BOTGAT_ROWWISE");  // read per call: the tests run every variant in one process
+static bool rowwise_wanted(int D, int64_t n_rows_table, bool backward = false) {
+  const char* s = getenv(backward ? "BOTGAT_ROWWISE_BWD" : "BOTGAT_ROWWISE_FWD");  // read per call: the tests run every variant in one process
+  if (!(s && *s)) s = getenv("BOTGAT_ROWWISE");
   if (s && *s) return *s != '0';
   const char* mb = getenv("BOTGAT_ROWWISE_MB");
   const int64_t thr = ((mb && *mb) ? atoll(mb) : 256) << 20;
@@ -760,7 +761,7 @@ static bool rowwise_wanted(int D, int64_t n_rows_table) {
 
 bool drec_node_major(int H, int D, int64_t n_dst) {
   int gsh, vpl;
-  return rowwise_wanted(D, n_dst) && rowwise_geometry(H, D, &gsh, &vpl);
+  return rowwise_wanted(D, n_dst, true) && rowwise_geometry(H, D, &gsh, &vpl);
 }
 
 int launch_fwd_rowwise(const FwdParams& p, const Tiling& t, cudaStream_t st) {
@@ -782,7 +783,7 @@ int launch_fwd_rowwise(const FwdParams& p, const Tiling& t, cudaStream_t st) {
 
 int launch_src_rowwise(const BwdParams& p, const Tiling& t, cudaStream_t st) {
   int gsh, vpl;
-  if (t.vw != 4 || p.ee || p.keep || p.amul_e || p.gz_e || !rowwise_wanted(p.D, p.n_dst) || !rowwise_geometry(p.h_count, p.D, &gsh, &vpl))
+  if (t.vw != 4 || p.ee || p.keep || p.amul_e || p.gz_e || !rowwise_wanted(p.D, p.n_dst, true) || !rowwise_geometry(p.h_count, p.D, &gsh, &vpl))
     return 1;
   const int64_t nblocks = ((int64_t)p.n_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
   if (nblocks <= 0 || nblocks >= (1ll << 31) || p.n_items <= 0) return 1;

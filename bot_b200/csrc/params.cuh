@@ -71,9 +71,9 @@ struct BwdParams {
   const uint8_t* keep;
   float* gz_e;         // (n_edges, H) edge-id order (direct mode), written by the src pass
   const float* g;      // g' (n_dst, ld_g)
-  const float4* drec;  // record of (head h, destination v) at drec[h * drec_hs + v * drec_vs]: head-major (hs = n_dst,
-                       // vs = 1) for the head-major kernels, node-major (hs = 1, vs = H: one contiguous 16*H-byte read per
-                       // edge) when the all-heads-per-row kernels are in charge (drec_node_major())
+  const float4* drec;  // per-destination records.  The head-major kernels read them head-major, drec[h * n_dst + v]; the
+                       // all-heads-per-row kernels (gat_rowwise.cu) through the strides below, which are node-major
+                       // (hs = 1, vs = H: one contiguous 16*H-byte read per edge) whenever drec_node_major() says so
   int drec_hs, drec_vs;  // 32-bit: n_dst * H < 2^31 is checked at launch
   int Hb;
   float slope, attn_p, inv_keep;

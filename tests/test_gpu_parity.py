@@ -174,10 +174,14 @@ def test_padded_edge_records(cuda):
     assert rel_err(er.grad, ref_g["er"]) <= 1e-4 and rel_err(ft.grad, ref_g["ft"]) <= 1e-4
 
 
+@pytest.mark.parametrize("rowwise", ["0", "1"])
 @pytest.mark.parametrize("mode", ["staged", "direct"])
-def test_edge_modes_agree(cuda, mode):
+def test_edge_modes_agree(cuda, monkeypatch, mode, rowwise):
+    """rowwise = 1 with the direct mode: the all-heads-per-row kernels do not take operands by edge id, so the src pass
+    falls back to the head-major kernels after the node phase already wrote node-major records (it is redone)."""
     from bot_b200 import functional
 
+    monkeypatch.setenv("BOTGAT_ROWWISE", rowwise)
     c = make_case(500, 500, 20000, 4, 32, ee=True, keep_p=0.2, attn_p=0.1, seed=22)
     old = functional.edge_mode
     functional.edge_mode = mode

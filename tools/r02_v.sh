@@ -1,0 +1,8 @@
+#!/bin/bash
+for i in 1 2; do for lib in variants/libbotgat_prev.so ""; do
+BOTGAT_LIB=${lib:+$PWD/$lib} python bench.py --shape proteins --no-cpu-baseline --no-skew --no-e2e --no-parity --steps 10 2>/dev/null | python -c "
+import json,sys
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('proteins', '$lib' or 'current', round(d['ms_per_step'],3), {k: v['avg_ms'] for k, v in d['kernels'].items()})"
+done; done
