@@ -28,7 +28,9 @@ namespace botgat {
 // 6 blocks x 4 warps (24 warps, <= 80 registers) per SM with 2 steps in flight: the best of the occupancy /
 // loads-in-flight sweep on B200 (profiles/r01_sweeps.md)
 
-template <int VW, int GSH, int VPL>
+// EP: the fused layer tail (inference) is compiled into its own instantiation — carried as a run-time option it cost
+// the training-path forward 2.9 % at the proteins shape (5.94 vs 5.77 ms, same box, profiles/r02_sweeps.md)
+template <int VW, int GSH, int VPL, bool EP>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, fwd_min_blocks(VPL)) gat_fwd_kernel(const FwdParams p) {
   constexpr int NS = steps_in_flight(VPL);
   constexpr int G = 1 << GSH;     // lanes per neighbour
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, fwd_min_blocks(VPL)) gat_
     for (int i = 0; i < VPL; ++i) {
       if (act[i]) {
         acc[i].scale(scale);
-        p.ep.apply(acc[i], row, (int64_t)h * p.D + c0 + (v0 + i * G) * VW);
+        if constexpr (EP) p.ep.apply(acc[i], row, (int64_t)h * p.D + c0 + (v0 + i * G) * VW);
         acc[i].store(o + i * G * VW);
       }
     }
@@ -221,7 +223,10 @@ static int launch_fwd(const FwdParams& p, const Tiling& t, dim3 grid, cudaStream
   dim3 block(kWarpsPerBlock * 32);
 #define BG_X(VW, GSH, VPL)                                        \
   if (t.vw == VW && t.gshift == GSH && t.vpl == VPL) {            \
-    gat_fwd_kernel<VW, GSH, VPL><<<grid, block, 0, st>>>(p);      \
+    if (p.ep.any())                                               \
+      gat_fwd_kernel<VW, GSH, VPL, true><<<grid, block, 0, st>>>(p);  \
+    else                                                          \
+      gat_fwd_kernel<VW, GSH, VPL, false><<<grid, block, 0, st>>>(p); \
     BG_LAUNCHED(1);                                               \
     return 0;                                                     \
   }

@@ -41,7 +41,7 @@ template <int G> __device__ __forceinline__ float group_sum(float v) {
 // ---------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------
-template <int VW, int GSH, int VPL>
+template <int VW, int GSH, int VPL, bool EP>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, fwd_min_blocks(VPL)) gat_fwd_lowdeg_kernel(const FwdParams p, int warps_per_slab) {
   constexpr int NS = steps_in_flight(VPL);
   constexpr int G = 1 << GSH;     // lanes per row
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, fwd_min_blocks(VPL)) gat_
     for (int i = 0; i < VPL; ++i) {
       if (act[i]) {
         acc[i].scale(scale);
-        p.ep.apply(acc[i], row, (int64_t)h * p.D + c0 + (v0 + i * G) * VW);
+        if constexpr (EP) p.ep.apply(acc[i], row, (int64_t)h * p.D + c0 + (v0 + i * G) * VW);
         acc[i].store(o + i * G * VW);
       }
     }
@@ -205,7 +205,10 @@ int launch_fwd_lowdeg(const FwdParams& p, const Tiling& t, cudaStream_t st) {
   dim3 grid((unsigned)nblocks), block(kWarpsPerBlock * 32);
 #define BG_X(VW, GSH, VPL)                                                               \
   if (t.vw == VW && t.gshift == GSH && t.vpl == VPL) {                                   \
-    gat_fwd_lowdeg_kernel<VW, GSH, VPL><<<grid, block, 0, st>>>(p, warps_per_slab);      \
+    if (p.ep.any())                                                                      \
+      gat_fwd_lowdeg_kernel<VW, GSH, VPL, true><<<grid, block, 0, st>>>(p, warps_per_slab);  \
+    else                                                                                 \
+      gat_fwd_lowdeg_kernel<VW, GSH, VPL, false><<<grid, block, 0, st>>>(p, warps_per_slab); \
     BG_LAUNCHED(1);                                                                      \
     return 0;                                                                            \
   }

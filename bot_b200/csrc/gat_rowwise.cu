@@ -72,7 +72,7 @@ __device__ __forceinline__ void philox_heads(uint64_t seed, uint32_t eid, int hd
 // ---------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------
-template <int GSH, int VPL>
+template <int GSH, int VPL, bool EP>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, rw_fwd_blocks(VPL)) gat_fwd_rowwise_kernel(const FwdParams p) {
   constexpr int G = 1 << GSH;     // lanes per head
   constexpr int HG = 32 >> GSH;   // head groups per warp (>= heads of this launch)
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, rw_fwd_blocks(VPL)) gat_f
   for (int i = 0; i < VPL; ++i) {
     if (act[i]) {
       acc[i].scale(scale);
-      p.ep.apply(acc[i], row, (int64_t)h * D + (j + i * G) * 4);
+      if constexpr (EP) p.ep.apply(acc[i], row, (int64_t)h * D + (j + i * G) * 4);
       acc[i].store(o + (j + i * G) * 4);
     }
   }
@@ -772,7 +772,10 @@ int launch_fwd_rowwise(const FwdParams& p, const Tiling& t, cudaStream_t st) {
   if (nblocks <= 0 || nblocks >= (1ll << 31)) return 1;
 #define BG_X(GSH, VPL)                                                                                       \
   if (gsh == GSH && vpl == VPL) {                                                                            \
-    gat_fwd_rowwise_kernel<GSH, VPL><<<dim3((unsigned)nblocks), dim3(kWarpsPerBlock * 32), 0, st>>>(p);      \
+    if (p.ep.any())                                                                                          \
+      gat_fwd_rowwise_kernel<GSH, VPL, true><<<dim3((unsigned)nblocks), dim3(kWarpsPerBlock * 32), 0, st>>>(p);  \
+    else                                                                                                     \
+      gat_fwd_rowwise_kernel<GSH, VPL, false><<<dim3((unsigned)nblocks), dim3(kWarpsPerBlock * 32), 0, st>>>(p); \
     BG_LAUNCHED(1);                                                                                          \
     return 0;                                                                                                \
   }

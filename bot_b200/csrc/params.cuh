@@ -15,9 +15,13 @@ struct Epilogue {
   int relu;
   float* y;
   int64_t ld_y;
+  __host__ __device__ bool any() const { return res || res2 || y; }
   // `a` holds dst_scale * agg of columns [col, col + VW) of row `row`; on return it holds `out`
   template <int VW>
   __device__ __forceinline__ void apply(Vec<VW>& a, int64_t row, int64_t col) const {
+#ifdef BG_NO_EPILOGUE  // developer A/B builds: what the fused tail costs the training-path forward
+    return;
+#endif
     Vec<VW> t;
     if (res) { t.load(res + row * ld_res + col); a.add(t); }
     if (res2) { t.load(res2 + row * ld_res2 + col); a.add(t); }
