@@ -8,7 +8,7 @@ import sys
 
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 # bench.py kernel-timer name <- kernel-name substrings
-GROUPS = {"gat_fwd": ["gat_fwd_kernel", "gat_fwd_lowdeg", "k_fwd_combine"], "gat_bwd_node": ["gat_bwd_node"],
+GROUPS = {"gat_fwd": ["gat_fwd_kernel", "gat_fwd_lowdeg", "gat_fwd_rowwise", "k_fwd_combine"], "gat_bwd_node": ["gat_bwd_node"],
           "gat_bwd_src": ["gat_bwd_src", "k_bwd_combine"], "edge_stage": ["k_edge_stage"],
           "gat_bwd_edge": ["k_edge_unstage", "k_edge_reduce_dst"], "edge_drop_draw": ["k_drop_"]}
 
