@@ -104,7 +104,11 @@ def _worker(rank, world, port, ret):
         # the peer-memory exchange moves the same numbers whatever the chunking; its fixed-order reduction makes the
         # gradients independent of it bit for bit
         a, b = results[("p2p", 1)], results[("p2p", 6)]
-        assert all(torch.equal(x, y) for x, y in zip(a, b))
+        if os.environ.get("BOTGAT_ROWWISE") == "1":
+            # the all-heads-per-row kernels give a head range of another width another lane geometry (summation order)
+            assert all(rel_err(y, x) <= 2e-6 for x, y in zip(a, b))
+        else:
+            assert all(torch.equal(x, y) for x, y in zip(a, b))
         ret[rank] = "ok"
     except Exception as ex:
         import traceback
