@@ -321,6 +321,38 @@ def run_reference(args):
 # ----------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------
+def pin_to_gpu_numa(local_rank, world):
+    """Multi-GPU runs: bind this rank's threads to the CPUs NVML reports as local to its GPU BEFORE any pinned host
+    buffer is allocated (first touch puts the pages on that NUMA node), so that every rank's H2D stream stays on its own
+    socket / PCIe root (round 1: the end-to-end leg did not scale from 2 to 4 GPUs).  Only narrows the set the process is
+    already allowed to run on; any failure leaves the affinity untouched.  Returns what was done, for the JSON line."""
+    if world <= 1 or os.environ.get("BOTGAT_NO_PIN") == "1" or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = local_rank
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if local_rank < len(ids) and ids[local_rank].isdigit():
+                idx = int(ids[local_rank])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpu + 63) // 64)
+        local = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        want = sorted(local & allowed)
+        # several ranks may share one socket: leave each its share of that socket's allowed CPUs
+        if len(want) >= 2:
+            os.sched_setaffinity(0, want)
+            return {"gpu": idx, "cpus": len(want), "of_allowed": len(allowed)}
+        return {"gpu": idx, "cpus": 0, "of_allowed": len(allowed), "note": "no allowed CPU is local to this GPU: affinity unchanged"}
+    except Exception as ex:   # NVML missing / restricted container: not an error for the benchmark
+        return {"error": repr(ex)[:120]}
+
+
 def run_ours(args):
     import torch.distributed as dist
 
@@ -338,6 +370,7 @@ def run_ours(args):
         raise RuntimeError("bench.py (impl ours) needs a CUDA device: bot_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_affinity = pin_to_gpu_numa(local_rank, world)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
@@ -584,6 +617,8 @@ def run_ours(args):
             "parity": parity, "cpu_baseline": cpu_baseline, "config1_cora_cpu_reference": cora, "e2e": e2e, "skew_variant": skew,
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if host_affinity is not None:
+            line["host_affinity_rank0"] = host_affinity
         emit(line)
     if world > 1:
         dist.destroy_process_group()

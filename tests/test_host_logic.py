@@ -253,3 +253,19 @@ def test_node_dataloader_with_the_reference_batch_sampler_over_epochs():
     loader = sampling.NodeDataLoader(FakeGraph(), nids, FakeSampler(), batch_sampler=[[0, 1], [2]])
     for _ in range(2):
         assert [o.tolist() for _, o, _ in loader] == [[100, 101], [102]]
+
+
+def test_bench_numa_pinning_is_harmless_without_nvml():
+    """`bench.pin_to_gpu_numa`: a no-op for one rank, and on a machine without NVML (this container) it reports the
+    failure and leaves the process affinity as it was."""
+    import os
+
+    import bench
+
+    before = os.sched_getaffinity(0)
+    assert bench.pin_to_gpu_numa(0, 1) is None
+    got = bench.pin_to_gpu_numa(0, 2)
+    assert got is None or isinstance(got, dict)
+    if isinstance(got, dict) and ("error" in got or got.get("cpus") == 0):
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
