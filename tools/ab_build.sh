@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B of two builds of the library on the same box: bash tools/r02_v.sh variants/libX.so [shape]
+# A/B of two builds of the library on the same box: bash tools/ab_build.sh variants/libX.so [shape]
 var=$1; shape=${2:-proteins}
 for i in 1 2; do for lib in $var ""; do
 BOTGAT_LIB=${lib:+$PWD/$lib} python bench.py --shape $shape --no-cpu-baseline --no-skew --no-e2e --no-parity --steps 10 2>/dev/null | python -c "
