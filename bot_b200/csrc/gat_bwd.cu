@@ -341,7 +341,7 @@ extern "C" int botgat_gat_backward(const botgat_graph* g, const botgat_bwd_args*
   const int64_t ld_gee = a->ld_gee > 0 ? a->ld_gee : a->H;
   BG_REQUIRE(a->gz || ld_gee == a->H, "backward: a padded grad_ee needs the staged path (gz workspace)");
 
-  const bool node_major = drec_node_major(a->H, a->D, g->n_dst);
+  const bool node_major = drec_node_major(a->H, a->D, g->n_dst, g->n_edges, g->n_src);
   BG_REQUIRE(g->n_dst * (int64_t)a->H < (1ll << 31), "backward: n_dst * H must be < 2^31");
   const int drec_hs = node_major ? 1 : (int)g->n_dst, drec_vs = node_major ? a->H : 1;
   if (phases & 1) {

@@ -746,27 +746,41 @@ static bool rowwise_geometry(int heads, int D, int* gsh, int* vpl) {
   return true;
 }
 
-// The all-heads-per-row kernels pay when even one column part of one head's slab cannot stay in L2 (the head-major
-// order then has nothing to offer).  BOTGAT_ROWWISE=0 / 1 forces the choice (tests, sweeps); BOTGAT_ROWWISE_MB moves
-// the slab size (per column part, MB) from which they are used.
-static bool rowwise_wanted(int D, int64_t n_rows_table, bool backward = false) {
+// When the all-heads-per-row kernels are used (swept on B200 with tools/rowwise_crossover.sh, profiles/r02_sweeps.md):
+//   * never while a head's slab (one column part of it, forward) fits the L2 budget of the head-major order
+//     (BOTGAT_SLAB_MB, 64 MB): proteins / Reddit shapes stay head-major, whatever the degree;
+//   * beyond that, always for low-degree graphs (< 96 neighbours per row: 1.6 - 2x at 25 and 60 neighbours per row from a
+//     69 MB slab upwards — the head-major order pays the row's dependent load chain once per head and part);
+//   * for long rows only once the slab is well past the L2: forward from 96 MB (still 1.25x at 240 neighbours per row
+//     and a 137 MB slab), backward src pass from 256 MB (at 137 MB and >= 120 neighbours per row the TMA src pass wins).
+// BOTGAT_ROWWISE[_FWD|_BWD]=0 / 1 forces the choice (tests, sweeps); BOTGAT_ROWWISE_MB replaces both "always" sizes.
+static bool rowwise_wanted(int D, int64_t n_rows_table, int64_t n_edges, int64_t n_csr_rows, bool backward) {
   const char* s = getenv(backward ? "BOTGAT_ROWWISE_BWD" : "BOTGAT_ROWWISE_FWD");  // read per call: the tests run every variant in one process
   if (!(s && *s)) s = getenv("BOTGAT_ROWWISE");
   if (s && *s) return *s != '0';
   const char* mb = getenv("BOTGAT_ROWWISE_MB");
-  const int64_t thr = ((mb && *mb) ? atoll(mb) : 256) << 20;
-  const int max_parts = D / 64 > 0 ? D / 64 : 1;  // choose_tiling keeps column parts >= 16 vectors wide
-  return n_rows_table * (int64_t)D * 4 / max_parts > thr;
+  const char* sb = getenv("BOTGAT_SLAB_MB");
+  const int64_t always = ((mb && *mb) ? atoll(mb) : (backward ? 256 : 96)) << 20;
+  int64_t resident = ((sb && *sb) ? atoll(sb) : 64) << 20;
+  if (resident > always) resident = always;
+  // the forward may split a head into column parts of >= 16 vectors (choose_tiling); the src pass gathers whole heads
+  const int max_parts = (!backward && D / 64 > 0) ? D / 64 : 1;
+  const int64_t part_bytes = n_rows_table * (int64_t)D * 4 / max_parts;
+  if (part_bytes <= resident) return false;
+  // (rows of a handful of out-edges — the per-rank out-CSR of an 8-way partitioned products graph has 3 — are not what
+  // the one-warp-per-row src pass was swept on: they keep the group-per-row kernel unless the table is huge)
+  const bool low_degree = n_edges < 96 * n_csr_rows && (!backward || n_edges >= 8 * n_csr_rows);
+  return low_degree || part_bytes > always;
 }
 
-bool drec_node_major(int H, int D, int64_t n_dst) {
+bool drec_node_major(int H, int D, int64_t n_dst, int64_t n_edges, int64_t n_src) {
   int gsh, vpl;
-  return rowwise_wanted(D, n_dst, true) && rowwise_geometry(H, D, &gsh, &vpl);
+  return rowwise_wanted(D, n_dst, n_edges, n_src, true) && rowwise_geometry(H, D, &gsh, &vpl);
 }
 
 int launch_fwd_rowwise(const FwdParams& p, const Tiling& t, cudaStream_t st) {
   int gsh, vpl;
-  if (t.vw != 4 || p.ee || p.keep || p.amul_e || !rowwise_wanted(p.D, p.n_src_table) || !rowwise_geometry(p.h_count, p.D, &gsh, &vpl))
+  if (t.vw != 4 || p.ee || p.keep || p.amul_e || !rowwise_wanted(p.D, p.n_src_table, p.n_edges, p.n_rows, false) || !rowwise_geometry(p.h_count, p.D, &gsh, &vpl))
     return 1;
   const int64_t nblocks = ((int64_t)p.n_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
   if (nblocks <= 0 || nblocks >= (1ll << 31)) return 1;
@@ -786,7 +800,7 @@ int launch_fwd_rowwise(const FwdParams& p, const Tiling& t, cudaStream_t st) {
 
 int launch_src_rowwise(const BwdParams& p, const Tiling& t, cudaStream_t st) {
   int gsh, vpl;
-  if (t.vw != 4 || p.ee || p.keep || p.amul_e || p.gz_e || !rowwise_wanted(p.D, p.n_dst, true) || !rowwise_geometry(p.h_count, p.D, &gsh, &vpl))
+  if (t.vw != 4 || p.ee || p.keep || p.amul_e || p.gz_e || !rowwise_wanted(p.D, p.n_dst, p.n_edges, p.n_rows, true) || !rowwise_geometry(p.h_count, p.D, &gsh, &vpl))
     return 1;
   const int64_t nblocks = ((int64_t)p.n_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
   if (nblocks <= 0 || nblocks >= (1ll << 31) || p.n_items <= 0) return 1;

@@ -116,7 +116,7 @@ int launch_src_tma(const BwdParams& p, const Tiling& t, cudaStream_t st);
 // same return convention as launch_src_tma
 // layout of the per-destination records: a function of the shape alone, so that the node phase (writer) and every src
 // kernel (readers) agree even when the phases are launched by separate calls
-bool drec_node_major(int H, int D, int64_t n_dst);
+bool drec_node_major(int H, int D, int64_t n_dst, int64_t n_edges, int64_t n_src);
 int launch_fwd_rowwise(const FwdParams& p, const Tiling& t, cudaStream_t st);
 int launch_src_rowwise(const BwdParams& p, const Tiling& t, cudaStream_t st);
 int segment_length();

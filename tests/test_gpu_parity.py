@@ -116,6 +116,7 @@ def test_column_parts_forward(cuda, monkeypatch):
     c = make_case(3000, 3000, 20000, 2, 128, ee=True, seed=5)
     ref, _ = oracle_run(c)
     monkeypatch.setenv("BOTGAT_SLAB_MB", "1")
+    monkeypatch.setenv("BOTGAT_ROWWISE", "0")   # the budget also steers the family choice; this test is about column parts
     out, _, _ = engine_run(c, cuda)
     assert rel_err(out, ref) <= FWD_TOL
 
