@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, rw_fwd_blocks(VPL)) gat_f
   constexpr int G = 1 << GSH;     // lanes per head
   constexpr int HG = 32 >> GSH;   // head groups per warp (>= heads of this launch)
   constexpr int U = rw_in_flight(VPL);
-  __shared__ float wsm_all[kWarpsPerBlock][32 * HG];
+  __shared__ __align__(16) float wsm_all[kWarpsPerBlock][32 * HG];  // float4 stores
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x * kWarpsPerBlock + warp;
   if (item >= p.n_items) return;
@@ -265,8 +265,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, rw_bwd_blocks(VPL)) gat_b
   constexpr int HG = 32 >> GSH;
   constexpr int U = rw_in_flight_bwd(VPL) <= G ? rw_in_flight_bwd(VPL) : G;  // the packed dot reduction needs U <= G
   constexpr int LPU = G / U;                                                  // lanes of a group per ring slot after it
-  __shared__ float wsm_all[kWarpsPerBlock][32 * HG];
-  __shared__ float dsm_all[kWarpsPerBlock][32 * HG];
+  __shared__ __align__(16) float wsm_all[kWarpsPerBlock][32 * HG];  // float4 stores
+  __shared__ __align__(16) float dsm_all[kWarpsPerBlock][32 * HG];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x * kWarpsPerBlock + warp;
   if (item >= p.n_items) return;
